@@ -1,0 +1,137 @@
+/*
+ * kserve_b200 — C ABI of the B200-native LLM predict path.
+ *
+ * This is the drop-in boundary for the reference's HF generative runtime: every entry point below
+ * replaces one call the reference makes into its third-party compute backend (transformers/torch) or,
+ * for the batcher, the body of one Go function.  Plain pointers and sizes only; no torch types.
+ * All functions return 0 on success, non-zero on failure; b200_last_error() returns the message for the
+ * calling thread.  One engine handle per GPU; calls on one handle must be serialised by the caller
+ * (the reference serialises them too: generative_model.py:341-354 single worker thread).
+ *
+ * Reference citations are relative to /root/reference.
+ */
+#ifndef KSERVE_B200_H_
+#define KSERVE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_engine b200_engine_t;
+
+/* Model / runtime configuration. Mirrors the fields of the HF config the reference reads in
+ * python/huggingfaceserver/huggingfaceserver/__main__.py:242-246 plus the serving limits of
+ * generative_model.py:203-271 (max_length) and the TP layout of SURVEY.md §8e. */
+typedef struct b200_model_config {
+  int32_t vocab_size;          /* rows of embed_tokens / lm_head (after any [PAD] resize, :256-265) */
+  int32_t hidden_size;
+  int32_t intermediate_size;
+  int32_t num_layers;
+  int32_t num_heads;
+  int32_t num_kv_heads;
+  int32_t head_dim;            /* must be 128 */
+  int32_t max_position;        /* rope table length */
+  float rms_eps;
+  float rope_theta;
+  int32_t max_batch;           /* <= 64 sequences decoded together */
+  int32_t max_seq_len;         /* prompt + generated tokens per sequence */
+  int32_t max_prefill_tokens;  /* packed prompt tokens per generate() call */
+  int32_t num_kv_pages;        /* 0 = max_batch * ceil(max_seq_len / 64) */
+  int32_t tp_rank;
+  int32_t tp_size;             /* 1, 2, 4 or 8; heads, kv heads and intermediate must divide */
+  int32_t device;              /* CUDA device ordinal */
+} b200_model_config_t;
+
+/* Creates the engine on cfg->device. nccl_unique_id: 128 bytes shared by all ranks (from
+ * b200_nccl_unique_id on rank 0, distributed by the host), or NULL when tp_size == 1. */
+int b200_engine_create(const b200_model_config_t* cfg, const void* nccl_unique_id, b200_engine_t** out);
+int b200_engine_destroy(b200_engine_t* e);
+int b200_nccl_unique_id(void* out128);
+
+/* Weights, by HF state_dict name (what AutoModelForCausalLM.from_pretrained would load,
+ * generative_model.py:249-254).  `data` is the FULL (unsharded) bf16 tensor, row-major, on the host
+ * (on_device=0) or on this engine's GPU (on_device=1); the engine copies the shard of its tp_rank and
+ * fuses q/k/v and gate/up.  b200_engine_finalize_weights fails if a tensor is missing. */
+int b200_engine_set_weight(b200_engine_t* e, const char* hf_name, const void* data, int on_device,
+                           int ndim, const int64_t* shape);
+int b200_engine_finalize_weights(b200_engine_t* e);
+/* Optional: bf16 cos/sin tables [max_position][64] computed by the host exactly as
+ * LlamaRotaryEmbedding.forward does (fp32 inv_freq * position -> cos/sin -> bf16).  Without this call the
+ * engine computes the tables itself from rope_theta. */
+int b200_engine_set_rope_table(b200_engine_t* e, const void* cos_bf16, const void* sin_bf16, int32_t rows);
+
+/* Generation parameters == what the reference puts into GenerationConfig + StoppingCriteria
+ * (generative_model.py:388-402, 576-593).  Greedy only this round (do_sample is never set there). */
+typedef struct b200_gen_params {
+  int32_t max_new_tokens;
+  int64_t pad_token_id;          /* finished rows are padded with it (transformers utils.py:2796-2797) */
+  const int64_t* eos_token_ids;  /* may be NULL */
+  int32_t num_eos;
+  const int64_t* stop_tokens;    /* flattened stop sequences (token ids) */
+  const int32_t* stop_offsets;   /* [num_stop + 1] offsets into stop_tokens */
+  int32_t num_stop;
+  const int64_t* forced_tokens;  /* testing: [B][max_new_tokens] tokens to append instead of argmax, or NULL */
+} b200_gen_params_t;
+
+/* Per-step callback for streaming (TextIteratorStreamer in the reference, generative_model.py:307-322):
+ * called on the calling thread after each step with the B new tokens. Return non-zero to abort. */
+typedef int (*b200_token_callback)(void* user, int32_t step, const int64_t* tokens, int32_t batch);
+
+/* Replaces `self._model.generate(**kwargs)` (generative_model.py:314,328).
+ *   input_ids      host int64 [B][S] (left padded when attention_mask has leading zeros)
+ *   attention_mask host int64 [B][S] or NULL (== all ones); must be left-contiguous padding
+ *   out_ids        host int64 [B][S + max_new_tokens]; rows are the prompt followed by generated tokens
+ *   out_len        S + number of generated tokens (same for every row, as in the reference)
+ *   stop_triggered 1 iff a stop sequence ended generation (finish_reason "stop", :621-627)
+ *   logits_bf16    NULL, or host uint16 [max_new_tokens][B][vocab_size] receiving each step's bf16 logits */
+int b200_generate(b200_engine_t* e, const int64_t* input_ids, const int64_t* attention_mask, int32_t B,
+                  int32_t S, const b200_gen_params_t* params, int64_t* out_ids, int32_t* out_len,
+                  int32_t* stop_triggered, uint16_t* logits_bf16, b200_token_callback cb, void* user);
+
+/* Timing of the last b200_generate on this engine, measured with CUDA events on the engine stream. */
+typedef struct b200_timing {
+  float prefill_ms;       /* H2D of the prompt .. first token selected */
+  float decode_ms;        /* all decode steps */
+  int32_t decode_steps;
+  int32_t kernel_launches;/* kernels of this library launched by the call (graph nodes included) */
+} b200_timing_t;
+int b200_engine_last_timing(b200_engine_t* e, b200_timing_t* out);
+
+/* Device-resident variant for benchmarking the kernels alone: prompt already staged with
+ * b200_stage_prompt (no H2D/D2H inside), runs prefill + `steps` decode steps, no result copy. */
+int b200_stage_prompt(b200_engine_t* e, const int64_t* input_ids, const int64_t* attention_mask, int32_t B,
+                      int32_t S, const b200_gen_params_t* params);
+int b200_run_staged(b200_engine_t* e, int32_t do_prefill, int32_t decode_steps);
+int b200_fetch_staged(b200_engine_t* e, int64_t* out_ids, int32_t* out_len, int32_t* stop_triggered);
+
+/* ---- single kernels on caller-provided device pointers (unit tests / micro-benchmarks) ------------- */
+/* D = A[M,K] * B[N,K]^T, bf16, fp32 accumulate. epi: 0 store, 1 store+residual, 2 swiglu (B rows
+ * interleaved 16 gate/16 up), 3 transposed store, 4 transposed swiglu (A rows interleaved),
+ * 5 transposed fp32 split-K partials.  block_n: 256 for epi 0-2, 16/32/64 for epi 3-5. */
+int b200_op_gemm(const void* A, const void* B, void* out, const void* residual, int M, int N, int K, int epi,
+                 int block_n, int splits, int64_t ldo, void* stream);
+int b200_op_rmsnorm(void* x, const void* w, void* xn, int rows, int H, float eps, const float* partial,
+                    int splits, const void* y, void* stream);
+int b200_op_attn_prefill(const void* q, int64_t ldq, void* out, int64_t ldo, const void* kcache,
+                         const void* vcache, const int32_t* page_table, int max_pages,
+                         const int32_t* cu_seqlens, const int32_t* seq_slot, int B, int max_len, int nh, int nkv,
+                         void* stream);
+int b200_op_attn_decode(const void* q, int64_t ldq, void* out, int64_t ldo, const void* kcache,
+                        const void* vcache, const int32_t* page_table, int max_pages, const int32_t* seq_slot,
+                        const int32_t* tok_pos, int B, int nh, int nkv, int splits, float* part_o, float* part_ml,
+                        void* stream);
+int b200_op_rope_kv(const void* qkv, int64_t ld, void* q_out, int64_t ldq, void* kcache, void* vcache,
+                    const int32_t* page_table, int max_pages, const int32_t* tok_seq, const int32_t* tok_pos,
+                    const void* cos_tab, const void* sin_tab, int T, int nh, int nkv, void* stream);
+int b200_op_argmax(const void* logits, int64_t ld, int B, int V, float* out_val, int32_t* out_idx, void* stream);
+
+const char* b200_last_error(void);
+const char* b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KSERVE_B200_H_ */

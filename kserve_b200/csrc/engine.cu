@@ -1,0 +1,919 @@
+// The generation engine behind the C ABI in include/kserve_b200.h.
+//
+// Replaces what the reference delegates to `transformers` at
+// python/huggingfaceserver/huggingfaceserver/generative_model.py:328 (`self._model.generate(**kwargs)`):
+// prefill over the packed (un-padded) prompt tokens, then a CUDA-graph-captured decode step per token,
+// with sampling (greedy), EOS / stop-sequence / max-length checks kept on the device.
+#include <dlfcn.h>
+#include <math.h>
+
+#include <algorithm>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/kserve_b200.h"
+#include "launch.cuh"
+
+namespace b200 {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+// ---------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (only needed when tp_size > 1)
+// ---------------------------------------------------------------------------------------------------
+struct Nccl {
+  typedef struct { char internal[128]; } UniqueId;
+  typedef void* Comm;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(Comm) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, Comm, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  static constexpr int kBf16 = 9, kFloat = 7, kInt32 = 2, kSum = 0;
+  static Nccl& get() {
+    static Nccl n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+      if (!h) return;
+      n.GetUniqueId = (decltype(n.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      n.CommInitRank = (decltype(n.CommInitRank))dlsym(h, "ncclCommInitRank");
+      n.CommDestroy = (decltype(n.CommDestroy))dlsym(h, "ncclCommDestroy");
+      n.AllReduce = (decltype(n.AllReduce))dlsym(h, "ncclAllReduce");
+      n.AllGather = (decltype(n.AllGather))dlsym(h, "ncclAllGather");
+      n.GetErrorString = (decltype(n.GetErrorString))dlsym(h, "ncclGetErrorString");
+      n.ok = n.GetUniqueId && n.CommInitRank && n.AllReduce && n.AllGather;
+    });
+    return n;
+  }
+};
+
+#define B200_NCCL_OK(expr)                                                                  \
+  do {                                                                                      \
+    int _r = (expr);                                                                        \
+    if (_r != 0) {                                                                          \
+      Nccl& _n = Nccl::get();                                                               \
+      set_last_error(std::string(#expr) + " failed: " +                                     \
+                     (_n.GetErrorString ? _n.GetErrorString(_r) : std::to_string(_r)));     \
+      return -4;                                                                            \
+    }                                                                                       \
+  } while (0)
+
+template <class T>
+static int dmalloc(T** p, size_t n) {
+  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return 0;
+}
+
+struct LayerW {
+  bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr, *ln1 = nullptr, *ln2 = nullptr;
+};
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_engine {
+  b200_model_config_t cfg;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  // per-rank dims
+  int H, nh, nkv, G, I, V, Vl, v0, qkv_cols, L;
+  // weights
+  bf16 *embed = nullptr, *lm_head = nullptr, *final_norm = nullptr;
+  std::vector<LayerW> layers;
+  std::unordered_map<std::string, int> seen;
+  bool finalized = false;
+  bf16 *cos_tab = nullptr, *sin_tab = nullptr;
+  // KV cache
+  bf16 *kcache = nullptr, *vcache = nullptr;
+  long long layer_stride = 0;  // elements per layer in each cache
+  int num_pages = 0, max_pages = 0;
+  int32_t* d_page_table = nullptr;
+  std::vector<int32_t> h_page_table;
+  // activations
+  int cap_T = 0;  // rows of the token-major buffers
+  bf16 *x = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr, *ybuf = nullptr, *xl = nullptr,
+       *qdec = nullptr, *logits = nullptr;
+  float* ws = nullptr;
+  size_t ws_elems = 0;
+  float *part_o = nullptr, *part_ml = nullptr;
+  float* cand_val = nullptr;
+  int32_t* cand_idx = nullptr;
+  float* cand_val_all = nullptr;
+  int32_t* cand_idx_all = nullptr;
+  // token bookkeeping (device)
+  int32_t *d_tok = nullptr, *d_tok_seq = nullptr, *d_tok_pos = nullptr, *d_cu = nullptr, *d_seq_slot = nullptr,
+          *d_last_rows = nullptr, *d_cur_len = nullptr, *d_next_tok = nullptr, *d_dec_pos = nullptr,
+          *d_finished = nullptr, *d_out_tokens = nullptr, *d_forced = nullptr, *d_eos = nullptr,
+          *d_stop_tok = nullptr, *d_stop_off = nullptr;
+  StepState* d_state = nullptr;
+  int out_ld = 0;
+  // pinned staging
+  int32_t* h_stage = nullptr;
+  size_t h_stage_elems = 0;
+  StepState* h_state = nullptr;
+  int32_t* h_out_tokens = nullptr;
+  // staged request
+  struct Staged {
+    int B = 0, S = 0, T = 0, max_len = 0, max_new = 0;
+    std::vector<int> lens;
+    std::vector<int64_t> input;  // [B][S] copy of the prompt (with pads) for output assembly
+    int32_t pad = 0;
+    int num_eos = 0, num_stop = 0;
+    bool forced = false;
+    bool prefilled = false;
+  } st;
+  // graphs per batch size
+  std::unordered_map<int, cudaGraphExec_t> graphs;
+  std::unordered_map<int, int> graph_nodes;
+  TmapCache tmaps;
+  // comm
+  Nccl::Comm comm = nullptr;
+  b200_timing_t timing{};
+  int launches = 0;
+};
+
+namespace b200 {
+
+static int pick_block_n(int B) { return B <= 16 ? 16 : (B <= 32 ? 32 : 64); }
+
+static int pick_splits(const b200_engine* e, int n_out, int K) {
+  const int m_tiles = (n_out + kGemmBlockM - 1) / kGemmBlockM;
+  int s = e->num_sms / m_tiles;
+  s = std::max(1, std::min(s, 16));
+  return effective_splits(K, s);
+}
+
+static int allreduce_bf16(b200_engine* e, bf16* buf, size_t count) {
+  if (e->cfg.tp_size == 1) return 0;
+  Nccl& n = Nccl::get();
+  B200_NCCL_OK(n.AllReduce(buf, buf, count, Nccl::kBf16, Nccl::kSum, e->comm, e->stream));
+  return 0;
+}
+
+// ---- one transformer stack pass over T token rows --------------------------------------------------
+// decode == true : T == B rows, swap-AB GEMMs (+ split-K), flash-decoding attention
+// decode == false: packed prompt tokens, row-major GEMMs, causal flash attention
+static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode) {
+  cudaStream_t s = e->stream;
+  const int H = e->H, bn = pick_block_n(B);
+  const float eps = e->cfg.rms_eps;
+  const float scale_log2 = (1.0f / sqrtf((float)kHeadDim)) * 1.4426950408889634f;
+  const bool tp = e->cfg.tp_size > 1;
+  int rc;
+  embed_gather_kernel<<<T, 128, 0, s>>>(decode ? e->d_next_tok : e->d_tok, e->embed, e->x, H, e->V);
+  B200_CUDA_OK(cudaGetLastError());
+  e->launches++;
+  if ((rc = launch_rmsnorm(0, e->x, e->layers[0].ln1, e->xn, T, H, eps, nullptr, 0, 0, 0, nullptr, s))) return rc;
+  e->launches++;
+  for (int l = 0; l < e->L; ++l) {
+    const LayerW& w = e->layers[l];
+    bf16* kc = e->kcache + (long long)l * e->layer_stride;
+    bf16* vc = e->vcache + (long long)l * e->layer_stride;
+    // ---- QKV projection
+    RopeKvParams rp{};
+    rp.ld = e->qkv_cols;
+    if (decode) {
+      const int sp = pick_splits(e, e->qkv_cols, H);
+      GemmArgs a{w.wqkv, e->qkv_cols, e->xn, e->cap_T, e->qkv_cols, B, H, sp > 1 ? EPI_T_PARTIAL : EPI_T_STORE, bn, sp,
+                 sp > 1 ? (void*)e->ws : (void*)e->qkv, nullptr, e->qkv_cols, (long long)B * e->qkv_cols, 0, true};
+      if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+      if (sp > 1) { rp.partial = e->ws; rp.splits = sp; rp.split_stride = (long long)B * e->qkv_cols; rp.ld_partial = e->qkv_cols; }
+      rp.qkv = e->qkv;
+      rp.q_out = e->qdec; rp.ldq = e->nh * kHeadDim;
+      rp.tok_seq = e->d_seq_slot; rp.tok_pos = e->d_dec_pos;
+    } else {
+      GemmArgs a{e->xn, e->cap_T, w.wqkv, e->qkv_cols, T, e->qkv_cols, H, EPI_STORE, 256, 1,
+                 e->qkv, nullptr, e->qkv_cols, 0, 0, false};
+      if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+      rp.qkv = e->qkv;
+      rp.q_out = e->qkv; rp.ldq = e->qkv_cols;  // in place
+      rp.tok_seq = e->d_tok_seq; rp.tok_pos = e->d_tok_pos;
+    }
+    rp.kcache = kc; rp.vcache = vc; rp.page_table = e->d_page_table; rp.max_pages = e->max_pages;
+    rp.cos_tab = e->cos_tab; rp.sin_tab = e->sin_tab; rp.nh = e->nh; rp.nkv = e->nkv;
+    rope_kv_kernel<<<T, 256, 0, s>>>(rp);
+    B200_CUDA_OK(cudaGetLastError());
+    e->launches += 2;
+    // ---- attention
+    if (decode) {
+      AttnDecodeParams ap{};
+      ap.q = e->qdec; ap.ldq = e->nh * kHeadDim; ap.out = e->attn; ap.ldo = e->nh * kHeadDim;
+      ap.kcache = kc; ap.vcache = vc; ap.page_table = e->d_page_table; ap.max_pages = e->max_pages;
+      ap.seq_slot = e->d_seq_slot; ap.tok_pos = e->d_dec_pos; ap.nh = e->nh; ap.nkv = e->nkv; ap.G = e->G;
+      int splits = (2 * e->num_sms + B * e->nkv - 1) / (B * e->nkv);
+      ap.splits = std::max(1, std::min(splits, 8));
+      ap.part_o = e->part_o; ap.part_ml = e->part_ml; ap.scale_log2 = scale_log2;
+      if ((rc = launch_attn_decode(ap, B, s))) return rc;
+      e->launches += ap.splits > 1 ? 2 : 1;
+    } else {
+      AttnPrefillParams ap{};
+      ap.q = e->qkv; ap.ldq = e->qkv_cols; ap.out = e->attn; ap.ldo = e->nh * kHeadDim;
+      ap.kcache = kc; ap.vcache = vc; ap.page_table = e->d_page_table; ap.max_pages = e->max_pages;
+      ap.cu_seqlens = e->d_cu; ap.seq_slot = e->d_seq_slot; ap.nh = e->nh; ap.nkv = e->nkv; ap.scale_log2 = scale_log2;
+      if ((rc = launch_attn_prefill(ap, B, max_len, s))) return rc;
+      e->launches++;
+    }
+    // ---- row-parallel projections (o_proj, down_proj) followed by residual add + next RMSNorm
+    auto row_parallel = [&](const bf16* act, int K, const bf16* wmat, const bf16* next_norm) -> int {
+      int rc2;
+      if (decode) {
+        const int sp = pick_splits(e, H, K);
+        if (sp > 1) {
+          GemmArgs a{wmat, H, act, e->cap_T, H, B, K, EPI_T_PARTIAL, bn, sp, e->ws, nullptr, H, (long long)B * H, 0, true};
+          if ((rc2 = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc2;
+          e->launches++;
+          if (!tp) {
+            if ((rc2 = launch_rmsnorm(1, e->x, next_norm, e->xn, T, H, eps, e->ws, sp, (long long)B * H, H, nullptr, s))) return rc2;
+            e->launches++;
+            return 0;
+          }
+          reduce_partials_kernel<<<T, 256, 0, s>>>(e->ws, sp, (long long)B * H, H, e->ybuf, H);
+          B200_CUDA_OK(cudaGetLastError());
+          e->launches++;
+        } else {
+          GemmArgs a{wmat, H, act, e->cap_T, H, B, K, EPI_T_STORE, bn, 1, e->ybuf, nullptr, H, 0, 0, true};
+          if ((rc2 = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc2;
+          e->launches++;
+        }
+      } else {
+        if (!tp) {
+          GemmArgs a{act, e->cap_T, wmat, H, T, H, K, EPI_STORE_RES, 256, 1, e->x, e->x, H, 0, 0, false};
+          if ((rc2 = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc2;
+          if ((rc2 = launch_rmsnorm(0, e->x, next_norm, e->xn, T, H, eps, nullptr, 0, 0, 0, nullptr, s))) return rc2;
+          e->launches += 2;
+          return 0;
+        }
+        GemmArgs a{act, e->cap_T, wmat, H, T, H, K, EPI_STORE, 256, 1, e->ybuf, nullptr, H, 0, 0, false};
+        if ((rc2 = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc2;
+        e->launches++;
+      }
+      if ((rc2 = allreduce_bf16(e, e->ybuf, (size_t)T * H))) return rc2;
+      if ((rc2 = launch_rmsnorm(2, e->x, next_norm, e->xn, T, H, eps, nullptr, 0, 0, 0, e->ybuf, s))) return rc2;
+      e->launches++;
+      return 0;
+    };
+    if ((rc = row_parallel(e->attn, e->nh * kHeadDim, w.wo, w.ln2))) return rc;
+    // ---- gate/up projection with the SwiGLU fused into the epilogue
+    if (decode) {
+      GemmArgs a{w.wgu, 2 * e->I, e->xn, e->cap_T, 2 * e->I, B, H, EPI_T_SWIGLU, bn, 1, e->hbuf, nullptr, e->I, 0, e->I, true};
+      if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+    } else {
+      GemmArgs a{e->xn, e->cap_T, w.wgu, 2 * e->I, T, 2 * e->I, H, EPI_SWIGLU, 256, 1, e->hbuf, nullptr, e->I, 0, e->I, false};
+      if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+    }
+    e->launches++;
+    const bf16* next_norm = (l + 1 < e->L) ? e->layers[l + 1].ln1 : e->final_norm;
+    if ((rc = row_parallel(e->hbuf, e->I, w.wdown, next_norm))) return rc;
+  }
+  return 0;
+}
+
+// LM head on `rows` (B x H, already final-normed) -> logits -> per-rank argmax candidates -> step update
+static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int B) {
+  cudaStream_t s = e->stream;
+  int rc;
+  GemmArgs a{e->lm_head, e->Vl, rows_xn, rows_cap, e->Vl, B, e->H, EPI_T_STORE, pick_block_n(B), 1,
+             e->logits, nullptr, e->Vl, 0, 0, true};
+  if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+  argmax_kernel<<<B, 1024, 0, s>>>(e->logits, e->Vl, e->Vl, e->v0, e->cand_val, e->cand_idx);
+  B200_CUDA_OK(cudaGetLastError());
+  e->launches += 2;
+  const float* cv = e->cand_val;
+  const int32_t* ci = e->cand_idx;
+  int ranks = 1;
+  if (e->cfg.tp_size > 1) {
+    Nccl& n = Nccl::get();
+    B200_NCCL_OK(n.AllGather(e->cand_val, e->cand_val_all, B, Nccl::kFloat, e->comm, s));
+    B200_NCCL_OK(n.AllGather(e->cand_idx, e->cand_idx_all, B, Nccl::kInt32, e->comm, s));
+    cv = e->cand_val_all; ci = e->cand_idx_all; ranks = e->cfg.tp_size;
+  }
+  StepParams sp{};
+  sp.cand_val = cv; sp.cand_idx = ci; sp.ranks = ranks; sp.B = B;
+  sp.forced = e->st.forced ? e->d_forced : nullptr; sp.forced_ld = e->out_ld;
+  sp.out_tokens = e->d_out_tokens; sp.out_ld = e->out_ld;
+  sp.next_tok = e->d_next_tok; sp.cur_len = e->d_cur_len; sp.tok_pos = e->d_dec_pos; sp.finished = e->d_finished;
+  sp.eos = e->d_eos; sp.num_eos = e->st.num_eos; sp.pad_token = e->st.pad;
+  sp.stop_tok = e->d_stop_tok; sp.stop_off = e->d_stop_off; sp.num_stop = e->st.num_stop;
+  sp.st = e->d_state;
+  step_update_kernel<<<1, 128, 0, s>>>(sp);
+  B200_CUDA_OK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
+static int prefill(b200_engine* e) {
+  auto& st = e->st;
+  int rc;
+  if ((rc = forward_layers(e, st.T, st.B, st.max_len, false))) return rc;
+  gather_rows_kernel<<<st.B, 128, 0, e->stream>>>(e->xn, e->d_last_rows, e->xl, e->H);
+  B200_CUDA_OK(cudaGetLastError());
+  e->launches++;
+  return head_and_step(e, e->xl, e->cfg.max_batch, st.B);
+}
+
+static int decode_step_enqueue(b200_engine* e) {
+  int rc;
+  if ((rc = forward_layers(e, e->st.B, e->st.B, 0, true))) return rc;
+  return head_and_step(e, e->xn, e->cap_T, e->st.B);
+}
+
+// Decode step through a CUDA graph captured once per (batch size, forced, stop/eos counts).
+static int decode_step(b200_engine* e, bool use_graph) {
+  if (!use_graph) return decode_step_enqueue(e);
+  const int key = e->st.B | (e->st.forced ? 1 << 8 : 0) | (e->st.num_eos << 9) | (e->st.num_stop << 14);
+  auto it = e->graphs.find(key);
+  if (it == e->graphs.end()) {
+    // one eager step first: creates tensor maps / sets function attributes outside of capture
+    const int before = e->launches;
+    int rc = decode_step_enqueue(e);
+    if (rc) return rc;
+    const int per_step = e->launches - before;
+    B200_CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    rc = decode_step_enqueue(e);
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+    e->launches -= per_step;  // the captured enqueue did not execute
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    B200_CUDA_OK(ce);
+    cudaGraphExec_t ge = nullptr;
+    B200_CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    e->graphs[key] = ge;
+    e->graph_nodes[key] = per_step;
+    return 0;  // the eager step above already advanced the sequence by one token
+  }
+  B200_CUDA_OK(cudaGraphLaunch(it->second, e->stream));
+  e->launches += e->graph_nodes[key];
+  return 0;
+}
+
+static int stage_prompt(b200_engine* e, const int64_t* ids, const int64_t* mask, int B, int S,
+                        const b200_gen_params_t* gp) {
+  B200_REQUIRE(e->finalized, "weights not finalized");
+  B200_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch size out of range");
+  B200_REQUIRE(gp->max_new_tokens >= 1, "max_new_tokens must be >= 1");
+  B200_REQUIRE(S >= 1 && S + gp->max_new_tokens <= e->cfg.max_seq_len, "prompt + max_new_tokens exceeds max_seq_len");
+  B200_REQUIRE(S + gp->max_new_tokens <= e->cfg.max_position, "exceeds rope table");
+  B200_REQUIRE(gp->num_eos <= 16 && gp->num_stop <= 16, "too many eos / stop sequences");
+  auto& st = e->st;
+  st.B = B; st.S = S; st.max_new = gp->max_new_tokens; st.lens.assign(B, 0);
+  st.input.assign(ids, ids + (size_t)B * S);
+  st.pad = (int32_t)gp->pad_token_id; st.num_eos = gp->num_eos; st.num_stop = gp->num_stop;
+  st.forced = gp->forced_tokens != nullptr; st.prefilled = false;
+  int T = 0, max_len = 0;
+  for (int b = 0; b < B; ++b) {
+    int first = 0;
+    if (mask) {
+      while (first < S && mask[(size_t)b * S + first] == 0) ++first;
+      for (int i = first; i < S; ++i)
+        B200_REQUIRE(mask[(size_t)b * S + i] != 0, "attention_mask must be left padding only");
+    }
+    B200_REQUIRE(first < S, "empty sequence");
+    st.lens[b] = S - first;
+    T += st.lens[b];
+    max_len = std::max(max_len, st.lens[b]);
+  }
+  B200_REQUIRE(T <= e->cap_T, "packed prompt tokens exceed max_prefill_tokens");
+  st.T = T; st.max_len = max_len;
+  // page allocation: sequence b owns a contiguous run of pages (fresh allocator per call)
+  const int per_seq = (S + gp->max_new_tokens + kPageTokens - 1) / kPageTokens;
+  B200_REQUIRE(per_seq <= e->max_pages && (long long)per_seq * B <= e->num_pages, "KV page pool too small");
+  std::fill(e->h_page_table.begin(), e->h_page_table.end(), 0);
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < per_seq; ++i) e->h_page_table[(size_t)b * e->max_pages + i] = b * per_seq + i;
+  // pack host staging: tok | tok_seq | tok_pos | cu | seq_slot | last_rows | cur_len | dec_pos | finished
+  int32_t* h = e->h_stage;
+  int32_t *h_tok = h, *h_seq = h + e->cap_T, *h_pos = h + 2 * e->cap_T, *h_misc = h + 3 * e->cap_T;
+  int32_t *h_cu = h_misc, *h_slot = h_cu + 80, *h_last = h_slot + 80, *h_len = h_last + 80, *h_dpos = h_len + 80,
+          *h_fin = h_dpos + 80;
+  int t = 0;
+  for (int b = 0; b < B; ++b) {
+    h_cu[b] = t;
+    const int first = S - st.lens[b];
+    for (int i = 0; i < st.lens[b]; ++i, ++t) {
+      h_tok[t] = (int32_t)ids[(size_t)b * S + first + i];
+      h_seq[t] = b;
+      h_pos[t] = i;
+    }
+    h_slot[b] = b; h_last[b] = t - 1; h_len[b] = st.lens[b]; h_dpos[b] = st.lens[b]; h_fin[b] = 0;
+  }
+  h_cu[B] = t;
+  cudaStream_t s = e->stream;
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_tok, h_tok, T * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_tok_seq, h_seq, T * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_tok_pos, h_pos, T * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_cu, h_cu, (B + 1) * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_seq_slot, h_slot, B * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_last_rows, h_last, B * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_cur_len, h_len, B * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_dec_pos, h_dpos, B * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_finished, h_fin, B * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_page_table, e->h_page_table.data(), e->h_page_table.size() * 4, cudaMemcpyHostToDevice, s));
+  // eos / stop / forced
+  std::vector<int32_t> tmp;
+  if (gp->num_eos) {
+    tmp.assign(gp->num_eos, 0);
+    for (int i = 0; i < gp->num_eos; ++i) tmp[i] = (int32_t)gp->eos_token_ids[i];
+    B200_CUDA_OK(cudaMemcpy(e->d_eos, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+  }
+  if (gp->num_stop) {
+    const int total = gp->stop_offsets[gp->num_stop];
+    B200_REQUIRE(total <= 1024, "stop sequences too long");
+    tmp.assign(total, 0);
+    for (int i = 0; i < total; ++i) tmp[i] = (int32_t)gp->stop_tokens[i];
+    B200_CUDA_OK(cudaMemcpy(e->d_stop_tok, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(e->d_stop_off, gp->stop_offsets, (gp->num_stop + 1) * 4, cudaMemcpyHostToDevice));
+  }
+  if (gp->forced_tokens) {
+    tmp.assign((size_t)B * e->out_ld, 0);
+    for (int b = 0; b < B; ++b)
+      for (int i = 0; i < gp->max_new_tokens; ++i) tmp[(size_t)b * e->out_ld + i] = (int32_t)gp->forced_tokens[(size_t)b * gp->max_new_tokens + i];
+    B200_CUDA_OK(cudaMemcpy(e->d_forced, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+  }
+  StepState init{0, 0, 0, gp->max_new_tokens};
+  *e->h_state = init;
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_state, e->h_state, sizeof(StepState), cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+static int fetch_result(b200_engine* e, int64_t* out_ids, int32_t* out_len, int32_t* stop_triggered) {
+  auto& st = e->st;
+  cudaStream_t s = e->stream;
+  B200_CUDA_OK(cudaMemcpyAsync(e->h_state, e->d_state, sizeof(StepState), cudaMemcpyDeviceToHost, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->h_out_tokens, e->d_out_tokens, (size_t)st.B * e->out_ld * 4, cudaMemcpyDeviceToHost, s));
+  B200_CUDA_OK(cudaStreamSynchronize(s));
+  const int Tn = e->h_state->step;
+  const int W = st.S + st.max_new;
+  for (int b = 0; b < st.B; ++b) {
+    for (int i = 0; i < st.S; ++i) out_ids[(size_t)b * W + i] = st.input[(size_t)b * st.S + i];
+    for (int i = 0; i < st.max_new; ++i)
+      out_ids[(size_t)b * W + st.S + i] = i < Tn ? (int64_t)e->h_out_tokens[(size_t)b * e->out_ld + i] : (int64_t)st.pad;
+  }
+  *out_len = st.S + Tn;
+  if (stop_triggered) *stop_triggered = e->h_state->stop_triggered;
+  return 0;
+}
+
+// shard copy helpers -------------------------------------------------------------------------------
+static int copy_rows(bf16* dst, const bf16* src, long long row0, long long rows, long long cols, bool on_device) {
+  B200_CUDA_OK(cudaMemcpy(dst, src + row0 * cols, (size_t)rows * cols * 2, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  return 0;
+}
+static int copy_cols(bf16* dst, const bf16* src, long long rows, long long src_cols, long long col0, long long cols, bool on_device) {
+  B200_CUDA_OK(cudaMemcpy2D(dst, cols * 2, src + col0, src_cols * 2, cols * 2, rows, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  return 0;
+}
+
+}  // namespace b200
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* b200_last_error(void) { return g_last_error.c_str(); }
+const char* b200_version(void) { return "kserve_b200 0.1 (sm_100a)"; }
+
+int b200_nccl_unique_id(void* out128) {
+  Nccl& n = Nccl::get();
+  B200_REQUIRE(n.ok, "libnccl.so.2 could not be loaded");
+  Nccl::UniqueId id;
+  B200_NCCL_OK(n.GetUniqueId(&id));
+  memcpy(out128, &id, 128);
+  return 0;
+}
+
+int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_engine_t** out) {
+  B200_REQUIRE(c && out, "null argument");
+  B200_REQUIRE(c->head_dim == kHeadDim, "head_dim must be 128");
+  B200_REQUIRE(c->tp_size >= 1 && c->tp_rank >= 0 && c->tp_rank < c->tp_size, "bad tp rank/size");
+  B200_REQUIRE(c->num_heads % c->tp_size == 0 && c->num_kv_heads % c->tp_size == 0, "heads must divide tp_size");
+  B200_REQUIRE(c->intermediate_size % (16 * c->tp_size) == 0, "intermediate_size must be a multiple of 16*tp_size");
+  B200_REQUIRE(c->hidden_size % 64 == 0, "hidden_size must be a multiple of 64");
+  B200_REQUIRE(c->max_batch >= 1 && c->max_batch <= 64, "max_batch must be in [1, 64]");
+  B200_REQUIRE(c->num_heads % c->num_kv_heads == 0 && c->num_heads / c->num_kv_heads <= 8, "GQA group must be <= 8");
+  int ndev = 0;
+  B200_CUDA_OK(cudaGetDeviceCount(&ndev));
+  B200_REQUIRE(c->device >= 0 && c->device < ndev, "no such CUDA device (this library has no CPU fallback)");
+  B200_CUDA_OK(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  B200_CUDA_OK(cudaGetDeviceProperties(&prop, c->device));
+  B200_REQUIRE(prop.major == 10, std::string("kserve_b200 kernels are built for sm_100a only; device is sm_") +
+                                     std::to_string(prop.major) + std::to_string(prop.minor));
+  std::unique_ptr<b200_engine> e(new b200_engine());
+  e->cfg = *c;
+  e->num_sms = prop.multiProcessorCount;
+  const int tp = c->tp_size;
+  e->H = c->hidden_size; e->nh = c->num_heads / tp; e->nkv = c->num_kv_heads / tp; e->G = c->num_heads / c->num_kv_heads;
+  e->I = c->intermediate_size / tp; e->V = c->vocab_size; e->L = c->num_layers;
+  const int vper = (c->vocab_size + tp - 1) / tp;
+  e->v0 = vper * c->tp_rank;
+  e->Vl = std::max(0, std::min(vper, c->vocab_size - e->v0));
+  B200_REQUIRE(e->Vl > 0, "empty vocabulary shard");
+  e->qkv_cols = (e->nh + 2 * e->nkv) * kHeadDim;
+  B200_CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  B200_CUDA_OK(cudaEventCreate(&e->ev0));
+  B200_CUDA_OK(cudaEventCreate(&e->ev1));
+  B200_CUDA_OK(cudaEventCreate(&e->ev2));
+  int rc;
+  const size_t H = e->H;
+  // weights
+  if ((rc = dmalloc(&e->embed, (size_t)e->V * H))) return rc;
+  if ((rc = dmalloc(&e->lm_head, (size_t)e->Vl * H))) return rc;
+  if ((rc = dmalloc(&e->final_norm, H))) return rc;
+  e->layers.resize(e->L);
+  for (auto& w : e->layers) {
+    if ((rc = dmalloc(&w.wqkv, (size_t)e->qkv_cols * H))) return rc;
+    if ((rc = dmalloc(&w.wo, H * e->nh * kHeadDim))) return rc;
+    if ((rc = dmalloc(&w.wgu, (size_t)2 * e->I * H))) return rc;
+    if ((rc = dmalloc(&w.wdown, H * e->I))) return rc;
+    if ((rc = dmalloc(&w.ln1, H))) return rc;
+    if ((rc = dmalloc(&w.ln2, H))) return rc;
+  }
+  // rope tables (engine default: double-precision angles; hosts that need bit parity with
+  // LlamaRotaryEmbedding pass their own via b200_engine_set_rope_table)
+  {
+    const int R = c->max_position;
+    std::vector<bf16> hc((size_t)R * 64), hs((size_t)R * 64);
+    for (int i = 0; i < 64; ++i) {
+      const float inv = 1.0f / powf(c->rope_theta, (float)(2 * i) / 128.0f);
+      for (int pos = 0; pos < R; ++pos) {
+        const float ang = (float)pos * inv;
+        hc[(size_t)pos * 64 + i] = __float2bfloat16_rn(cosf(ang));
+        hs[(size_t)pos * 64 + i] = __float2bfloat16_rn(sinf(ang));
+      }
+    }
+    if ((rc = dmalloc(&e->cos_tab, (size_t)R * 64))) return rc;
+    if ((rc = dmalloc(&e->sin_tab, (size_t)R * 64))) return rc;
+    B200_CUDA_OK(cudaMemcpy(e->cos_tab, hc.data(), hc.size() * 2, cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(e->sin_tab, hs.data(), hs.size() * 2, cudaMemcpyHostToDevice));
+  }
+  // KV cache (zero-filled: masked-out V rows must be finite)
+  e->max_pages = (c->max_seq_len + kPageTokens - 1) / kPageTokens;
+  e->num_pages = c->num_kv_pages > 0 ? c->num_kv_pages : c->max_batch * e->max_pages;
+  e->layer_stride = (long long)e->num_pages * e->nkv * kPageTokens * kHeadDim;
+  if ((rc = dmalloc(&e->kcache, (size_t)e->layer_stride * e->L))) return rc;
+  if ((rc = dmalloc(&e->vcache, (size_t)e->layer_stride * e->L))) return rc;
+  B200_CUDA_OK(cudaMemset(e->kcache, 0, (size_t)e->layer_stride * e->L * 2));
+  B200_CUDA_OK(cudaMemset(e->vcache, 0, (size_t)e->layer_stride * e->L * 2));
+  if ((rc = dmalloc(&e->d_page_table, (size_t)c->max_batch * e->max_pages))) return rc;
+  e->h_page_table.assign((size_t)c->max_batch * e->max_pages, 0);
+  // activations
+  e->cap_T = std::max(c->max_prefill_tokens, 128);
+  const size_t T = e->cap_T;
+  if ((rc = dmalloc(&e->x, T * H))) return rc;
+  if ((rc = dmalloc(&e->xn, T * H))) return rc;
+  if ((rc = dmalloc(&e->qkv, T * e->qkv_cols))) return rc;
+  if ((rc = dmalloc(&e->attn, T * e->nh * kHeadDim))) return rc;
+  if ((rc = dmalloc(&e->hbuf, T * e->I))) return rc;
+  if ((rc = dmalloc(&e->ybuf, T * H))) return rc;
+  if ((rc = dmalloc(&e->xl, (size_t)c->max_batch * H))) return rc;
+  if ((rc = dmalloc(&e->qdec, (size_t)c->max_batch * e->nh * kHeadDim))) return rc;
+  if ((rc = dmalloc(&e->logits, (size_t)c->max_batch * e->Vl))) return rc;
+  B200_CUDA_OK(cudaMemset(e->x, 0, T * H * 2));
+  B200_CUDA_OK(cudaMemset(e->xn, 0, T * H * 2));
+  B200_CUDA_OK(cudaMemset(e->attn, 0, T * e->nh * kHeadDim * 2));
+  B200_CUDA_OK(cudaMemset(e->hbuf, 0, T * e->I * 2));
+  B200_CUDA_OK(cudaMemset(e->xl, 0, (size_t)c->max_batch * H * 2));
+  e->ws_elems = (size_t)16 * c->max_batch * std::max(e->qkv_cols, e->H);
+  if ((rc = dmalloc(&e->ws, e->ws_elems))) return rc;
+  if ((rc = dmalloc(&e->part_o, (size_t)c->max_batch * e->nkv * 8 * e->G * kHeadDim))) return rc;
+  if ((rc = dmalloc(&e->part_ml, (size_t)c->max_batch * e->nkv * 8 * e->G * 2))) return rc;
+  if ((rc = dmalloc(&e->cand_val, (size_t)c->max_batch))) return rc;
+  if ((rc = dmalloc(&e->cand_idx, (size_t)c->max_batch))) return rc;
+  if ((rc = dmalloc(&e->cand_val_all, (size_t)c->max_batch * tp))) return rc;
+  if ((rc = dmalloc(&e->cand_idx_all, (size_t)c->max_batch * tp))) return rc;
+  // bookkeeping
+  e->out_ld = c->max_seq_len;
+  if ((rc = dmalloc(&e->d_tok, T))) return rc;
+  if ((rc = dmalloc(&e->d_tok_seq, T))) return rc;
+  if ((rc = dmalloc(&e->d_tok_pos, T))) return rc;
+  if ((rc = dmalloc(&e->d_cu, 80))) return rc;
+  if ((rc = dmalloc(&e->d_seq_slot, 80))) return rc;
+  if ((rc = dmalloc(&e->d_last_rows, 80))) return rc;
+  if ((rc = dmalloc(&e->d_cur_len, 80))) return rc;
+  if ((rc = dmalloc(&e->d_next_tok, 80))) return rc;
+  if ((rc = dmalloc(&e->d_dec_pos, 80))) return rc;
+  if ((rc = dmalloc(&e->d_finished, 80))) return rc;
+  if ((rc = dmalloc(&e->d_out_tokens, (size_t)c->max_batch * e->out_ld))) return rc;
+  if ((rc = dmalloc(&e->d_forced, (size_t)c->max_batch * e->out_ld))) return rc;
+  if ((rc = dmalloc(&e->d_eos, 16))) return rc;
+  if ((rc = dmalloc(&e->d_stop_tok, 1024))) return rc;
+  if ((rc = dmalloc(&e->d_stop_off, 32))) return rc;
+  if ((rc = dmalloc(&e->d_state, 1))) return rc;
+  e->h_stage_elems = 3 * T + 6 * 80;
+  B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_stage), e->h_stage_elems * 4));
+  B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_state), sizeof(StepState)));
+  B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_out_tokens), (size_t)c->max_batch * e->out_ld * 4));
+  if (tp > 1) {
+    Nccl& n = Nccl::get();
+    B200_REQUIRE(n.ok, "tp_size > 1 needs libnccl.so.2");
+    B200_REQUIRE(nccl_id != nullptr, "tp_size > 1 needs an NCCL unique id");
+    Nccl::UniqueId id;
+    memcpy(&id, nccl_id, 128);
+    B200_NCCL_OK(n.CommInitRank(&e->comm, tp, id, c->tp_rank));
+  }
+  B200_CUDA_OK(cudaDeviceSynchronize());
+  *out = e.release();
+  return 0;
+}
+
+int b200_engine_destroy(b200_engine_t* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  if (e->comm) Nccl::get().CommDestroy(e->comm);
+  void* ptrs[] = {e->embed, e->lm_head, e->final_norm, e->cos_tab, e->sin_tab, e->kcache, e->vcache, e->d_page_table,
+                  e->x, e->xn, e->qkv, e->attn, e->hbuf, e->ybuf, e->xl, e->qdec, e->logits, e->ws, e->part_o, e->part_ml,
+                  e->cand_val, e->cand_idx, e->cand_val_all, e->cand_idx_all, e->d_tok, e->d_tok_seq, e->d_tok_pos, e->d_cu,
+                  e->d_seq_slot, e->d_last_rows, e->d_cur_len, e->d_next_tok, e->d_dec_pos, e->d_finished, e->d_out_tokens,
+                  e->d_forced, e->d_eos, e->d_stop_tok, e->d_stop_off, e->d_state};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& w : e->layers) {
+    void* lp[] = {w.wqkv, w.wo, w.wgu, w.wdown, w.ln1, w.ln2};
+    for (void* p : lp) if (p) cudaFree(p);
+  }
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  if (e->h_state) cudaFreeHost(e->h_state);
+  if (e->h_out_tokens) cudaFreeHost(e->h_out_tokens);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->ev2) cudaEventDestroy(e->ev2);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return 0;
+}
+
+int b200_engine_set_weight(b200_engine_t* e, const char* name, const void* data, int on_device, int ndim,
+                           const int64_t* shape) {
+  B200_REQUIRE(e && name && data && shape, "null argument");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  const std::string n(name);
+  const bf16* src = reinterpret_cast<const bf16*>(data);
+  const bool dev = on_device != 0;
+  const long long H = e->H;
+  const int r = e->cfg.tp_rank, tp = e->cfg.tp_size;
+  auto expect = [&](long long d0, long long d1) -> bool {
+    if (d1 < 0) return ndim == 1 && shape[0] == d0;
+    return ndim == 2 && shape[0] == d0 && shape[1] == d1;
+  };
+  int rc = 0;
+  if (n == "model.embed_tokens.weight") {
+    B200_REQUIRE(expect(e->V, H), "shape mismatch for " + n);
+    rc = copy_rows(e->embed, src, 0, e->V, H, dev);
+  } else if (n == "lm_head.weight") {
+    B200_REQUIRE(expect(e->V, H), "shape mismatch for " + n);
+    rc = copy_rows(e->lm_head, src, e->v0, e->Vl, H, dev);
+  } else if (n == "model.norm.weight") {
+    B200_REQUIRE(expect(H, -1), "shape mismatch for " + n);
+    rc = copy_rows(e->final_norm, src, 0, 1, H, dev);
+  } else if (n.rfind("model.layers.", 0) == 0) {
+    const size_t dot = n.find('.', 13);
+    B200_REQUIRE(dot != std::string::npos, "bad weight name " + n);
+    const int l = atoi(n.substr(13, dot - 13).c_str());
+    B200_REQUIRE(l >= 0 && l < e->L, "layer index out of range in " + n);
+    const std::string rest = n.substr(dot + 1);
+    LayerW& w = e->layers[l];
+    const long long QH = (long long)e->cfg.num_heads * kHeadDim, KH = (long long)e->cfg.num_kv_heads * kHeadDim;
+    const long long ql = (long long)e->nh * kHeadDim, kl = (long long)e->nkv * kHeadDim;
+    const long long If = e->cfg.intermediate_size, Il = e->I;
+    if (rest == "input_layernorm.weight") {
+      B200_REQUIRE(expect(H, -1), "shape mismatch for " + n);
+      rc = copy_rows(w.ln1, src, 0, 1, H, dev);
+    } else if (rest == "post_attention_layernorm.weight") {
+      B200_REQUIRE(expect(H, -1), "shape mismatch for " + n);
+      rc = copy_rows(w.ln2, src, 0, 1, H, dev);
+    } else if (rest == "self_attn.q_proj.weight") {
+      B200_REQUIRE(expect(QH, H), "shape mismatch for " + n);
+      rc = copy_rows(w.wqkv, src, r * ql, ql, H, dev);
+    } else if (rest == "self_attn.k_proj.weight") {
+      B200_REQUIRE(expect(KH, H), "shape mismatch for " + n);
+      rc = copy_rows(w.wqkv + ql * H, src, r * kl, kl, H, dev);
+    } else if (rest == "self_attn.v_proj.weight") {
+      B200_REQUIRE(expect(KH, H), "shape mismatch for " + n);
+      rc = copy_rows(w.wqkv + (ql + kl) * H, src, r * kl, kl, H, dev);
+    } else if (rest == "self_attn.o_proj.weight") {
+      B200_REQUIRE(expect(H, QH), "shape mismatch for " + n);
+      rc = copy_cols(w.wo, src, H, QH, r * ql, ql, dev);
+    } else if (rest == "mlp.gate_proj.weight" || rest == "mlp.up_proj.weight") {
+      B200_REQUIRE(expect(If, H), "shape mismatch for " + n);
+      // interleave in groups of 16 rows: fused rows [32j, 32j+16) = gate[16j..], [32j+16, 32j+32) = up[16j..]
+      bf16* dst = w.wgu + (rest == "mlp.up_proj.weight" ? 16 * H : 0);
+      B200_CUDA_OK(cudaMemcpy2D(dst, 32 * H * 2, src + (long long)r * Il * H, 16 * H * 2, 16 * H * 2, Il / 16,
+                                dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    } else if (rest == "mlp.down_proj.weight") {
+      B200_REQUIRE(expect(H, If), "shape mismatch for " + n);
+      rc = copy_cols(w.wdown, src, H, If, r * Il, Il, dev);
+    } else if (rest == "self_attn.rotary_emb.inv_freq") {
+      return 0;
+    } else {
+      set_last_error("unknown weight " + n);
+      return -5;
+    }
+  } else {
+    set_last_error("unknown weight " + n);
+    return -5;
+  }
+  if (rc) return rc;
+  e->seen[n] = 1;
+  return 0;
+}
+
+int b200_engine_finalize_weights(b200_engine_t* e) {
+  B200_REQUIRE(e, "null engine");
+  const size_t want = 3 + (size_t)e->L * 9;
+  B200_REQUIRE(e->seen.size() == want, "expected " + std::to_string(want) + " weight tensors, got " + std::to_string(e->seen.size()));
+  B200_CUDA_OK(cudaDeviceSynchronize());
+  e->finalized = true;
+  return 0;
+}
+
+int b200_engine_set_rope_table(b200_engine_t* e, const void* cos_bf16, const void* sin_bf16, int32_t rows) {
+  B200_REQUIRE(e && cos_bf16 && sin_bf16, "null argument");
+  B200_REQUIRE(rows == e->cfg.max_position, "rope table must have max_position rows");
+  B200_CUDA_OK(cudaMemcpy(e->cos_tab, cos_bf16, (size_t)rows * 64 * 2, cudaMemcpyHostToDevice));
+  B200_CUDA_OK(cudaMemcpy(e->sin_tab, sin_bf16, (size_t)rows * 64 * 2, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int b200_stage_prompt(b200_engine_t* e, const int64_t* ids, const int64_t* mask, int32_t B, int32_t S,
+                      const b200_gen_params_t* gp) {
+  B200_REQUIRE(e && ids && gp, "null argument");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  int rc = stage_prompt(e, ids, mask, B, S, gp);
+  if (rc) return rc;
+  B200_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int b200_run_staged(b200_engine_t* e, int32_t do_prefill, int32_t decode_steps) {
+  B200_REQUIRE(e, "null engine");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  int rc;
+  if (do_prefill) {
+    // reset the per-request device state so the same staged prompt can be replayed
+    auto& st = e->st;
+    int32_t* h = e->h_stage + 3 * e->cap_T;
+    B200_CUDA_OK(cudaMemcpyAsync(e->d_cur_len, h + 240, st.B * 4, cudaMemcpyHostToDevice, e->stream));
+    B200_CUDA_OK(cudaMemcpyAsync(e->d_dec_pos, h + 320, st.B * 4, cudaMemcpyHostToDevice, e->stream));
+    B200_CUDA_OK(cudaMemcpyAsync(e->d_finished, h + 400, st.B * 4, cudaMemcpyHostToDevice, e->stream));
+    StepState init{0, 0, 0, st.max_new};
+    *e->h_state = init;
+    B200_CUDA_OK(cudaMemcpyAsync(e->d_state, e->h_state, sizeof(StepState), cudaMemcpyHostToDevice, e->stream));
+    if ((rc = prefill(e))) return rc;
+    st.prefilled = true;
+  }
+  B200_REQUIRE(e->st.prefilled, "run_staged: prefill has not run");
+  for (int i = 0; i < decode_steps; ++i)
+    if ((rc = decode_step(e, true))) return rc;
+  return 0;
+}
+
+int b200_fetch_staged(b200_engine_t* e, int64_t* out_ids, int32_t* out_len, int32_t* stop_triggered) {
+  B200_REQUIRE(e && out_ids && out_len, "null argument");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  return fetch_result(e, out_ids, out_len, stop_triggered);
+}
+
+int b200_generate(b200_engine_t* e, const int64_t* ids, const int64_t* mask, int32_t B, int32_t S,
+                  const b200_gen_params_t* gp, int64_t* out_ids, int32_t* out_len, int32_t* stop_triggered,
+                  uint16_t* logits_bf16, b200_token_callback cb, void* user) {
+  B200_REQUIRE(e && ids && gp && out_ids && out_len, "null argument");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = e->stream;
+  e->launches = 0;
+  B200_CUDA_OK(cudaEventRecord(e->ev0, s));
+  int rc = stage_prompt(e, ids, mask, B, S, gp);
+  if (rc) return rc;
+  if ((rc = prefill(e))) return rc;
+  e->st.prefilled = true;
+  B200_CUDA_OK(cudaEventRecord(e->ev1, s));
+  const bool record = logits_bf16 != nullptr;
+  const bool eager = record;             // per-step logits copies -> no graph
+  const size_t lrow = (size_t)e->Vl;     // logits of this rank's vocab shard
+  B200_REQUIRE(!record || e->cfg.tp_size == 1, "logits recording is single-GPU only");
+  std::vector<int64_t> cbuf(B);
+  auto after_step = [&](int step) -> int {
+    if (record)
+      B200_CUDA_OK(cudaMemcpyAsync(logits_bf16 + (size_t)step * B * lrow, e->logits, (size_t)B * lrow * 2, cudaMemcpyDeviceToHost, s));
+    if (cb) {
+      B200_CUDA_OK(cudaMemcpyAsync(e->h_out_tokens, e->d_out_tokens, (size_t)B * e->out_ld * 4, cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaMemcpyAsync(e->h_state, e->d_state, sizeof(StepState), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+      if (e->h_state->step > step) {
+        for (int b = 0; b < B; ++b) cbuf[b] = e->h_out_tokens[(size_t)b * e->out_ld + step];
+        if (cb(user, step, cbuf.data(), B)) return 1;
+      }
+      return e->h_state->done ? 2 : 0;
+    }
+    return 0;
+  };
+  int steps = 0;
+  int ar = after_step(0);
+  if (ar == 0) {
+    for (int i = 1; i < gp->max_new_tokens; ++i) {
+      if ((rc = decode_step(e, !eager))) return rc;
+      ++steps;
+      ar = after_step(i);
+      if (ar) break;
+      if (!cb && (i % 8) == 0) {  // poll the device-side done flag without a per-token sync
+        B200_CUDA_OK(cudaMemcpyAsync(e->h_state, e->d_state, sizeof(StepState), cudaMemcpyDeviceToHost, s));
+        B200_CUDA_OK(cudaStreamSynchronize(s));
+        if (e->h_state->done) break;
+      }
+    }
+  }
+  B200_CUDA_OK(cudaEventRecord(e->ev2, s));
+  if ((rc = fetch_result(e, out_ids, out_len, stop_triggered))) return rc;
+  B200_CUDA_OK(cudaEventElapsedTime(&e->timing.prefill_ms, e->ev0, e->ev1));
+  B200_CUDA_OK(cudaEventElapsedTime(&e->timing.decode_ms, e->ev1, e->ev2));
+  e->timing.decode_steps = steps;
+  e->timing.kernel_launches = e->launches;
+  return ar == 1 ? 1 : 0;
+}
+
+int b200_engine_last_timing(b200_engine_t* e, b200_timing_t* out) {
+  B200_REQUIRE(e && out, "null argument");
+  *out = e->timing;
+  return 0;
+}
+
+// ---- single-kernel entry points ---------------------------------------------------------------------
+static TmapCache g_op_tmaps;
+static int g_op_sms = 0;
+static int op_sms() {
+  if (!g_op_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_op_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_op_sms;
+}
+
+int b200_op_gemm(const void* A, const void* B, void* out, const void* residual, int M, int N, int K, int epi,
+                 int block_n, int splits, int64_t ldo, void* stream) {
+  g_op_tmaps.maps.clear();  // caller buffers may be reused at other shapes
+  const bool t = epi >= EPI_T_STORE;
+  int out_cols = (epi == EPI_SWIGLU) ? N / 2 : (epi == EPI_T_SWIGLU ? M / 2 : 0);
+  GemmArgs a{(const bf16*)A, M, (const bf16*)B, N, M, N, K, epi, block_n, effective_splits(K, splits), out,
+             (const bf16*)residual, ldo, (long long)N * ldo, out_cols, t};
+  return launch_gemm(g_op_tmaps, a, op_sms(), (cudaStream_t)stream);
+}
+
+int b200_op_rmsnorm(void* x, const void* w, void* xn, int rows, int H, float eps, const float* partial, int splits,
+                    const void* y, void* stream) {
+  const int mode = partial ? 1 : (y ? 2 : 0);
+  return launch_rmsnorm(mode, (bf16*)x, (const bf16*)w, (bf16*)xn, rows, H, eps, partial, splits, (long long)rows * H, H,
+                        (const bf16*)y, (cudaStream_t)stream);
+}
+
+int b200_op_attn_prefill(const void* q, int64_t ldq, void* out, int64_t ldo, const void* kcache, const void* vcache,
+                         const int32_t* page_table, int max_pages, const int32_t* cu_seqlens, const int32_t* seq_slot,
+                         int B, int max_len, int nh, int nkv, void* stream) {
+  AttnPrefillParams p{};
+  p.q = (const bf16*)q; p.ldq = ldq; p.out = (bf16*)out; p.ldo = ldo; p.kcache = (const bf16*)kcache; p.vcache = (const bf16*)vcache;
+  p.page_table = page_table; p.max_pages = max_pages; p.cu_seqlens = cu_seqlens; p.seq_slot = seq_slot; p.nh = nh; p.nkv = nkv;
+  p.scale_log2 = (1.0f / sqrtf((float)kHeadDim)) * 1.4426950408889634f;
+  return launch_attn_prefill(p, B, max_len, (cudaStream_t)stream);
+}
+
+int b200_op_attn_decode(const void* q, int64_t ldq, void* out, int64_t ldo, const void* kcache, const void* vcache,
+                        const int32_t* page_table, int max_pages, const int32_t* seq_slot, const int32_t* tok_pos, int B,
+                        int nh, int nkv, int splits, float* part_o, float* part_ml, void* stream) {
+  AttnDecodeParams p{};
+  p.q = (const bf16*)q; p.ldq = ldq; p.out = (bf16*)out; p.ldo = ldo; p.kcache = (const bf16*)kcache; p.vcache = (const bf16*)vcache;
+  p.page_table = page_table; p.max_pages = max_pages; p.seq_slot = seq_slot; p.tok_pos = tok_pos; p.nh = nh; p.nkv = nkv;
+  p.G = nh / nkv; p.splits = splits; p.part_o = part_o; p.part_ml = part_ml;
+  p.scale_log2 = (1.0f / sqrtf((float)kHeadDim)) * 1.4426950408889634f;
+  return launch_attn_decode(p, B, (cudaStream_t)stream);
+}
+
+int b200_op_rope_kv(const void* qkv, int64_t ld, void* q_out, int64_t ldq, void* kcache, void* vcache,
+                    const int32_t* page_table, int max_pages, const int32_t* tok_seq, const int32_t* tok_pos,
+                    const void* cos_tab, const void* sin_tab, int T, int nh, int nkv, void* stream) {
+  RopeKvParams p{};
+  p.qkv = (const bf16*)qkv; p.ld = ld; p.q_out = (bf16*)q_out; p.ldq = ldq; p.kcache = (bf16*)kcache; p.vcache = (bf16*)vcache;
+  p.page_table = page_table; p.max_pages = max_pages; p.tok_seq = tok_seq; p.tok_pos = tok_pos;
+  p.cos_tab = (const bf16*)cos_tab; p.sin_tab = (const bf16*)sin_tab; p.nh = nh; p.nkv = nkv;
+  rope_kv_kernel<<<T, 256, 0, (cudaStream_t)stream>>>(p);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int b200_op_argmax(const void* logits, int64_t ld, int B, int V, float* out_val, int32_t* out_idx, void* stream) {
+  argmax_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, V, 0, out_val, out_idx);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

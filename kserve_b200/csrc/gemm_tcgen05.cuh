@@ -1,0 +1,292 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T  (both K-major).
+//
+//   warp 0   : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1   : MMA issuer    (one thread, tcgen05.mma cta_group::1 kind::f16, fp32 accumulators in TMEM)
+//   warps 2-5: epilogue      (tcgen05.ld -> registers -> fused epilogue -> global), double-buffered TMEM
+//
+// The same kernel serves both phases of the LLM path:
+//   * prefill  : A = activations [T,K], B = weight [N_out,K]           -> row-major epilogues
+//   * decode   : A = weight [N_out,K] (M = N_out), B = activations [batch,K] ("swap-AB": the 128-row MMA
+//                M dimension is filled by weight rows, the small batch rides in the MMA N dimension, so no
+//                tensor-core work is wasted on padding and each CTA streams a contiguous weight slab)
+//                -> transposed epilogues, optional split-K with fp32 partials.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+enum GemmEpi : int {
+  EPI_STORE = 0,      // out[m][n] = bf16(acc)
+  EPI_STORE_RES = 1,  // out[m][n] = bf16(bf16(acc) + residual[m][n])           (o_proj / down_proj + residual)
+  EPI_SWIGLU = 2,     // B rows interleaved {16 gate,16 up}: out[m][n/2] = bf16(bf16(silu(g)) * u)
+  EPI_T_STORE = 3,    // out[n][m] = bf16(acc)                                    (swap-AB)
+  EPI_T_SWIGLU = 4,   // A rows interleaved {16 gate,16 up}: out[n][m/2] = ...    (swap-AB)
+  EPI_T_PARTIAL = 5,  // ws[split][n][m] = acc (fp32)                             (swap-AB split-K)
+};
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles, splits;
+  int kb_total;       // ceil(K / 64)
+  int kb_per_split;   // ceil(kb_total / splits)
+  void* out;
+  const bf16* residual;
+  long long ldo;           // leading dimension of out (elements)
+  long long split_stride;  // EPI_T_PARTIAL: elements between split slices
+  int out_cols;            // logical number of output columns (bounds for SWIGLU modes = N/2 resp. M/2)
+  unsigned long long hint_a, hint_b;
+};
+
+constexpr int kGemmBlockM = 128;
+constexpr int kGemmBlockK = 64;
+constexpr int kGemmThreads = 192;
+constexpr int kGemmGroupM = 16;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KB
+  static constexpr int kBBytes = BLOCK_N * kGemmBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // power of two for 16..256
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_units = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode_unit = [&](int u, int& m_t, int& n_t, int& kb0, int& kb1) {
+    const int tile = u / p.splits;
+    const int s = u - tile * p.splits;
+    const int per_group = kGemmGroupM * p.n_tiles;
+    const int g = tile / per_group;
+    const int first_m = g * kGemmGroupM;
+    const int gsize = min(p.m_tiles - first_m, kGemmGroupM);
+    const int r = tile - g * per_group;
+    m_t = first_m + r % gsize;
+    n_t = r / gsize;
+    kb0 = s * p.kb_per_split;
+    kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+    return s;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        int m_t, n_t, kb0, kb1;
+        decode_unit(u, m_t, n_t, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m_t * kGemmBlockM, p.hint_a);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n_t * BLOCK_N, p.hint_b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kGemmBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        int m_t, n_t, kb0, kb1;
+        decode_unit(u, m_t, n_t, kb0, kb1);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = make_smem_desc_sw128(sa);
+          const uint64_t bdesc = make_smem_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kGemmBlockK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle atom: +2 in the (addr>>4) field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      int m_t, n_t, kb0, kb1;
+      const int s = decode_unit(u, m_t, n_t, kb0, kb1);
+      const int m = m_t * kGemmBlockM + q * 32 + lane;  // accumulator row of this thread
+      const int n0 = n_t * BLOCK_N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+      constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
+        if (n0 + c0 >= p.N) break;  // warp-uniform: nothing valid in this chunk
+        float v[CH];
+        {
+          uint32_t r[CH];
+          if constexpr (CH == 32) tmem_ld_32x32(taddr + c0, r); else tmem_ld_32x16(taddr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        const int nvalid = min(CH, p.N - (n0 + c0));
+        if constexpr (EPI == EPI_STORE || EPI == EPI_STORE_RES) {
+          if (m < p.M) {
+            bf16* orow = reinterpret_cast<bf16*>(p.out) + (long long)m * p.ldo + n0 + c0;
+            const bf16* rrow = (EPI == EPI_STORE_RES) ? p.residual + (long long)m * p.ldo + n0 + c0 : nullptr;
+            const bool vec = (nvalid == CH) && ((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 8) {
+                float f[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) f[t] = v[j + t];
+                if constexpr (EPI == EPI_STORE_RES) {
+                  uint4 rr = *reinterpret_cast<const uint4*>(rrow + j);
+                  const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    float2 r2 = unpack_bf16x2(rw[t]);
+                    f[2 * t] = bf16_round(f[2 * t]) + r2.x;
+                    f[2 * t + 1] = bf16_round(f[2 * t + 1]) + r2.y;
+                  }
+                }
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]);
+                o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]);
+                o.w = pack_bf16x2(f[6], f[7]);
+                *reinterpret_cast<uint4*>(orow + j) = o;
+              }
+            } else {
+              for (int j = 0; j < nvalid; ++j) {
+                float f = v[j];
+                if constexpr (EPI == EPI_STORE_RES) f = bf16_round(f) + __bfloat162float(rrow[j]);
+                orow[j] = __float2bfloat16_rn(f);
+              }
+            }
+          }
+        } else if constexpr (EPI == EPI_SWIGLU) {
+          // columns [c0, c0+16) = gate, [c0+16, c0+32) = up of output columns (n0+c0)/2 + j
+          static_assert(EPI != EPI_SWIGLU || CH == 32, "SWIGLU needs 32-column chunks");
+          if (m < p.M) {
+            const int oc = (n0 + c0) >> 1;
+            bf16* orow = reinterpret_cast<bf16*>(p.out) + (long long)m * p.ldo + oc;
+            float h[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float g = bf16_round(v[j]);
+              const float up = bf16_round(v[16 + j]);
+              h[j] = bf16_round(silu_f(g)) * up;
+            }
+            if (oc + 16 <= p.out_cols && (p.ldo & 7) == 0) {
+              uint4 o0, o1;
+              o0.x = pack_bf16x2(h[0], h[1]);   o0.y = pack_bf16x2(h[2], h[3]);
+              o0.z = pack_bf16x2(h[4], h[5]);   o0.w = pack_bf16x2(h[6], h[7]);
+              o1.x = pack_bf16x2(h[8], h[9]);   o1.y = pack_bf16x2(h[10], h[11]);
+              o1.z = pack_bf16x2(h[12], h[13]); o1.w = pack_bf16x2(h[14], h[15]);
+              reinterpret_cast<uint4*>(orow)[0] = o0;
+              reinterpret_cast<uint4*>(orow)[1] = o1;
+            } else {
+              for (int j = 0; j < 16 && oc + j < p.out_cols; ++j) orow[j] = __float2bfloat16_rn(h[j]);
+            }
+          }
+        } else if constexpr (EPI == EPI_T_STORE) {
+          if (m < p.M) {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)(n0 + c0) * p.ldo + m;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (j < nvalid) o[(long long)j * p.ldo] = __float2bfloat16_rn(v[j]);
+          }
+        } else if constexpr (EPI == EPI_T_SWIGLU) {
+          // rows of a 32-row warp slab: lanes 0-15 gate, lanes 16-31 up, for output feature (slab/2 + lane)
+          const int f = ((m_t * kGemmBlockM + q * 32) >> 1) + (lane & 15);
+          bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)(n0 + c0) * p.ldo + f;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const float mine = bf16_round(v[j]);
+            const float up = __shfl_down_sync(0xffffffffu, mine, 16);
+            if (lane < 16 && j < nvalid && f < p.out_cols)
+              o[(long long)j * p.ldo] = __float2bfloat16_rn(bf16_round(silu_f(mine)) * up);
+          }
+        } else {  // EPI_T_PARTIAL
+          if (m < p.M) {
+            float* o = reinterpret_cast<float*>(p.out) + (long long)s * p.split_stride +
+                       (long long)(n0 + c0) * p.ldo + m;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (j < nvalid) o[(long long)j * p.ldo] = v[j];
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace b200

@@ -1,0 +1,194 @@
+// Host-side launchers: TMA tensor-map cache, GEMM dispatch, op launch helpers.
+#pragma once
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"
+#include "ops.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency,
+// so the library also loads on a GPU-less box for the symbol-export test).
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2D bf16 row-major [rows][cols] (cols contiguous), box = [box_rows][64], 128B swizzle, OOB -> zeros.
+inline int make_tmap_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                        uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  B200_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base must be 16-byte aligned");
+  B200_REQUIRE((ld_elems * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+  return 0;
+}
+
+struct TmapCache {
+  std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t>, CUtensorMap> maps;
+  int get(const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, const CUtensorMap** out) {
+    auto key = std::make_tuple(ptr, rows, cols, box_rows);
+    auto it = maps.find(key);
+    if (it == maps.end()) {
+      CUtensorMap m;
+      int rc = make_tmap_2d(&m, ptr, rows, cols, cols, box_rows);
+      if (rc) return rc;
+      it = maps.emplace(key, m).first;
+    }
+    *out = &it->second;
+    return 0;
+  }
+};
+
+template <int BLOCK_N, int EPI>
+int launch_gemm_inst(const CUtensorMap* ta, const CUtensorMap* tb, const GemmParams& p, int grid, cudaStream_t s) {
+  auto kern = gemm_tn_kernel<BLOCK_N, EPI>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BLOCK_N>::kSmemBytes));
+    configured = true;
+  }
+  kern<<<grid, kGemmThreads, GemmCfg<BLOCK_N>::kSmemBytes, s>>>(*ta, *tb, p);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+struct GemmArgs {
+  const bf16* A; int a_rows;        // rows of the A buffer as declared to TMA (>= M)
+  const bf16* B; int b_rows;        // rows of the B buffer as declared to TMA (>= N)
+  int M, N, K;
+  int epi, block_n, splits;
+  void* out; const bf16* residual; long long ldo; long long split_stride; int out_cols;
+  bool stream_a;                    // true: A is the weight (decode) -> evict-first on A, keep B
+};
+
+inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStream_t s) {
+  B200_REQUIRE(a.K % 8 == 0, "K must be a multiple of 8");
+  const CUtensorMap *ta, *tb;
+  int rc = cache.get(a.A, a.a_rows, a.K, kGemmBlockM, &ta);
+  if (rc) return rc;
+  rc = cache.get(a.B, a.b_rows, a.K, a.block_n, &tb);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.m_tiles = (a.M + kGemmBlockM - 1) / kGemmBlockM;
+  p.n_tiles = (a.N + a.block_n - 1) / a.block_n;
+  p.kb_total = (a.K + kGemmBlockK - 1) / kGemmBlockK;
+  p.splits = a.splits < 1 ? 1 : (a.splits > p.kb_total ? p.kb_total : a.splits);
+  p.kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  B200_REQUIRE(p.splits == a.splits || a.epi != EPI_T_PARTIAL, "caller must use effective_splits() for partials");
+  p.out = a.out; p.residual = a.residual; p.ldo = a.ldo; p.split_stride = a.split_stride; p.out_cols = a.out_cols;
+  p.hint_a = a.stream_a ? kEvictFirst : kEvictLast;
+  p.hint_b = a.stream_a ? kEvictLast : kEvictNormal;
+  const int units = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = units < num_sms ? units : num_sms;
+  B200_REQUIRE(p.splits == 1 || a.epi == EPI_T_PARTIAL, "split-K only with the fp32 partial epilogue");
+#define B200_GEMM_CASE(BN, E) \
+  if (a.block_n == BN && a.epi == E) return launch_gemm_inst<BN, E>(ta, tb, p, grid, s);
+  B200_GEMM_CASE(256, EPI_STORE)
+  B200_GEMM_CASE(256, EPI_STORE_RES)
+  B200_GEMM_CASE(256, EPI_SWIGLU)
+  B200_GEMM_CASE(16, EPI_T_STORE)
+  B200_GEMM_CASE(16, EPI_T_SWIGLU)
+  B200_GEMM_CASE(16, EPI_T_PARTIAL)
+  B200_GEMM_CASE(32, EPI_T_STORE)
+  B200_GEMM_CASE(32, EPI_T_SWIGLU)
+  B200_GEMM_CASE(32, EPI_T_PARTIAL)
+  B200_GEMM_CASE(64, EPI_T_STORE)
+  B200_GEMM_CASE(64, EPI_T_SWIGLU)
+  B200_GEMM_CASE(64, EPI_T_PARTIAL)
+#undef B200_GEMM_CASE
+  set_last_error("unsupported GEMM variant block_n=" + std::to_string(a.block_n) + " epi=" + std::to_string(a.epi));
+  return -3;
+}
+
+// number of split-K slices launch_gemm will really use for a request of `want`
+inline int effective_splits(int K, int want) {
+  const int kb = (K + kGemmBlockK - 1) / kGemmBlockK;
+  int s = want < 1 ? 1 : (want > kb ? kb : want);
+  const int per = (kb + s - 1) / s;
+  return (kb + per - 1) / per;
+}
+
+inline int launch_rmsnorm(int mode, bf16* x, const bf16* w, bf16* xn, int rows, int H, float eps,
+                          const float* partial, int splits, long long split_stride, long long ld_partial,
+                          const bf16* y, cudaStream_t s) {
+  B200_REQUIRE(H % 8 == 0, "hidden size must be a multiple of 8");
+  const size_t smem = (size_t)(H + 32) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(rmsnorm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    B200_CUDA_OK(cudaFuncSetAttribute(rmsnorm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    B200_CUDA_OK(cudaFuncSetAttribute(rmsnorm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  B200_REQUIRE(smem <= 96 * 1024, "hidden size too large for the rmsnorm kernel");
+  if (rows == 0) return 0;
+  if (mode == 0) rmsnorm_kernel<0><<<rows, 256, smem, s>>>(x, w, xn, H, eps, nullptr, 0, 0, 0, nullptr);
+  else if (mode == 1) rmsnorm_kernel<1><<<rows, 256, smem, s>>>(x, w, xn, H, eps, partial, splits, split_stride, ld_partial, nullptr);
+  else rmsnorm_kernel<2><<<rows, 256, smem, s>>>(x, w, xn, H, eps, nullptr, 0, 0, 0, y);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+constexpr int kPrefillSmem = 5 * kTileBytes;
+constexpr int kDecodeSmem = 4096 + 4 * kTileBytes;
+
+inline int launch_attn_prefill(const AttnPrefillParams& p, int B, int max_len, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrefillSmem));
+    configured = true;
+  }
+  dim3 grid((max_len + 63) / 64, p.nh, B);
+  attn_prefill_kernel<<<grid, kAttnThreads, kPrefillSmem, s>>>(p);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+inline int launch_attn_decode(const AttnDecodeParams& p, int B, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecodeSmem));
+    configured = true;
+  }
+  B200_REQUIRE(p.G >= 1 && p.G <= 8, "GQA group size must be in [1, 8]");
+  dim3 grid(B * p.nkv, p.splits);
+  attn_decode_kernel<<<grid, kAttnThreads, kDecodeSmem, s>>>(p);
+  B200_CUDA_OK(cudaGetLastError());
+  if (p.splits > 1) {
+    attn_combine_kernel<<<B * p.nh, 128, 0, s>>>(p.part_o, p.part_ml, p.out, p.ldo, p.nkv, p.G, p.splits);
+    B200_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace b200

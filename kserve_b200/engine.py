@@ -1,0 +1,191 @@
+"""Python handle over the C ABI engine (include/kserve_b200.h).
+
+This is the object `B200GenerativeModel` calls where the reference calls
+``self._model.generate(**kwargs)`` (python/huggingfaceserver/huggingfaceserver/generative_model.py:314,328).
+PyTorch is used only to hold host/device buffers; all compute is in libkserve_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class GenerateResult:
+    output_ids: torch.Tensor          # int64 [B, S + T]  (prompt echoed, like transformers.generate)
+    stop_triggered: bool
+    num_generated: int
+    logits: Optional[torch.Tensor]    # bf16 [T, B, V] when requested
+    prefill_ms: float
+    decode_ms: float
+    decode_steps: int
+    kernel_launches: int
+
+
+def hf_rope_tables(rope_theta: float, head_dim: int, max_pos: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """cos/sin exactly as LlamaRotaryEmbedding computes them (transformers modeling_llama.py:96-135):
+    fp32 inv_freq, fp32 angle = inv_freq * position, cos/sin in fp32, cast to bf16."""
+    inv_freq = 1.0 / (rope_theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).to(torch.float) / head_dim))
+    pos = torch.arange(max_pos, dtype=torch.float32)
+    freqs = pos[:, None] * inv_freq[None, :]
+    return freqs.cos().to(torch.bfloat16).contiguous(), freqs.sin().to(torch.bfloat16).contiguous()
+
+
+class B200Engine:
+    def __init__(self, cfg: dict, *, max_batch: int = 8, max_seq_len: int = 2048,
+                 max_prefill_tokens: Optional[int] = None, num_kv_pages: int = 0, device: int = 0,
+                 tp_rank: int = 0, tp_size: int = 1, nccl_id: Optional[bytes] = None,
+                 vocab_rows: Optional[int] = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.B200Error("no CUDA device: kserve_b200 has no CPU fallback")
+        self.cfg = dict(cfg)
+        self.vocab = int(vocab_rows or cfg["vocab_size"])
+        self.max_batch, self.max_seq_len = max_batch, max_seq_len
+        mc = _lib.ModelConfig()
+        mc.vocab_size = self.vocab
+        mc.hidden_size = cfg["hidden_size"]
+        mc.intermediate_size = cfg["intermediate_size"]
+        mc.num_layers = cfg["num_hidden_layers"]
+        mc.num_heads = cfg["num_attention_heads"]
+        mc.num_kv_heads = cfg["num_key_value_heads"]
+        mc.head_dim = cfg.get("head_dim") or cfg["hidden_size"] // cfg["num_attention_heads"]
+        mc.max_position = max(max_seq_len, 64)
+        mc.rms_eps = cfg.get("rms_norm_eps", 1e-5)
+        mc.rope_theta = cfg.get("rope_theta", 10000.0)
+        mc.max_batch = max_batch
+        mc.max_seq_len = max_seq_len
+        mc.max_prefill_tokens = max_prefill_tokens or max_batch * max_seq_len
+        mc.num_kv_pages = num_kv_pages
+        mc.tp_rank, mc.tp_size, mc.device = tp_rank, tp_size, device
+        self.device = device
+        self.tp_size = tp_size
+        h = C.c_void_p()
+        idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+        _lib.check(self.lib.b200_engine_create(C.byref(mc), idbuf, C.byref(h)), "b200_engine_create")
+        self.h = h
+        cos, sin = hf_rope_tables(mc.rope_theta, mc.head_dim, mc.max_position)
+        _lib.check(self.lib.b200_engine_set_rope_table(self.h, cos.data_ptr(), sin.data_ptr(), mc.max_position),
+                   "b200_engine_set_rope_table")
+        self._cb_keepalive = None
+
+    # ------------------------------------------------------------------ weights
+    def set_weight(self, name: str, t: torch.Tensor) -> None:
+        if "inv_freq" in name:
+            return
+        if t.dtype != torch.bfloat16:
+            t = t.to(torch.bfloat16)
+        t = t.contiguous()
+        on_dev = 1 if t.is_cuda else 0
+        shape = (C.c_int64 * t.dim())(*t.shape)
+        _lib.check(self.lib.b200_engine_set_weight(self.h, name.encode(), t.data_ptr(), on_dev, t.dim(), shape),
+                   f"set_weight({name})")
+
+    def load_weights(self, named_tensors: Iterable[Tuple[str, torch.Tensor]]) -> None:
+        for name, t in named_tensors:
+            self.set_weight(name, t)
+        _lib.check(self.lib.b200_engine_finalize_weights(self.h), "finalize_weights")
+
+    # ------------------------------------------------------------------ generate
+    def _params(self, max_new_tokens, pad_token_id, eos_token_ids, stop_sequences, forced_tokens):
+        gp = _lib.GenParams()
+        keep = []
+        gp.max_new_tokens = int(max_new_tokens)
+        gp.pad_token_id = int(pad_token_id if pad_token_id is not None else 0)
+        eos = [int(x) for x in (eos_token_ids or [])]
+        if eos:
+            arr = (C.c_int64 * len(eos))(*eos)
+            keep.append(arr)
+            gp.eos_token_ids = arr
+        gp.num_eos = len(eos)
+        stops = [list(map(int, s)) for s in (stop_sequences or []) if len(s) > 0]
+        if stops:
+            flat = [t for s in stops for t in s]
+            offs = [0]
+            for s in stops:
+                offs.append(offs[-1] + len(s))
+            a1 = (C.c_int64 * len(flat))(*flat)
+            a2 = (C.c_int32 * len(offs))(*offs)
+            keep += [a1, a2]
+            gp.stop_tokens, gp.stop_offsets = a1, a2
+        gp.num_stop = len(stops)
+        if forced_tokens is not None:
+            ft = torch.as_tensor(forced_tokens, dtype=torch.int64).contiguous()
+            assert ft.shape[1] == max_new_tokens
+            keep.append(ft)
+            gp.forced_tokens = C.cast(ft.data_ptr(), C.POINTER(C.c_int64))
+        return gp, keep
+
+    def generate(self, input_ids, attention_mask=None, *, max_new_tokens: int, pad_token_id: Optional[int] = 0,
+                 eos_token_ids: Sequence[int] = (), stop_sequences: Sequence[Sequence[int]] = (),
+                 forced_tokens=None, want_logits: bool = False,
+                 streamer: Optional[Callable[[int, List[int]], bool]] = None) -> GenerateResult:
+        ids = torch.as_tensor(input_ids, dtype=torch.int64).contiguous()
+        assert ids.dim() == 2 and not ids.is_cuda
+        B, S = ids.shape
+        mask = None
+        if attention_mask is not None:
+            mask = torch.as_tensor(attention_mask, dtype=torch.int64).contiguous()
+            assert mask.shape == ids.shape
+        gp, keep = self._params(max_new_tokens, pad_token_id, eos_token_ids, stop_sequences, forced_tokens)
+        out = torch.empty((B, S + max_new_tokens), dtype=torch.int64).pin_memory()
+        out_len, stop = C.c_int32(0), C.c_int32(0)
+        logits = None
+        if want_logits:
+            logits = torch.empty((max_new_tokens, B, self.vocab), dtype=torch.bfloat16).pin_memory()
+        if streamer is not None:
+            def _cb(user, step, toks, batch):
+                return 1 if streamer(step, [toks[i] for i in range(batch)]) else 0
+            cb = _lib.TOKEN_CALLBACK(_cb)
+        else:
+            cb = _lib.TOKEN_CALLBACK()
+        self._cb_keepalive = cb
+        rc = self.lib.b200_generate(self.h, ids.data_ptr(), mask.data_ptr() if mask is not None else None, B, S,
+                                    C.byref(gp), out.data_ptr(), C.byref(out_len), C.byref(stop),
+                                    logits.data_ptr() if logits is not None else None, cb, None)
+        if rc not in (0, 1):
+            _lib.check(rc, "b200_generate")
+        tm = _lib.Timing()
+        self.lib.b200_engine_last_timing(self.h, C.byref(tm))
+        T = out_len.value - S
+        return GenerateResult(output_ids=out[:, :out_len.value].clone(), stop_triggered=bool(stop.value),
+                              num_generated=T, logits=logits[:T].clone() if logits is not None else None,
+                              prefill_ms=tm.prefill_ms, decode_ms=tm.decode_ms, decode_steps=tm.decode_steps,
+                              kernel_launches=tm.kernel_launches)
+
+    # ------------------------------------------------------------------ device-resident replay (bench)
+    def stage(self, input_ids, attention_mask=None, *, max_new_tokens: int, pad_token_id: int = 0):
+        ids = torch.as_tensor(input_ids, dtype=torch.int64).contiguous()
+        mask = None if attention_mask is None else torch.as_tensor(attention_mask, dtype=torch.int64).contiguous()
+        gp, keep = self._params(max_new_tokens, pad_token_id, (), (), None)
+        B, S = ids.shape
+        self._staged_shape = (B, S, max_new_tokens)
+        _lib.check(self.lib.b200_stage_prompt(self.h, ids.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                              B, S, C.byref(gp)), "b200_stage_prompt")
+
+    def run_staged(self, do_prefill: bool, decode_steps: int) -> None:
+        _lib.check(self.lib.b200_run_staged(self.h, 1 if do_prefill else 0, decode_steps), "b200_run_staged")
+
+    def fetch_staged(self) -> torch.Tensor:
+        B, S, T = self._staged_shape
+        out = torch.empty((B, S + T), dtype=torch.int64)
+        out_len, stop = C.c_int32(0), C.c_int32(0)
+        _lib.check(self.lib.b200_fetch_staged(self.h, out.data_ptr(), C.byref(out_len), C.byref(stop)),
+                   "b200_fetch_staged")
+        return out[:, :out_len.value]
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.b200_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
