@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on its config: output tokens/s for Llama-3-8B (bf16, synthetic weights
+of that architecture), 1024-in / 128-out, batch 32, on N GPUs of one node (N>1 = tensor parallel), plus p50 TTFT.
+
+One "step" = one pass of the hot path over one batch: prefill of B x 1024 prompt tokens + 128 greedy tokens.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3              # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 2        # the reference's HF-transformers CPU backend
+    torchrun --nproc-per-node N ... bench.py --gpus N ...      # TP=N over NCCL
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LLAMA3_8B = dict(vocab_size=128256, hidden_size=4096, intermediate_size=14336, num_hidden_layers=32,
+                 num_attention_heads=32, num_key_value_heads=8, head_dim=128, max_position_embeddings=8192,
+                 rms_norm_eps=1e-5, rope_theta=500000.0)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+def algorithmic(cfg, B, S_in, S_out, tp=1):
+    """SURVEY.md §8(d) figures, computed from the config (per GPU when tp > 1)."""
+    H, I, V, L = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"], cfg["num_hidden_layers"]
+    nh, nkv, d = cfg["num_attention_heads"], cfg["num_key_value_heads"], cfg["head_dim"]
+    layer_params = H * (nh + 2 * nkv) * d + nh * d * H + 3 * H * I
+    weight_bytes = (L * layer_params + V * H) * 2 / tp
+    kv_per_tok = L * 2 * nkv * d * 2 / tp
+    mean_ctx = S_in + (S_out - 1) / 2 + 1
+    decode_bytes = weight_bytes + B * mean_ctx * kv_per_tok
+    prefill_flops = (2 * L * layer_params * B * S_in + 2 * S_in * S_in * nh * d * L * B + 2 * V * H * B) / tp
+    return dict(weight_bytes=weight_bytes, decode_bytes_per_step=decode_bytes, prefill_flops=prefill_flops,
+                kv_bytes_per_token=kv_per_tok, layer_params=layer_params)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU implementation of the path
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference(cfg, sample_B, sample_S, sample_T, steps, warmup):
+    """HF-transformers CPU backend (what huggingfaceserver runs with --backend huggingface on CPU), through the
+    oracle's restated create_completion; random weights of the architecture (values do not affect timing)."""
+    import torch
+    from oracle.hf_oracle import OracleGenerativeModel
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.set_num_threads(os.cpu_count())
+    hf_cfg = LlamaConfig(**cfg, tie_word_embeddings=False, eos_token_id=None, bos_token_id=None, pad_token_id=None)
+    with torch.device("meta"):
+        model = LlamaForCausalLM(hf_cfg)
+    model = model.to_empty(device="cpu").to(torch.bfloat16)
+    g = torch.Generator().manual_seed(0)
+    block = (torch.randn(1 << 24, generator=g) * 0.02).to(torch.bfloat16)
+    with torch.no_grad():
+        for p in model.parameters():
+            flat = p.data.view(-1)
+            for o in range(0, flat.numel(), block.numel()):
+                n = min(block.numel(), flat.numel() - o)
+                flat[o:o + n] = block[:n]
+            if p.dim() == 1:
+                p.data.fill_(1.0)
+    for mod in model.modules():
+        if hasattr(mod, "inv_freq"):
+            inv_freq, scaling = type(mod).compute_default_rope_parameters(mod.config, "cpu")
+            mod.register_buffer("inv_freq", inv_freq.float(), persistent=False)
+            mod.register_buffer("original_inv_freq", inv_freq.float().clone(), persistent=False)
+    model.eval()
+    orc = OracleGenerativeModel(model, pad_token_id=cfg["vocab_size"] - 1, max_length=cfg["max_position_embeddings"])
+    ids = torch.randint(3, 128000, (sample_B, sample_S), generator=g).tolist()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = orc.create_completion(ids, max_tokens=sample_T, temperature=0)
+        dt = time.perf_counter() - t0
+        assert r.completion_tokens == sample_B * sample_T
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return dict(value=sample_B * sample_T / (ms / 1e3), ms_per_step=ms, cores=torch.get_num_threads(),
+                sample=f"Llama-3-8B dims (32 layers, bf16) on the host CPU: batch {sample_B}, {sample_S}-in/{sample_T}-out, "
+                       f"{steps} timed step(s) after {warmup} warm-up")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(LLAMA3_8B, args.ref_batch, args.ref_prompt_len, args.ref_gen_len, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "output tokens/s", "value": round(r["value"], 3), "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 2),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Llama-3-8B 1024-in/128-out batch 32 (reference CPU backend timed on a bounded sample)",
+                   "sample": r["sample"]},
+        "cpu_baseline": {"value": round(r["value"], 3), "unit": "tokens/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": round(r["value"], 3), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------
+def gpu_weights(cfg, device):
+    """random-init weights of the architecture, generated on the device one tensor at a time"""
+    import torch
+    from kserve_b200.model_spec import llama_tensor_specs as tensor_specs
+    g = torch.Generator(device=device).manual_seed(0)
+    for name, shape, kind in tensor_specs(cfg):
+        if kind == "norm":
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)
+        elif kind == "embed":
+            t = torch.randn(shape, generator=g, device=device)
+        else:
+            t = torch.randn(shape, generator=g, device=device) * (shape[-1] ** -0.5)
+        yield name, t.to(torch.bfloat16)
+        del t
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from kserve_b200 import _lib
+    from kserve_b200.engine import B200Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        lib = _lib.load()
+        buf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            import ctypes as C
+            raw = C.create_string_buffer(128)
+            _lib.check(lib.b200_nccl_unique_id(raw), "nccl_unique_id")
+            buf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        buf = buf.to(dev)
+        dist.broadcast(buf, 0)
+        nccl_id = bytes(buf.cpu().tolist())
+
+    cfg = LLAMA3_8B
+    B, S, T = args.batch, args.prompt_len, args.gen_len
+    eng = B200Engine(cfg, max_batch=B, max_seq_len=S + T, max_prefill_tokens=B * S, device=local,
+                     tp_rank=rank, tp_size=world, nccl_id=nccl_id)
+    eng.load_weights(gpu_weights(cfg, dev))
+    torch.cuda.empty_cache()
+    g = torch.Generator().manual_seed(1234)
+    ids = torch.randint(3, 128000, (B, S), generator=g, dtype=torch.int64).pin_memory()
+    pad = cfg["vocab_size"] - 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: prompt staged once, K x (prefill + T-1 decode steps), CUDA events on the
+    # engine stream; weights (16 GB) >> L2 (126 MB) so every step re-reads HBM.
+    eng.stage(ids, None, max_new_tokens=T, pad_token_id=pad)
+    for _ in range(args.warmup):
+        eng.run_staged_timed(T - 1)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    pre, dec = [], []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        a, b = eng.run_staged_timed(T - 1)
+        pre.append(a); dec.append(b)
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    launches = eng.last_launches()
+    clocks = sampler.stop() if rank == 0 else None
+    out = eng.fetch_staged()
+    assert out.shape == (B, S + T), out.shape
+    dev_ms = sum(pre) + sum(dec)
+    tm = torch.tensor([dev_ms, statistics.median(pre), sum(dec)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms, ttft_p50, dec_ms_total = [float(v) for v in tm.tolist()]
+    ms_per_step = dev_ms / args.steps
+    value = B * T / (ms_per_step / 1e3)
+
+    # ---- end to end through the public call with HOST buffers (H2D of ids + D2H of results inside)
+    e2e_times = []
+    for i in range(2 + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        r = eng.generate(ids, None, max_new_tokens=T, pad_token_id=pad)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            e2e_times.append(dt)
+    e2e_t = torch.tensor([sum(e2e_times) / len(e2e_times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = B * T / float(e2e_t.item())
+    h2d = 3 * B * S * 4 + 6 * B * 4 + B * eng.max_seq_len // 64 * 4 + 16
+    d2h = B * (S + T) * 4 + 16
+
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    alg = algorithmic(cfg, B, S, T, tp=world)
+    dec_step_ms = dec_ms_total / (args.steps * (T - 1))
+    ach_gbs = alg["decode_bytes_per_step"] / (dec_step_ms * 1e-3) / 1e9
+    pre_ms = statistics.median(pre)
+    ach_tf = alg["prefill_flops"] / (pre_ms * 1e-3) / 1e12
+    line = {
+        "metric": "output tokens/s", "value": round(value, 1), "unit": "tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"Llama-3-8B (random-init, bf16) {S}-in/{T}-out batch {B}, greedy, "
+                               f"{'TP=' + str(world) if world > 1 else '1 GPU'}",
+                   "global_batch": B, "prompt_len": S, "gen_len": T, "parallelism": f"tp{world}",
+                   "l2": "weights 16 GB / N per GPU >> 126 MB L2: no flush needed", "timer": "CUDA events on the engine stream, max over ranks"},
+        "ttft_p50_ms": round(ttft_p50, 2),
+        "decode_ms_per_token_step": round(dec_step_ms, 4),
+        "wall_s": round(wall, 3),
+        "e2e": {"value": round(e2e_val, 1), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "call": "b200_generate (C ABI) with host int64 ids in / host ids out"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "decode step: gemm_tn_kernel<swap-AB> weight streaming + attn_decode KV read",
+                     "bound": "hbm", "achieved": round(ach_gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": round(ach_gbs / peaks["hbm_gbs"], 4), "traffic": None, "peak_src": peaks["src"],
+                     "algorithmic_bytes_per_launch": int(alg["decode_bytes_per_step"])},
+        "roofline_prefill": {"kernel": "prefill: gemm_tn_kernel<256> + attn_prefill", "bound": "tensor",
+                             "achieved": round(ach_tf, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                             "frac": round(ach_tf / peaks["tf_sustained"], 4), "peak_src": peaks["src"],
+                             "algorithmic_flops_per_launch": alg["prefill_flops"]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+        r = cpu_reference(cfg, args.ref_batch, args.ref_prompt_len, args.ref_gen_len, 1, 0)
+        line["cpu_baseline"] = {"value": round(r["value"], 3), "unit": "tokens/s", "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"]}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--prompt-len", type=int, default=1024)
+    ap.add_argument("--gen-len", type=int, default=128)
+    ap.add_argument("--ref-batch", type=int, default=1)
+    ap.add_argument("--ref-prompt-len", type=int, default=128)
+    ap.add_argument("--ref-gen-len", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

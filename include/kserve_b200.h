@@ -105,6 +105,9 @@ int b200_engine_last_timing(b200_engine_t* e, b200_timing_t* out);
 int b200_stage_prompt(b200_engine_t* e, const int64_t* input_ids, const int64_t* attention_mask, int32_t B,
                       int32_t S, const b200_gen_params_t* params);
 int b200_run_staged(b200_engine_t* e, int32_t do_prefill, int32_t decode_steps);
+/* prefill + decode_steps decode steps of the staged prompt, each phase bracketed by CUDA events on the
+ * engine's own stream (the stream every kernel of the engine is launched on); synchronises at the end. */
+int b200_run_staged_timed(b200_engine_t* e, int32_t decode_steps, float* prefill_ms, float* decode_ms);
 int b200_fetch_staged(b200_engine_t* e, int64_t* out_ids, int32_t* out_len, int32_t* stop_triggered);
 
 /* ---- single kernels on caller-provided device pointers (unit tests / micro-benchmarks) ------------- */

@@ -60,6 +60,7 @@ def load() -> C.CDLL:
     lib.b200_engine_last_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.b200_stage_prompt.argtypes = [vp, vp, vp, i32, i32, C.POINTER(GenParams)]
     lib.b200_run_staged.argtypes = [vp, i32, i32]
+    lib.b200_run_staged_timed.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.b200_fetch_staged.argtypes = [vp, vp, C.POINTER(i32), C.POINTER(i32)]
     lib.b200_op_gemm.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64, vp]
     lib.b200_op_rmsnorm.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_float, vp, C.c_int, vp, vp]

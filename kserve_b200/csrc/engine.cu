@@ -779,6 +779,24 @@ int b200_run_staged(b200_engine_t* e, int32_t do_prefill, int32_t decode_steps) 
   return 0;
 }
 
+int b200_run_staged_timed(b200_engine_t* e, int32_t decode_steps, float* prefill_ms, float* decode_ms) {
+  B200_REQUIRE(e && prefill_ms && decode_ms, "null argument");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  e->launches = 0;
+  B200_CUDA_OK(cudaEventRecord(e->ev0, e->stream));
+  int rc = b200_run_staged(e, 1, 0);
+  if (rc) return rc;
+  B200_CUDA_OK(cudaEventRecord(e->ev1, e->stream));
+  if ((rc = b200_run_staged(e, 0, decode_steps))) return rc;
+  B200_CUDA_OK(cudaEventRecord(e->ev2, e->stream));
+  B200_CUDA_OK(cudaStreamSynchronize(e->stream));
+  B200_CUDA_OK(cudaEventElapsedTime(prefill_ms, e->ev0, e->ev1));
+  B200_CUDA_OK(cudaEventElapsedTime(decode_ms, e->ev1, e->ev2));
+  e->timing.prefill_ms = *prefill_ms; e->timing.decode_ms = *decode_ms;
+  e->timing.decode_steps = decode_steps; e->timing.kernel_launches = e->launches;
+  return 0;
+}
+
 int b200_fetch_staged(b200_engine_t* e, int64_t* out_ids, int32_t* out_len, int32_t* stop_triggered) {
   B200_REQUIRE(e && out_ids && out_len, "null argument");
   B200_CUDA_OK(cudaSetDevice(e->cfg.device));

@@ -171,6 +171,17 @@ class B200Engine:
     def run_staged(self, do_prefill: bool, decode_steps: int) -> None:
         _lib.check(self.lib.b200_run_staged(self.h, 1 if do_prefill else 0, decode_steps), "b200_run_staged")
 
+    def run_staged_timed(self, decode_steps: int):
+        """-> (prefill_ms, decode_ms) from CUDA events on the engine stream."""
+        a, b = C.c_float(0), C.c_float(0)
+        _lib.check(self.lib.b200_run_staged_timed(self.h, decode_steps, C.byref(a), C.byref(b)), "b200_run_staged_timed")
+        return a.value, b.value
+
+    def last_launches(self) -> int:
+        tm = _lib.Timing()
+        self.lib.b200_engine_last_timing(self.h, C.byref(tm))
+        return tm.kernel_launches
+
     def fetch_staged(self) -> torch.Tensor:
         B, S, T = self._staged_shape
         out = torch.empty((B, S + T), dtype=torch.int64)

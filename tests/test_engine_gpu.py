@@ -134,3 +134,31 @@ def test_streamer_callback(engines):
                      streamer=lambda step, toks: seen.append((step, list(toks))) and False)
     assert [s for s, _ in seen] == list(range(6))
     assert torch.tensor([t for _, t in seen]).T.tolist() == c["gen"][:, :6].tolist()
+
+
+@pytest.mark.slow
+def test_llama3_8b_shapes_two_layers():
+    """Full-size Llama-3-8B layer / vocabulary shapes (2 layers): every production GEMM shape, 128256-row LM head."""
+    c = load_case("llama3_8b_2l_ids")
+    m = c["meta"]
+    eng = make_engine(m["cfg"], m["seed"], vocab_rows=m["vocab_rows"], max_batch=4, max_seq_len=256)
+    try:
+        r = eng.generate(c["input_ids"], None, max_new_tokens=c["T"], pad_token_id=m["pad_token_id"],
+                         forced_tokens=c["gen"], want_logits=True)
+        got = r.logits.float().permute(1, 0, 2)      # [B, T, V]
+        ref0 = c["step0_logits"]                      # fp16-stored bf16 logits of step 0
+        tol = logits_tol(ref0)
+        err0 = (got[:, 0] - ref0).abs()
+        # top-k values of every step
+        idx = c["topk_idx"].long()
+        gv = torch.gather(got, 2, idx)
+        errk = (gv - c["topk_vals"]).abs()
+        _record("llama3_8b_2l:teacher_forced", max_err_step0=float(err0.max()), max_err_topk=float(errk.max()), tol=tol,
+                max_logit=float(ref0.abs().max()))
+        assert float(err0.max()) <= tol and float(errk.max()) <= tol
+        pred = got.argmax(-1)
+        decisive = c["margin"] > 2 * tol
+        assert bool((pred == c["gen"])[decisive].all())
+        _record("llama3_8b_2l:greedy_tf", steps=int(pred.numel()), agree=int((pred == c["gen"]).sum()), decisive=int(decisive.sum()))
+    finally:
+        eng.close()
