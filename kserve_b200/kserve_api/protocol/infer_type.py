@@ -1,0 +1,316 @@
+"""Open Inference Protocol (V2) tensor envelope: InferInput / InferRequest / InferOutput / InferResponse.
+
+Mirrors the public surface of python/kserve/kserve/protocol/infer_type.py (constructors, ``from_bytes``
+binary extension :593-666, ``as_numpy`` :235-258, ``to_rest`` :717, :1328) for the REST legs the LLM path
+uses.  One deliberate difference: raw binary tensors stay a zero-copy
+``np.frombuffer`` view — the reference converts them to Python lists (``set_data_from_numpy(...,
+binary_data=False)`` :642-644), a full round trip this runtime skips so ``input_ids`` can go straight to
+pinned memory.
+"""
+from __future__ import annotations
+
+import json
+import struct
+import uuid
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+
+from ..errors import InvalidInput
+
+_DT = {
+    "BOOL": np.bool_, "UINT8": np.uint8, "UINT16": np.uint16, "UINT32": np.uint32, "UINT64": np.uint64,
+    "INT8": np.int8, "INT16": np.int16, "INT32": np.int32, "INT64": np.int64,
+    "FP16": np.float16, "FP32": np.float32, "FP64": np.float64, "BYTES": np.object_,
+}
+_NP2DT = {np.dtype(v): k for k, v in _DT.items() if k != "BYTES"}
+
+
+def to_np_dtype(datatype: str):
+    if datatype not in _DT:
+        raise InvalidInput(f"unsupported datatype {datatype}")
+    return _DT[datatype]
+
+
+def from_np_dtype(dt) -> str:
+    dt = np.dtype(dt)
+    if dt == np.object_ or dt.type in (np.bytes_, np.str_):
+        return "BYTES"
+    if dt not in _NP2DT:
+        raise InvalidInput(f"unsupported numpy dtype {dt}")
+    return _NP2DT[dt]
+
+
+def serialize_byte_tensor(arr: np.ndarray) -> bytes:
+    """BYTES elements are <uint32 little-endian length><bytes> back to back (OIP binary extension)."""
+    out = bytearray()
+    for item in arr.reshape(-1):
+        b = item if isinstance(item, (bytes, bytearray)) else str(item).encode("utf-8")
+        out += struct.pack("<I", len(b)) + b
+    return bytes(out)
+
+
+def deserialize_bytes_tensor(raw: bytes) -> np.ndarray:
+    items, off = [], 0
+    while off < len(raw):
+        (n,) = struct.unpack_from("<I", raw, off)
+        off += 4
+        items.append(bytes(raw[off:off + n]))
+        off += n
+    return np.array(items, dtype=np.object_)
+
+
+class _Tensor:
+    def __init__(self, name: str, shape: List[int], datatype: str, data=None, parameters: Optional[Dict] = None):
+        self._name, self._shape, self._datatype = name, list(shape), datatype.upper()
+        self._parameters = parameters if parameters is not None else {}
+        self._data = data
+        self._raw_data: Optional[bytes] = None
+
+    name = property(lambda s: s._name)
+    datatype = property(lambda s: s._datatype)
+    parameters = property(lambda s: s._parameters)
+
+    @property
+    def shape(self):
+        return self._shape
+
+    @shape.setter
+    def shape(self, v):
+        self._shape = list(v)
+
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, v):
+        self._data = v
+
+    def as_numpy(self) -> np.ndarray:
+        dtype = to_np_dtype(self._datatype)
+        if self._raw_data is not None:
+            if self._datatype == "BYTES":
+                return deserialize_bytes_tensor(self._raw_data).reshape(self._shape)
+            return np.frombuffer(self._raw_data, dtype=dtype).reshape(self._shape)   # zero copy
+        if self._data is None:
+            raise InvalidInput(f"'data' field is missing for tensor '{self._name}'")
+        if isinstance(self._data, np.ndarray):
+            return self._data.reshape(self._shape)
+        if self._datatype == "BYTES":
+            return np.array([x.encode("utf-8") if isinstance(x, str) else x for x in _flatten(self._data)],
+                            dtype=np.object_).reshape(self._shape)
+        return np.asarray(self._data, dtype=dtype).reshape(self._shape)
+
+    def as_string(self) -> List[str]:
+        return [x.decode("utf-8") if isinstance(x, (bytes, bytearray)) else str(x) for x in self.as_numpy().reshape(-1)]
+
+    def set_data_from_numpy(self, arr: np.ndarray, binary_data: bool = True):
+        if not isinstance(arr, np.ndarray):
+            raise InvalidInput("input tensor must be a numpy array")
+        dt = from_np_dtype(arr.dtype)
+        if dt != self._datatype:
+            raise InvalidInput(f"got unexpected datatype {dt} from numpy array, expected {self._datatype}")
+        self._shape = list(arr.shape)
+        if binary_data:
+            self._data = None
+            self._raw_data = serialize_byte_tensor(arr) if dt == "BYTES" else np.ascontiguousarray(arr).tobytes()
+            self._parameters["binary_data_size"] = len(self._raw_data)
+        else:
+            if dt == "FP16":
+                raise InvalidInput("FP16 tensors must use the binary data format")
+            self._raw_data = None
+            self._parameters.pop("binary_data_size", None)
+            if dt == "BYTES":
+                self._data = [x.decode("utf-8") if isinstance(x, (bytes, bytearray)) else str(x) for x in arr.reshape(-1)]
+            else:
+                self._data = arr.reshape(-1).tolist()
+
+    def _to_dict(self, binary: bool, raw_out: List[bytes]) -> Dict[str, Any]:
+        d: Dict[str, Any] = {"name": self._name, "shape": self._shape, "datatype": self._datatype}
+        params = dict(self._parameters)
+        if binary:
+            raw = self._raw_data
+            if raw is None:
+                arr = self.as_numpy()
+                raw = serialize_byte_tensor(arr) if self._datatype == "BYTES" else np.ascontiguousarray(arr).tobytes()
+            params["binary_data_size"] = len(raw)
+            raw_out.append(raw)
+        else:
+            params.pop("binary_data_size", None)
+            if self._datatype == "FP16":
+                raise InvalidInput(f"Sending FP16 data via JSON is not supported. Please use the binary data format for {self._name}")
+            if self._raw_data is not None or isinstance(self._data, np.ndarray):
+                arr = self.as_numpy()
+                d["data"] = ([x.decode("utf-8") if isinstance(x, (bytes, bytearray)) else x for x in arr.reshape(-1)]
+                             if self._datatype == "BYTES" else arr.reshape(-1).tolist())
+            else:
+                if self._data is None:
+                    raise InvalidInput(f"'data' field is missing for tensor '{self._name}'")
+                d["data"] = self._data
+        if params:
+            d["parameters"] = params
+        return d
+
+
+def _flatten(x):
+    if isinstance(x, (list, tuple)):
+        for y in x:
+            yield from _flatten(y)
+    else:
+        yield x
+
+
+class InferInput(_Tensor):
+    pass
+
+
+class InferOutput(_Tensor):
+    pass
+
+
+class RequestedOutput:
+    def __init__(self, name: str, parameters: Optional[Dict] = None):
+        self.name, self.parameters = name, parameters or {}
+
+    @property
+    def binary_data(self) -> Optional[bool]:
+        return self.parameters.get("binary_data")
+
+
+class InferRequest:
+    def __init__(self, model_name: str, infer_inputs: List[InferInput], request_id: Optional[str] = None,
+                 parameters: Optional[Dict] = None, request_outputs: Optional[List[RequestedOutput]] = None,
+                 model_version: Optional[str] = None):
+        self.id = request_id
+        self.model_name = model_name
+        self.model_version = model_version
+        self.inputs = infer_inputs
+        self.parameters = parameters or {}
+        self.request_outputs = request_outputs
+
+    @classmethod
+    def from_bytes(cls, req_bytes: bytes, json_length: int, model_name: str) -> "InferRequest":
+        """infer_type.py:593-666 — JSON header followed by the raw little-endian tensors, in input order."""
+        try:
+            d = json.loads(req_bytes[:json_length])
+        except json.JSONDecodeError as e:
+            raise InvalidInput(f"Unrecognized request format: {e}")
+        inputs, start = [], json_length
+        view = memoryview(req_bytes)
+        for inp in d.get("inputs", []):
+            params = inp.get("parameters") or {}
+            t = InferInput(inp["name"], inp["shape"], inp["datatype"], parameters=dict(params))
+            if inp.get("data") is not None:
+                if t.datatype == "FP16":
+                    raise InvalidInput(f"Receiving FP16 data via JSON is not supported. Please use the binary data format for input {t.name}")
+                t.data = inp["data"]
+            elif "binary_data_size" in params:
+                n = params["binary_data_size"]
+                if n is None:
+                    raise InvalidInput(f"'binary_data_size' is not specified for input '{t.name}' for model '{model_name}'")
+                t._raw_data = view[start:start + n]
+                start += n
+            else:
+                raise InvalidInput(f"'data' field is missing for input '{t.name}' for model '{model_name}'")
+            inputs.append(t)
+        outs = None
+        if d.get("outputs") is not None:
+            outs = [RequestedOutput(o["name"], o.get("parameters")) for o in d["outputs"]]
+        return cls(model_name=model_name, request_id=d.get("id"), parameters=d.get("parameters"), infer_inputs=inputs,
+                   request_outputs=outs)
+
+    @classmethod
+    def from_dict(cls, d: Dict, model_name: str) -> "InferRequest":
+        raw = json.dumps(d).encode()
+        return cls.from_bytes(raw, len(raw), model_name)
+
+    def get_input_by_name(self, name: str) -> Optional[InferInput]:
+        for i in self.inputs:
+            if i.name == name:
+                return i
+        return None
+
+    @property
+    def use_binary_outputs(self) -> bool:
+        if self.parameters.get("binary_data_output"):
+            return True
+        return any(o.binary_data for o in (self.request_outputs or []))
+
+    def to_rest(self) -> Tuple[Union[bytes, Dict], Optional[int]]:
+        raws: List[bytes] = []
+        ins = [i._to_dict(i._raw_data is not None, raws) for i in self.inputs]
+        res: Dict[str, Any] = {"id": self.id or str(uuid.uuid4()), "model_name": self.model_name, "inputs": ins}
+        if self.parameters:
+            res["parameters"] = self.parameters
+        if self.request_outputs:
+            res["outputs"] = [{"name": o.name, **({"parameters": o.parameters} if o.parameters else {})} for o in self.request_outputs]
+        if raws:
+            j = json.dumps(res).encode()
+            return j + b"".join(bytes(r) for r in raws), len(j)
+        return res, None
+
+
+class InferResponse:
+    def __init__(self, response_id: str, model_name: str, infer_outputs: List[InferOutput],
+                 model_version: Optional[str] = None, parameters: Optional[Dict] = None,
+                 use_binary_outputs: bool = False, requested_outputs: Optional[List[RequestedOutput]] = None):
+        self.id = response_id
+        self.model_name = model_name
+        self.model_version = model_version
+        self.outputs = infer_outputs
+        self.parameters = parameters or {}
+        self._use_binary_outputs = use_binary_outputs
+        self._requested_outputs = requested_outputs
+
+    def get_output_by_name(self, name: str) -> Optional[InferOutput]:
+        for o in self.outputs:
+            if o.name == name:
+                return o
+        return None
+
+    def to_rest(self) -> Tuple[Union[bytes, Dict], Optional[int]]:
+        """infer_type.py:1328-1404: dict, or JSON header + raw tensors when binary outputs were requested."""
+        want = {o.name: o for o in (self._requested_outputs or [])}
+        raws: List[bytes] = []
+        outs = []
+        for o in self.outputs:
+            if want and o.name not in want:
+                continue
+            binary = self._use_binary_outputs
+            if o.name in want and want[o.name].binary_data is not None:
+                binary = bool(want[o.name].binary_data)
+            outs.append(o._to_dict(binary, raws))
+        res: Dict[str, Any] = {"id": self.id, "model_name": self.model_name, "model_version": self.model_version, "outputs": outs}
+        if self.parameters:
+            res["parameters"] = self.parameters
+        if raws:
+            j = json.dumps(res).encode()
+            return j + b"".join(bytes(r) for r in raws), len(j)
+        return res, None
+
+
+def get_predict_input(payload: Union[Dict, InferRequest]):
+    """kserve/utils/utils.py:149-192 — V1 dict ``instances`` or V2 InferRequest -> numpy."""
+    if isinstance(payload, dict):
+        inst = payload["inputs"] if "inputs" in payload else payload["instances"]
+        return np.array(inst)
+    if isinstance(payload, InferRequest):
+        if len(payload.inputs) == 1:
+            return payload.inputs[0].as_numpy()
+        return {i.name: i.as_numpy() for i in payload.inputs}
+    raise InvalidInput(f"unsupported payload type {type(payload)}")
+
+
+def get_predict_response(payload, result: Union[np.ndarray, Dict[str, np.ndarray]], model_name: str):
+    """kserve/utils/utils.py:194-254 — numpy -> V1 dict or V2 InferResponse mirroring the request's encoding."""
+    if isinstance(payload, dict):
+        return {"predictions": result.tolist() if isinstance(result, np.ndarray) else result}
+    outs = []
+    items = result.items() if isinstance(result, dict) else [("output-0", result)]
+    for name, arr in items:
+        o = InferOutput(name, list(arr.shape), from_np_dtype(arr.dtype))
+        o.data = arr
+        outs.append(o)
+    return InferResponse(response_id=payload.id or str(uuid.uuid4()), model_name=model_name, infer_outputs=outs,
+                         use_binary_outputs=payload.use_binary_outputs, requested_outputs=payload.request_outputs)
