@@ -110,6 +110,31 @@ int b200_run_staged(b200_engine_t* e, int32_t do_prefill, int32_t decode_steps);
 int b200_run_staged_timed(b200_engine_t* e, int32_t decode_steps, float* prefill_ms, float* decode_ms);
 int b200_fetch_staged(b200_engine_t* e, int64_t* out_ids, int32_t* out_len, int32_t* stop_triggered);
 
+/* ---- batcher ----------------------------------------------------------------------------------------
+ * Replaces BatchHandler.batchPredict (pkg/batcher/handler.go:99-155).  rows[i] / row_lens[i] are the token
+ * ids of instance i of the formed batch (all waiting requests' instances, in arrival order); they are
+ * concatenated on the device, generated as ONE batch and returned as predictions[n_rows][max_new_tokens]
+ * (instance order, rows padded with pad_token_id after *n_generated tokens), so request r's answer is rows
+ * [first_r, first_r + count_r) exactly as handler.go:139-150 scatters them. */
+int b200_batch_predict(b200_engine_t* e, const int64_t* const* rows, const int32_t* row_lens, int32_t n_rows,
+                       const b200_gen_params_t* params, int64_t* predictions, int32_t* n_generated,
+                       int32_t* stop_triggered);
+
+/* The trigger / index bookkeeping of BatchHandler.batch (handler.go:157-188) as a clock-driven state machine
+ * (the host keeps its own concurrency: goroutines+channels in Go, asyncio in Python).
+ *   create: <=0 selects the reference defaults 32 instances / 5000 ms (handler.go:190-196).
+ *   add   : a request with n_instances arrived at now_us -> ticket (the `case req := <-channelIn` arm).
+ *   tick  : the check made after every select iteration (handler.go:180-186): fires when
+ *           instances >= max_batch_size, or whole ms since the first instance >= max_latency and > 0 waiting.
+ *           On fire returns the waiting requests (ticket, first index, count) and resets. */
+typedef struct b200_batcher b200_batcher_t;
+int b200_batcher_create(int32_t max_batch_size, int32_t max_latency_ms, b200_batcher_t** out);
+int b200_batcher_destroy(b200_batcher_t* b);
+int b200_batcher_config(b200_batcher_t* b, int32_t* max_batch_size, int32_t* max_latency_ms);
+int b200_batcher_add(b200_batcher_t* b, int64_t now_us, int32_t n_instances, int64_t* ticket);
+int b200_batcher_tick(b200_batcher_t* b, int64_t now_us, int32_t cap, int64_t* tickets, int32_t* first,
+                      int32_t* count, int32_t* n_requests, int32_t* total_instances);
+
 /* ---- single kernels on caller-provided device pointers (unit tests / micro-benchmarks) ------------- */
 /* D = A[M,K] * B[N,K]^T, bf16, fp32 accumulate. epi: 0 store, 1 store+residual, 2 swiglu (B rows
  * interleaved 16 gate/16 up), 3 transposed store, 4 transposed swiglu (A rows interleaved),

@@ -71,6 +71,12 @@ def load() -> C.CDLL:
     lib.b200_op_rope_kv.argtypes = [vp, i64, vp, i64, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int,
                                     C.c_int, vp]
     lib.b200_op_argmax.argtypes = [vp, i64, C.c_int, C.c_int, vp, vp, vp]
+    lib.b200_batch_predict.argtypes = [vp, vp, vp, i32, C.POINTER(GenParams), vp, C.POINTER(i32), C.POINTER(i32)]
+    lib.b200_batcher_create.argtypes = [i32, i32, C.POINTER(vp)]
+    lib.b200_batcher_destroy.argtypes = [vp]
+    lib.b200_batcher_config.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    lib.b200_batcher_add.argtypes = [vp, i64, i32, C.POINTER(i64)]
+    lib.b200_batcher_tick.argtypes = [vp, i64, i32, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     _lib = lib
     return lib
 

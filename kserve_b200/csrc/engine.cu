@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/kserve_b200.h"
+#include "batcher.cuh"
 #include "launch.cuh"
 
 namespace b200 {
@@ -116,6 +117,10 @@ struct b200_engine {
           *d_stop_tok = nullptr, *d_stop_off = nullptr;
   StepState* d_state = nullptr;
   int out_ld = 0;
+  // raw request staging (device-side concat/pad)
+  long long *d_raw_ids = nullptr, *d_raw_mask = nullptr, *d_pred = nullptr;
+  int32_t *d_flat = nullptr, *d_offs = nullptr;
+  long long *h_raw = nullptr, *h_pred = nullptr;
   // pinned staging
   int32_t* h_stage = nullptr;
   size_t h_stage_elems = 0;
@@ -131,6 +136,7 @@ struct b200_engine {
     bool forced = false;
     bool prefilled = false;
   } st;
+  bool staged_mask = false;
   // graphs per batch size
   std::unordered_map<int, cudaGraphExec_t> graphs;
   std::unordered_map<int, int> graph_nodes;
@@ -356,67 +362,35 @@ static int decode_step(b200_engine* e, bool use_graph) {
   return 0;
 }
 
-static int stage_prompt(b200_engine* e, const int64_t* ids, const int64_t* mask, int B, int S,
-                        const b200_gen_params_t* gp) {
+// Validates the request, sizes the KV pages and resets the per-request device state.  `lens` are the real
+// (un-padded) sequence lengths; S is the padded prompt width (0 for ragged batcher input).
+static int stage_common(b200_engine* e, int B, int S, const std::vector<int>& lens, const b200_gen_params_t* gp) {
   B200_REQUIRE(e->finalized, "weights not finalized");
   B200_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch size out of range");
   B200_REQUIRE(gp->max_new_tokens >= 1, "max_new_tokens must be >= 1");
-  B200_REQUIRE(S >= 1 && S + gp->max_new_tokens <= e->cfg.max_seq_len, "prompt + max_new_tokens exceeds max_seq_len");
-  B200_REQUIRE(S + gp->max_new_tokens <= e->cfg.max_position, "exceeds rope table");
   B200_REQUIRE(gp->num_eos <= 16 && gp->num_stop <= 16, "too many eos / stop sequences");
   auto& st = e->st;
-  st.B = B; st.S = S; st.max_new = gp->max_new_tokens; st.lens.assign(B, 0);
-  st.input.assign(ids, ids + (size_t)B * S);
+  st.B = B; st.S = S; st.max_new = gp->max_new_tokens; st.lens = lens;
   st.pad = (int32_t)gp->pad_token_id; st.num_eos = gp->num_eos; st.num_stop = gp->num_stop;
   st.forced = gp->forced_tokens != nullptr; st.prefilled = false;
   int T = 0, max_len = 0;
   for (int b = 0; b < B; ++b) {
-    int first = 0;
-    if (mask) {
-      while (first < S && mask[(size_t)b * S + first] == 0) ++first;
-      for (int i = first; i < S; ++i)
-        B200_REQUIRE(mask[(size_t)b * S + i] != 0, "attention_mask must be left padding only");
-    }
-    B200_REQUIRE(first < S, "empty sequence");
-    st.lens[b] = S - first;
-    T += st.lens[b];
-    max_len = std::max(max_len, st.lens[b]);
+    B200_REQUIRE(lens[b] >= 1, "empty sequence");
+    T += lens[b];
+    max_len = std::max(max_len, lens[b]);
   }
+  const int width = std::max(S, max_len);
+  B200_REQUIRE(width + gp->max_new_tokens <= e->cfg.max_seq_len, "prompt + max_new_tokens exceeds max_seq_len");
+  B200_REQUIRE(width + gp->max_new_tokens <= e->cfg.max_position, "exceeds rope table");
   B200_REQUIRE(T <= e->cap_T, "packed prompt tokens exceed max_prefill_tokens");
   st.T = T; st.max_len = max_len;
   // page allocation: sequence b owns a contiguous run of pages (fresh allocator per call)
-  const int per_seq = (S + gp->max_new_tokens + kPageTokens - 1) / kPageTokens;
+  const int per_seq = (width + gp->max_new_tokens + kPageTokens - 1) / kPageTokens;
   B200_REQUIRE(per_seq <= e->max_pages && (long long)per_seq * B <= e->num_pages, "KV page pool too small");
   std::fill(e->h_page_table.begin(), e->h_page_table.end(), 0);
   for (int b = 0; b < B; ++b)
     for (int i = 0; i < per_seq; ++i) e->h_page_table[(size_t)b * e->max_pages + i] = b * per_seq + i;
-  // pack host staging: tok | tok_seq | tok_pos | cu | seq_slot | last_rows | cur_len | dec_pos | finished
-  int32_t* h = e->h_stage;
-  int32_t *h_tok = h, *h_seq = h + e->cap_T, *h_pos = h + 2 * e->cap_T, *h_misc = h + 3 * e->cap_T;
-  int32_t *h_cu = h_misc, *h_slot = h_cu + 80, *h_last = h_slot + 80, *h_len = h_last + 80, *h_dpos = h_len + 80,
-          *h_fin = h_dpos + 80;
-  int t = 0;
-  for (int b = 0; b < B; ++b) {
-    h_cu[b] = t;
-    const int first = S - st.lens[b];
-    for (int i = 0; i < st.lens[b]; ++i, ++t) {
-      h_tok[t] = (int32_t)ids[(size_t)b * S + first + i];
-      h_seq[t] = b;
-      h_pos[t] = i;
-    }
-    h_slot[b] = b; h_last[b] = t - 1; h_len[b] = st.lens[b]; h_dpos[b] = st.lens[b]; h_fin[b] = 0;
-  }
-  h_cu[B] = t;
   cudaStream_t s = e->stream;
-  B200_CUDA_OK(cudaMemcpyAsync(e->d_tok, h_tok, T * 4, cudaMemcpyHostToDevice, s));
-  B200_CUDA_OK(cudaMemcpyAsync(e->d_tok_seq, h_seq, T * 4, cudaMemcpyHostToDevice, s));
-  B200_CUDA_OK(cudaMemcpyAsync(e->d_tok_pos, h_pos, T * 4, cudaMemcpyHostToDevice, s));
-  B200_CUDA_OK(cudaMemcpyAsync(e->d_cu, h_cu, (B + 1) * 4, cudaMemcpyHostToDevice, s));
-  B200_CUDA_OK(cudaMemcpyAsync(e->d_seq_slot, h_slot, B * 4, cudaMemcpyHostToDevice, s));
-  B200_CUDA_OK(cudaMemcpyAsync(e->d_last_rows, h_last, B * 4, cudaMemcpyHostToDevice, s));
-  B200_CUDA_OK(cudaMemcpyAsync(e->d_cur_len, h_len, B * 4, cudaMemcpyHostToDevice, s));
-  B200_CUDA_OK(cudaMemcpyAsync(e->d_dec_pos, h_dpos, B * 4, cudaMemcpyHostToDevice, s));
-  B200_CUDA_OK(cudaMemcpyAsync(e->d_finished, h_fin, B * 4, cudaMemcpyHostToDevice, s));
   B200_CUDA_OK(cudaMemcpyAsync(e->d_page_table, e->h_page_table.data(), e->h_page_table.size() * 4, cudaMemcpyHostToDevice, s));
   // eos / stop / forced
   std::vector<int32_t> tmp;
@@ -442,6 +416,68 @@ static int stage_prompt(b200_engine* e, const int64_t* ids, const int64_t* mask,
   StepState init{0, 0, 0, gp->max_new_tokens};
   *e->h_state = init;
   B200_CUDA_OK(cudaMemcpyAsync(e->d_state, e->h_state, sizeof(StepState), cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+static PackOut pack_out(b200_engine* e) {
+  return PackOut{e->d_tok, e->d_tok_seq, e->d_tok_pos, e->d_cu, e->d_seq_slot, e->d_last_rows, e->d_cur_len, e->d_dec_pos, e->d_finished};
+}
+
+// Padded [B][S] ids (+ left-padding mask) as they arrive on the OpenAI / V2 legs: the raw rows are copied to
+// the device once and concatenated into the packed layout by pack_padded_kernel.
+static int stage_prompt(b200_engine* e, const int64_t* ids, const int64_t* mask, int B, int S,
+                        const b200_gen_params_t* gp) {
+  B200_REQUIRE(B >= 1 && B <= e->cfg.max_batch && S >= 1 && S <= e->cfg.max_seq_len, "bad batch shape");
+  std::vector<int> lens(B, S);
+  if (mask) {
+    for (int b = 0; b < B; ++b) {
+      int first = 0;
+      while (first < S && mask[(size_t)b * S + first] == 0) ++first;
+      for (int i = first; i < S; ++i)
+        B200_REQUIRE(mask[(size_t)b * S + i] != 0, "attention_mask must be left padding only");
+      lens[b] = S - first;
+    }
+  }
+  int rc = stage_common(e, B, S, lens, gp);
+  if (rc) return rc;
+  e->staged_mask = mask != nullptr;
+  e->st.input.assign(ids, ids + (size_t)B * S);
+  cudaStream_t s = e->stream;
+  const size_t n = (size_t)B * S;
+  memcpy(e->h_raw, ids, n * 8);
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_raw_ids, e->h_raw, n * 8, cudaMemcpyHostToDevice, s));
+  if (mask) {
+    memcpy(e->h_raw + n, mask, n * 8);
+    B200_CUDA_OK(cudaMemcpyAsync(e->d_raw_mask, e->h_raw + n, n * 8, cudaMemcpyHostToDevice, s));
+  }
+  pack_padded_kernel<<<1, 1024, 0, s>>>(e->d_raw_ids, mask ? e->d_raw_mask : nullptr, B, S, pack_out(e));
+  B200_CUDA_OK(cudaGetLastError());
+  e->launches++;
+  return 0;
+}
+
+// Ragged rows as the batcher hands them over (one row per instance of every waiting request).
+static int stage_ragged(b200_engine* e, const int64_t* const* rows, const int32_t* row_lens, int B,
+                        const b200_gen_params_t* gp) {
+  B200_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch size out of range");
+  std::vector<int> lens(row_lens, row_lens + B);
+  int rc = stage_common(e, B, 0, lens, gp);
+  if (rc) return rc;
+  e->st.input.clear();
+  int32_t* flat = reinterpret_cast<int32_t*>(e->h_raw);
+  int32_t* offs = flat + e->cap_T;
+  int t = 0;
+  for (int b = 0; b < B; ++b) {
+    offs[b] = t;
+    for (int i = 0; i < lens[b]; ++i) flat[t++] = (int32_t)rows[b][i];
+  }
+  offs[B] = t;
+  cudaStream_t s = e->stream;
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_flat, flat, (size_t)t * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_offs, offs, (size_t)(B + 1) * 4, cudaMemcpyHostToDevice, s));
+  pack_ragged_kernel<<<1, 1024, 0, s>>>(e->d_flat, e->d_offs, B, pack_out(e));
+  B200_CUDA_OK(cudaGetLastError());
+  e->launches++;
   return 0;
 }
 
@@ -614,6 +650,17 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_stage), e->h_stage_elems * 4));
   B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_state), sizeof(StepState)));
   B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_out_tokens), (size_t)c->max_batch * e->out_ld * 4));
+  {
+    const size_t raw = (size_t)c->max_batch * c->max_seq_len;
+    if ((rc = dmalloc(&e->d_raw_ids, raw))) return rc;
+    if ((rc = dmalloc(&e->d_raw_mask, raw))) return rc;
+    if ((rc = dmalloc(&e->d_pred, raw))) return rc;
+    if ((rc = dmalloc(&e->d_flat, T))) return rc;
+    if ((rc = dmalloc(&e->d_offs, 80))) return rc;
+    const size_t hraw = std::max(2 * raw, (T + 80) / 2 + 1);
+    B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_raw), hraw * 8));
+    B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_pred), raw * 8));
+  }
   if (tp > 1) {
     Nccl& n = Nccl::get();
     B200_REQUIRE(n.ok, "tp_size > 1 needs libnccl.so.2");
@@ -761,12 +808,13 @@ int b200_run_staged(b200_engine_t* e, int32_t do_prefill, int32_t decode_steps) 
   B200_CUDA_OK(cudaSetDevice(e->cfg.device));
   int rc;
   if (do_prefill) {
-    // reset the per-request device state so the same staged prompt can be replayed
+    // reset the per-request device state so the same staged prompt can be replayed: the raw rows are still
+    // resident on the device, so this re-runs the device-side concat and nothing crosses PCIe
     auto& st = e->st;
-    int32_t* h = e->h_stage + 3 * e->cap_T;
-    B200_CUDA_OK(cudaMemcpyAsync(e->d_cur_len, h + 240, st.B * 4, cudaMemcpyHostToDevice, e->stream));
-    B200_CUDA_OK(cudaMemcpyAsync(e->d_dec_pos, h + 320, st.B * 4, cudaMemcpyHostToDevice, e->stream));
-    B200_CUDA_OK(cudaMemcpyAsync(e->d_finished, h + 400, st.B * 4, cudaMemcpyHostToDevice, e->stream));
+    if (st.S > 0) pack_padded_kernel<<<1, 1024, 0, e->stream>>>(e->d_raw_ids, e->staged_mask ? e->d_raw_mask : nullptr, st.B, st.S, pack_out(e));
+    else pack_ragged_kernel<<<1, 1024, 0, e->stream>>>(e->d_flat, e->d_offs, st.B, pack_out(e));
+    B200_CUDA_OK(cudaGetLastError());
+    e->launches++;
     StepState init{0, 0, 0, st.max_new};
     *e->h_state = init;
     B200_CUDA_OK(cudaMemcpyAsync(e->d_state, e->h_state, sizeof(StepState), cudaMemcpyHostToDevice, e->stream));
@@ -843,8 +891,11 @@ int b200_generate(b200_engine_t* e, const int64_t* ids, const int64_t* mask, int
       if ((rc = decode_step(e, !eager))) return rc;
       ++steps;
       ar = after_step(i);
-      if (ar) break;
-      if (!cb && (i % 8) == 0) {  // poll the device-side done flag without a per-token sync
+      // under TP every rank must leave the loop at the same step (the next step contains collectives), so the
+      // only exit points are the shared polling cadence below; a streaming leader just stops receiving tokens.
+      if (ar && e->cfg.tp_size == 1) break;
+      if (ar && e->cfg.tp_size > 1) ar = 0;
+      if ((!cb || e->cfg.tp_size > 1) && (i % 8) == 0) {  // poll the device-side done flag without a per-token sync
         B200_CUDA_OK(cudaMemcpyAsync(e->h_state, e->d_state, sizeof(StepState), cudaMemcpyDeviceToHost, s));
         B200_CUDA_OK(cudaStreamSynchronize(s));
         if (e->h_state->done) break;
@@ -858,6 +909,84 @@ int b200_generate(b200_engine_t* e, const int64_t* ids, const int64_t* mask, int
   e->timing.decode_steps = steps;
   e->timing.kernel_launches = e->launches;
   return ar == 1 ? 1 : 0;
+}
+
+// Replaces the body of BatchHandler.batchPredict (pkg/batcher/handler.go:99-155): the instances of every
+// waiting request (ragged token rows) are concatenated ON DEVICE, generated in one batch, and the predictions
+// come back as one [n_rows][max_new_tokens] matrix in instance order, so each request's answer is the
+// contiguous slice [first, first+count) the batcher recorded (handler.go:139-150).
+int b200_batch_predict(b200_engine_t* e, const int64_t* const* rows, const int32_t* row_lens, int32_t n_rows,
+                       const b200_gen_params_t* gp, int64_t* predictions, int32_t* n_generated,
+                       int32_t* stop_triggered) {
+  B200_REQUIRE(e && rows && row_lens && gp && predictions && n_generated, "null argument");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = e->stream;
+  e->launches = 0;
+  B200_CUDA_OK(cudaEventRecord(e->ev0, s));
+  int rc = stage_ragged(e, rows, row_lens, n_rows, gp);
+  if (rc) return rc;
+  if ((rc = prefill(e))) return rc;
+  e->st.prefilled = true;
+  B200_CUDA_OK(cudaEventRecord(e->ev1, s));
+  int steps = 0;
+  for (int i = 1; i < gp->max_new_tokens; ++i) {
+    if ((rc = decode_step(e, true))) return rc;
+    ++steps;
+    if ((i % 8) == 0) {
+      B200_CUDA_OK(cudaMemcpyAsync(e->h_state, e->d_state, sizeof(StepState), cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaStreamSynchronize(s));
+      if (e->h_state->done) break;
+    }
+  }
+  B200_CUDA_OK(cudaEventRecord(e->ev2, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->h_state, e->d_state, sizeof(StepState), cudaMemcpyDeviceToHost, s));
+  B200_CUDA_OK(cudaStreamSynchronize(s));
+  const int T = e->h_state->step;
+  scatter_predictions_kernel<<<n_rows, 128, 0, s>>>(e->d_out_tokens, e->out_ld, n_rows, T, e->d_pred);
+  B200_CUDA_OK(cudaGetLastError());
+  e->launches++;
+  B200_CUDA_OK(cudaMemcpyAsync(e->h_pred, e->d_pred, (size_t)n_rows * T * 8, cudaMemcpyDeviceToHost, s));
+  B200_CUDA_OK(cudaStreamSynchronize(s));
+  for (int b = 0; b < n_rows; ++b)
+    for (int i = 0; i < gp->max_new_tokens; ++i)
+      predictions[(size_t)b * gp->max_new_tokens + i] = i < T ? e->h_pred[(size_t)b * T + i] : gp->pad_token_id;
+  *n_generated = T;
+  if (stop_triggered) *stop_triggered = e->h_state->stop_triggered;
+  B200_CUDA_OK(cudaEventElapsedTime(&e->timing.prefill_ms, e->ev0, e->ev1));
+  B200_CUDA_OK(cudaEventElapsedTime(&e->timing.decode_ms, e->ev1, e->ev2));
+  e->timing.decode_steps = steps;
+  e->timing.kernel_launches = e->launches;
+  return 0;
+}
+
+// ---- batcher trigger state machine (pkg/batcher/handler.go:157-199) ---------------------------------
+struct b200_batcher { BatcherCore core; b200_batcher(int a, int b) : core(a, b) {} };
+
+int b200_batcher_create(int32_t max_batch_size, int32_t max_latency_ms, b200_batcher_t** out) {
+  B200_REQUIRE(out, "null argument");
+  *out = new b200_batcher(max_batch_size, max_latency_ms);
+  return 0;
+}
+int b200_batcher_destroy(b200_batcher_t* b) { delete b; return 0; }
+int b200_batcher_config(b200_batcher_t* b, int32_t* max_batch_size, int32_t* max_latency_ms) {
+  B200_REQUIRE(b && max_batch_size && max_latency_ms, "null argument");
+  *max_batch_size = b->core.max_batch_size; *max_latency_ms = b->core.max_latency_ms;
+  return 0;
+}
+int b200_batcher_add(b200_batcher_t* b, int64_t now_us, int32_t n_instances, int64_t* ticket) {
+  B200_REQUIRE(b && ticket, "null argument");
+  B200_REQUIRE(n_instances >= 1, "no instances in the request");
+  *ticket = b->core.add(now_us, n_instances);
+  return 0;
+}
+int b200_batcher_tick(b200_batcher_t* b, int64_t now_us, int32_t cap, int64_t* tickets, int32_t* first,
+                      int32_t* count, int32_t* n_requests, int32_t* total_instances) {
+  B200_REQUIRE(b && tickets && first && count && n_requests && total_instances, "null argument");
+  long long* tk = reinterpret_cast<long long*>(tickets);
+  const int n = b->core.tick(now_us, tk, first, count, cap, total_instances);
+  B200_REQUIRE(n >= 0, "ticket buffer too small");
+  *n_requests = n;
+  return 0;
 }
 
 int b200_engine_last_timing(b200_engine_t* e, b200_timing_t* out) {

@@ -158,6 +158,21 @@ class B200Engine:
                               prefill_ms=tm.prefill_ms, decode_ms=tm.decode_ms, decode_steps=tm.decode_steps,
                               kernel_launches=tm.kernel_launches)
 
+    # ------------------------------------------------------------------ batcher leg (ragged rows, no padding)
+    def batch_predict(self, rows: Sequence[Sequence[int]], *, max_new_tokens: int, pad_token_id: Optional[int] = 0,
+                      eos_token_ids: Sequence[int] = (), stop_sequences: Sequence[Sequence[int]] = ()):
+        """-> (predictions int64 [n_rows, T], stop_triggered). Rows are concatenated on the device."""
+        n = len(rows)
+        arrs = [(C.c_int64 * len(r))(*[int(t) for t in r]) for r in rows]
+        ptrs = (C.c_void_p * n)(*[C.cast(a, C.c_void_p) for a in arrs])
+        lens = (C.c_int32 * n)(*[len(r) for r in rows])
+        gp, keep = self._params(max_new_tokens, pad_token_id, eos_token_ids, stop_sequences, None)
+        pred = torch.empty((n, max_new_tokens), dtype=torch.int64)
+        ngen, stop = C.c_int32(0), C.c_int32(0)
+        _lib.check(self.lib.b200_batch_predict(self.h, ptrs, lens, n, C.byref(gp), pred.data_ptr(), C.byref(ngen),
+                                               C.byref(stop)), "b200_batch_predict")
+        return pred[:, :ngen.value].clone(), bool(stop.value)
+
     # ------------------------------------------------------------------ device-resident replay (bench)
     def stage(self, input_ids, attention_mask=None, *, max_new_tokens: int, pad_token_id: int = 0):
         ids = torch.as_tensor(input_ids, dtype=torch.int64).contiguous()

@@ -186,6 +186,9 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         return self.ready
 
     def stop(self):
+        if self.tp_size > 1 and self.tp_rank == 0 and self._engine is not None:
+            from .tp import leader_call
+            leader_call("stop", (), {})
         self._request_queue.put(None)    # :273-277
         if self._thread is not None:
             self._thread.join(timeout=5)
@@ -222,6 +225,14 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
             loop.call_soon_threadsafe(_set)
         self._request_queue.put((fn, done))
         return await fut
+
+    def _generate(self, ids, mask, streamer=None, **kw) -> GenerateResult:
+        """The call that replaces `self._model.generate(**kwargs)` (:314, :328).  Under TP the leader first
+        replicates the call to the follower ranks (they run it without the streamer)."""
+        if self.tp_size > 1:
+            from .tp import leader_call
+            leader_call("generate", (ids, mask), kw)
+        return self._engine.generate(ids, mask, streamer=streamer, **kw)
 
     # ------------------------------------------------------------------ request validation (:376-402)
     def validate_supported_completion_params(self, request: CompletionRequest):
@@ -312,7 +323,7 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                         if piece != "":                         # empty pieces are dropped (:317-319)
                             put(piece)
                         return False
-                    r = self._engine.generate(ids, mask, streamer=on_step, **common)
+                    r = self._generate(ids, mask, streamer=on_step, **common)
                     stop_state["triggered"] = r.stop_triggered
                     self._observe(r, B)
                     piece = detok.end()
@@ -332,7 +343,7 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                 yield "data: [DONE]\n\n"
             return stream_results()
 
-        r: GenerateResult = await self._submit(lambda: self._engine.generate(ids, mask, **common))
+        r: GenerateResult = await self._submit(lambda: self._generate(ids, mask, **common))
         self._observe(r, B)
         output_start = 0 if echo else S                        # :324-327
         stats.num_generation_tokens = r.num_generated * B      # :329-335 (every row counts the same length)
@@ -439,7 +450,7 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
             raise InvalidInput(f"batch of {B} exceeds this engine's max batch {self.max_batch}")
         if S + max_tokens > self.max_length:
             raise InvalidInput(f"prompt ({S}) + max_tokens ({max_tokens}) exceeds the model's maximum context length {self.max_length}")
-        r: GenerateResult = await self._submit(lambda: self._engine.generate(
+        r: GenerateResult = await self._submit(lambda: self._generate(
             ids, mask, max_new_tokens=max_tokens, pad_token_id=self._pad_token_id, eos_token_ids=self.eos_token_ids))
         self._observe(r, B)
         gen = r.output_ids[:, S:]
