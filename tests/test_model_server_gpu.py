@@ -70,13 +70,19 @@ def test_context_length_error_text(served):
 
 def test_stop_string_sets_finish_reason_stop(served):
     client, model, tok, c = served
-    full = client.post("/openai/v1/completions", json={"model": "tiny", "prompt": "KServe on B200!", "max_tokens": 12}).json()
-    text = full["choices"][0]["text"]
-    stop = text[3:5]
-    j = client.post("/openai/v1/completions", json={"model": "tiny", "prompt": "KServe on B200!", "max_tokens": 12, "stop": stop}).json()
+    prompt = "KServe on B200!"
+    ids = client.post("/v1/models/tiny:predict", json={"instances": [tok.encode(prompt)], "parameters": {"max_tokens": 12}}).json()["predictions"][0]
+    full = client.post("/openai/v1/completions", json={"model": "tiny", "prompt": prompt, "max_tokens": 12}).json()
+    # a stop string must survive decode -> encode (random weights emit arbitrary bytes): find such a token pair
+    pos = next((i for i in range(1, 10) if tok.encode(tok.decode(ids[i:i + 2]), add_special_tokens=False) == ids[i:i + 2]
+                and ids[i:i + 2] not in [ids[k:k + 2] for k in range(i)]), None)
+    if pos is None:
+        pytest.skip("no round-trippable token pair in this sample")
+    stop = tok.decode(ids[pos:pos + 2])
+    j = client.post("/openai/v1/completions", json={"model": "tiny", "prompt": prompt, "max_tokens": 12, "stop": stop}).json()
     assert j["choices"][0]["finish_reason"] == "stop"
-    assert j["choices"][0]["text"] == text[: text.index(stop) + len(stop)]
-    assert j["usage"]["completion_tokens"] < full["usage"]["completion_tokens"]
+    assert j["usage"]["completion_tokens"] == pos + 2 < full["usage"]["completion_tokens"]
+    assert j["choices"][0]["text"] == tok.decode(ids[:pos + 2], skip_special_tokens=True)
 
 
 def test_streaming_and_chat(served):

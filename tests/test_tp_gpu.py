@@ -10,35 +10,18 @@ from helpers import load_case, logits_tol
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, ret):
-    import torch.distributed as dist
-    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    from kserve_b200.engine import B200Engine
-    from kserve_b200.tp import broadcast_nccl_id
-    from oracle import weights as W
-    nccl_id = broadcast_nccl_id(rank)
-    for name in ("tiny_g4_ids", "tiny_g2_ids"):
-        c = load_case(name)
-        m = c["meta"]
-        eng = B200Engine(W.CONFIGS[m["cfg"]], max_batch=8, max_seq_len=512, device=rank, tp_rank=rank, tp_size=world, nccl_id=nccl_id)
-        eng.load_weights(W.iter_state_dict(W.CONFIGS[m["cfg"]], m["seed"]))
-        r = eng.generate(c["input_ids"], None, max_new_tokens=c["T"], pad_token_id=m["pad_token_id"])
-        r2 = eng.generate(c["input_ids"], None, max_new_tokens=c["T"], pad_token_id=m["pad_token_id"], forced_tokens=c["gen"])
-        if rank == 0:
-            ret[name] = r.output_ids
-            ret[name + ":forced"] = r2.output_ids
-        eng.close()
-        dist.barrier()
-    dist.destroy_process_group()
-
-
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_tp2_matches_oracle_fixture():
-    import torch.multiprocessing as mp
-    ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, 29633, ret), nprocs=2, join=True)
+    import json
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29633", os.path.join(here, "tp_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("TPRESULT ")][0]
+    ret = {k: torch.tensor(v) for k, v in json.loads(line[len("TPRESULT "):]).items()}
     for name in ("tiny_g4_ids", "tiny_g2_ids"):
         c = load_case(name)
         tol = logits_tol(c["step_logits"])
