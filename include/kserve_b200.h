@@ -156,6 +156,11 @@ int b200_op_rope_kv(const void* qkv, int64_t ld, void* q_out, int64_t ldq, void*
                     const void* cos_tab, const void* sin_tab, int T, int nh, int nkv, void* stream);
 int b200_op_argmax(const void* logits, int64_t ld, int B, int V, float* out_val, int32_t* out_idx, void* stream);
 
+/* Debug timeline: capacity > 0 enables per-CTA {t0, t1 (globaltimer ns), kind, block} records (24 bytes each),
+ * 0 disables; read drains up to `capacity` records into `out`. */
+int b200_debug_trace(int32_t capacity);
+int b200_debug_trace_read(void* out, int32_t capacity, int32_t* n);
+
 const char* b200_last_error(void);
 const char* b200_version(void);
 

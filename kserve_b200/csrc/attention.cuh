@@ -43,6 +43,9 @@ struct AttnPrefillParams {
 };
 
 __global__ void __launch_bounds__(kAttnThreads) attn_prefill_kernel(const AttnPrefillParams p) {
+  TraceScope _ts(TK_ATTN_PREFILL);
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
   const int tok0 = p.cu_seqlens[b];
@@ -194,6 +197,9 @@ struct AttnDecodeParams {
 };
 
 __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDecodeParams p) {
+  TraceScope _ts(TK_ATTN_DECODE);
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int bh = blockIdx.x, split = blockIdx.y;
   const int b = bh / p.nkv, kvh = bh - b * p.nkv;
@@ -345,6 +351,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
 __global__ void __launch_bounds__(128)
 attn_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, bf16* __restrict__ out,
                     long long ldo, int nkv, int G, int splits) {
+  TraceScope _ts(TK_ATTN_COMBINE);
+  pdl_launch_dependents();
+  pdl_wait();
   const int bhq = blockIdx.x;            // b * nh + head
   const int nh = nkv * G;
   const int b = bhq / nh, head = bhq - b * nh;

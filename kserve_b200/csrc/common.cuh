@@ -76,6 +76,46 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Optional per-CTA timeline (debug): when enabled through b200_debug_trace(), thread 0 of every CTA appends
+// {kind, block, globaltimer at entry, at exit}; off by default (one predictable branch per CTA).
+// ---------------------------------------------------------------------------------------------
+struct TraceRec { unsigned long long t0, t1; int kind, block; };
+__device__ TraceRec* g_trace_buf = nullptr;
+__device__ unsigned int g_trace_cap = 0;
+__device__ unsigned int g_trace_cnt = 0;
+enum TraceKind : int { TK_GEMM = 1, TK_RMSNORM = 2, TK_ROPE = 3, TK_ATTN_DECODE = 4, TK_ATTN_COMBINE = 5, TK_ARGMAX = 6,
+                       TK_STEP = 7, TK_EMBED = 8, TK_ATTN_PREFILL = 9, TK_OTHER = 10 };
+__device__ __forceinline__ unsigned long long global_timer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct TraceScope {
+  unsigned long long t0 = 0;
+  int kind;
+  __device__ __forceinline__ explicit TraceScope(int k) : kind(k) {
+    if (threadIdx.x == 0 && g_trace_buf != nullptr) t0 = global_timer();
+  }
+  __device__ __forceinline__ ~TraceScope() {
+    if (threadIdx.x == 0 && t0 != 0) {
+      const unsigned int i = atomicAdd(&g_trace_cnt, 1u);
+      if (i < g_trace_cap) {
+        TraceRec r; r.t0 = t0; r.t1 = global_timer(); r.kind = kind; r.block = blockIdx.x;
+        g_trace_buf[i] = r;
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel lets its successor start (prologue, weight prefetch) while it is
+// still running, and blocks only where it first touches data the predecessor produced.  Both are no-ops when
+// the kernel was launched without the programmatic-stream-serialization attribute.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

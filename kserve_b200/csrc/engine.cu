@@ -175,8 +175,8 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
   const float scale_log2 = (1.0f / sqrtf((float)kHeadDim)) * 1.4426950408889634f;
   const bool tp = e->cfg.tp_size > 1;
   int rc;
-  embed_gather_kernel<<<T, 128, 0, s>>>(decode ? e->d_next_tok : e->d_tok, e->embed, e->x, H, e->V);
-  B200_CUDA_OK(cudaGetLastError());
+  pdl_phase() = decode;
+  B200_CUDA_OK(launch_k(embed_gather_kernel, dim3(T), dim3(128), 0, s, (const int32_t*)(decode ? e->d_next_tok : e->d_tok), (const bf16*)e->embed, e->x, H, e->V));
   e->launches++;
   if ((rc = launch_rmsnorm(0, e->x, e->layers[0].ln1, e->xn, T, H, eps, nullptr, 0, 0, 0, nullptr, s))) return rc;
   e->launches++;
@@ -206,8 +206,7 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
     }
     rp.kcache = kc; rp.vcache = vc; rp.page_table = e->d_page_table; rp.max_pages = e->max_pages;
     rp.cos_tab = e->cos_tab; rp.sin_tab = e->sin_tab; rp.nh = e->nh; rp.nkv = e->nkv;
-    rope_kv_kernel<<<T, 256, 0, s>>>(rp);
-    B200_CUDA_OK(cudaGetLastError());
+    B200_CUDA_OK(launch_k(rope_kv_kernel, dim3(T), dim3(256), 0, s, rp));
     e->launches += 2;
     // ---- attention
     if (decode) {
@@ -215,8 +214,10 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
       ap.q = e->qdec; ap.ldq = e->nh * kHeadDim; ap.out = e->attn; ap.ldo = e->nh * kHeadDim;
       ap.kcache = kc; ap.vcache = vc; ap.page_table = e->d_page_table; ap.max_pages = e->max_pages;
       ap.seq_slot = e->d_seq_slot; ap.tok_pos = e->d_dec_pos; ap.nh = e->nh; ap.nkv = e->nkv; ap.G = e->G;
-      int splits = (2 * e->num_sms + B * e->nkv - 1) / (B * e->nkv);
-      ap.splits = std::max(1, std::min(splits, 8));
+      // one CTA per (sequence, kv head) already fills the machine at large batch; split the KV range only
+      // when there are fewer CTAs than SMs
+      const int ctas = B * e->nkv;
+      ap.splits = ctas >= e->num_sms ? 1 : std::max(1, std::min((e->num_sms + ctas - 1) / ctas, 8));
       ap.part_o = e->part_o; ap.part_ml = e->part_ml; ap.scale_log2 = scale_log2;
       if ((rc = launch_attn_decode(ap, B, s))) return rc;
       e->launches += ap.splits > 1 ? 2 : 1;
@@ -242,8 +243,7 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
             e->launches++;
             return 0;
           }
-          reduce_partials_kernel<<<T, 256, 0, s>>>(e->ws, sp, (long long)B * H, H, e->ybuf, H);
-          B200_CUDA_OK(cudaGetLastError());
+          B200_CUDA_OK(launch_k(reduce_partials_kernel, dim3(T), dim3(256), 0, s, (const float*)e->ws, sp, (long long)B * H, (long long)H, e->ybuf, H));
           e->launches++;
         } else {
           GemmArgs a{wmat, H, act, e->cap_T, H, B, K, EPI_T_STORE, bn, 1, e->ybuf, nullptr, H, 0, 0, true};
@@ -290,8 +290,7 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
   GemmArgs a{e->lm_head, e->Vl, rows_xn, rows_cap, e->Vl, B, e->H, EPI_T_STORE, pick_block_n(B), 1,
              e->logits, nullptr, e->Vl, 0, 0, true};
   if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
-  argmax_kernel<<<B, 1024, 0, s>>>(e->logits, e->Vl, e->Vl, e->v0, e->cand_val, e->cand_idx);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_k(argmax_kernel, dim3(B), dim3(1024), 0, s, (const bf16*)e->logits, (long long)e->Vl, e->Vl, e->v0, e->cand_val, e->cand_idx));
   e->launches += 2;
   const float* cv = e->cand_val;
   const int32_t* ci = e->cand_idx;
@@ -310,8 +309,7 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
   sp.eos = e->d_eos; sp.num_eos = e->st.num_eos; sp.pad_token = e->st.pad;
   sp.stop_tok = e->d_stop_tok; sp.stop_off = e->d_stop_off; sp.num_stop = e->st.num_stop;
   sp.st = e->d_state;
-  step_update_kernel<<<1, 128, 0, s>>>(sp);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_k(step_update_kernel, dim3(1), dim3(128), 0, s, sp));
   e->launches++;
   return 0;
 }
@@ -320,8 +318,7 @@ static int prefill(b200_engine* e) {
   auto& st = e->st;
   int rc;
   if ((rc = forward_layers(e, st.T, st.B, st.max_len, false))) return rc;
-  gather_rows_kernel<<<st.B, 128, 0, e->stream>>>(e->xn, e->d_last_rows, e->xl, e->H);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_k(gather_rows_kernel, dim3(st.B), dim3(128), 0, e->stream, (const bf16*)e->xn, (const int32_t*)e->d_last_rows, e->xl, e->H));
   e->launches++;
   return head_and_step(e, e->xl, e->cfg.max_batch, st.B);
 }
@@ -992,6 +989,30 @@ int b200_batcher_tick(b200_batcher_t* b, int64_t now_us, int32_t cap, int64_t* t
 int b200_engine_last_timing(b200_engine_t* e, b200_timing_t* out) {
   B200_REQUIRE(e && out, "null argument");
   *out = e->timing;
+  return 0;
+}
+
+// ---- debug timeline ---------------------------------------------------------------------------------
+static TraceRec* g_trace_dev = nullptr;
+int b200_debug_trace(int32_t capacity) {
+  if (g_trace_dev) { cudaFree(g_trace_dev); g_trace_dev = nullptr; }
+  TraceRec* nullp = nullptr;
+  unsigned int zero = 0, cap = (unsigned int)std::max(capacity, 0);
+  if (capacity > 0) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&g_trace_dev), sizeof(TraceRec) * capacity));
+  B200_CUDA_OK(cudaMemcpyToSymbol(g_trace_cnt, &zero, sizeof(zero)));
+  B200_CUDA_OK(cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap)));
+  B200_CUDA_OK(cudaMemcpyToSymbol(g_trace_buf, capacity > 0 ? &g_trace_dev : &nullp, sizeof(TraceRec*)));
+  return 0;
+}
+int b200_debug_trace_read(void* out, int32_t capacity, int32_t* n) {
+  B200_REQUIRE(out && n, "null argument");
+  B200_CUDA_OK(cudaDeviceSynchronize());
+  unsigned int cnt = 0, zero = 0;
+  B200_CUDA_OK(cudaMemcpyFromSymbol(&cnt, g_trace_cnt, sizeof(cnt)));
+  const int m = std::min<int>((int)cnt, capacity);
+  if (m > 0 && g_trace_dev) B200_CUDA_OK(cudaMemcpy(out, g_trace_dev, sizeof(TraceRec) * m, cudaMemcpyDeviceToHost));
+  B200_CUDA_OK(cudaMemcpyToSymbol(g_trace_cnt, &zero, sizeof(zero)));
+  *n = m;
   return 0;
 }
 

@@ -35,6 +35,7 @@ struct GemmParams {
   long long split_stride;  // EPI_T_PARTIAL: elements between split slices
   int out_cols;            // logical number of output columns (bounds for SWIGLU modes = N/2 resp. M/2)
   unsigned long long hint_a, hint_b;
+  int prefetch_a;          // A (weights) does not depend on the previous kernel: stream it before griddepcontrol.wait
 };
 
 constexpr int kGemmBlockM = 128;
@@ -58,6 +59,7 @@ template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
+  TraceScope _ts(TK_GEMM + 100 * EPI + 1000 * (p.M >> 7));
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -72,6 +74,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_units = p.m_tiles * p.n_tiles * p.splits;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -112,10 +115,31 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      bool first = true;
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
         int m_t, n_t, kb0, kb1;
         decode_unit(u, m_t, n_t, kb0, kb1);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        int kb = kb0;
+        if (first) {
+          first = false;
+          if (p.prefetch_a) {
+            // Weight tiles of the first k-blocks are requested before the previous kernel has finished; only the
+            // activation tiles wait for it.  (All stages are free at this point: no empty-barrier wait needed.)
+            const int npre = min(STAGES, kb1 - kb0);
+            for (int i = 0; i < npre; ++i) {
+              mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
+              tma_load_2d(smem + i * Cfg::kStageBytes, &tmap_a, &full_bar[i], (kb0 + i) * kGemmBlockK, m_t * kGemmBlockM, p.hint_a);
+            }
+            pdl_wait();
+            for (int i = 0; i < npre; ++i)
+              tma_load_2d(smem + i * Cfg::kStageBytes + Cfg::kABytes, &tmap_b, &full_bar[i], (kb0 + i) * kGemmBlockK, n_t * BLOCK_N, p.hint_b);
+            kb = kb0 + npre;
+            if (npre == STAGES) { stage = 0; phase = 1; } else { stage = npre; }
+          } else {
+            pdl_wait();
+          }
+        }
+        for (; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
@@ -163,6 +187,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    pdl_wait();              // outputs / residual must not be touched before the previous kernel is complete
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {

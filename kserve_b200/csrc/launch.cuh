@@ -67,6 +67,32 @@ struct TmapCache {
   }
 };
 
+// Every kernel of the forward path is launched with programmatic stream serialization so that its prologue
+// (and, for the weight-streaming GEMMs, its first weight tiles) overlaps the tail of its predecessor.
+// B200_NO_PDL=1 disables it (A/B measurement).
+inline bool pdl_enabled() {
+  static const bool v = getenv("B200_NO_PDL") == nullptr;
+  return v;
+}
+// set by the engine per phase: decode kernels are 5-50 us and benefit; the ms-scale prefill kernels do not
+// (early-launched successors only take SM slots away), measured r01: TTFT 410 -> 449 ms with PDL on.
+inline bool& pdl_phase() {
+  static bool v = false;
+  return v;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_enabled() && pdl_phase()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <int BLOCK_N, int EPI>
 int launch_gemm_inst(const CUtensorMap* ta, const CUtensorMap* tb, const GemmParams& p, int grid, cudaStream_t s) {
   auto kern = gemm_tn_kernel<BLOCK_N, EPI>;
@@ -75,8 +101,7 @@ int launch_gemm_inst(const CUtensorMap* ta, const CUtensorMap* tb, const GemmPar
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BLOCK_N>::kSmemBytes));
     configured = true;
   }
-  kern<<<grid, kGemmThreads, GemmCfg<BLOCK_N>::kSmemBytes, s>>>(*ta, *tb, p);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_k(kern, dim3(grid), dim3(kGemmThreads), GemmCfg<BLOCK_N>::kSmemBytes, s, *ta, *tb, p));
   return 0;
 }
 
@@ -108,6 +133,7 @@ inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStr
   p.out = a.out; p.residual = a.residual; p.ldo = a.ldo; p.split_stride = a.split_stride; p.out_cols = a.out_cols;
   p.hint_a = a.stream_a ? kEvictFirst : kEvictLast;
   p.hint_b = a.stream_a ? kEvictLast : kEvictNormal;
+  p.prefetch_a = a.stream_a ? 1 : 0;
   const int units = p.m_tiles * p.n_tiles * p.splits;
   const int grid = units < num_sms ? units : num_sms;
   B200_REQUIRE(p.splits == 1 || a.epi == EPI_T_PARTIAL, "split-K only with the fp32 partial epilogue");
@@ -152,10 +178,11 @@ inline int launch_rmsnorm(int mode, bf16* x, const bf16* w, bf16* xn, int rows, 
   }
   B200_REQUIRE(smem <= 96 * 1024, "hidden size too large for the rmsnorm kernel");
   if (rows == 0) return 0;
-  if (mode == 0) rmsnorm_kernel<0><<<rows, 256, smem, s>>>(x, w, xn, H, eps, nullptr, 0, 0, 0, nullptr);
-  else if (mode == 1) rmsnorm_kernel<1><<<rows, 256, smem, s>>>(x, w, xn, H, eps, partial, splits, split_stride, ld_partial, nullptr);
-  else rmsnorm_kernel<2><<<rows, 256, smem, s>>>(x, w, xn, H, eps, nullptr, 0, 0, 0, y);
-  B200_CUDA_OK(cudaGetLastError());
+  const float* np = nullptr;
+  const bf16* ny = nullptr;
+  if (mode == 0) B200_CUDA_OK(launch_k(rmsnorm_kernel<0>, dim3(rows), dim3(256), smem, s, x, w, xn, H, eps, np, 0, 0LL, 0LL, ny));
+  else if (mode == 1) B200_CUDA_OK(launch_k(rmsnorm_kernel<1>, dim3(rows), dim3(256), smem, s, x, w, xn, H, eps, partial, splits, split_stride, ld_partial, ny));
+  else B200_CUDA_OK(launch_k(rmsnorm_kernel<2>, dim3(rows), dim3(256), smem, s, x, w, xn, H, eps, np, 0, 0LL, 0LL, y));
   return 0;
 }
 
@@ -169,8 +196,7 @@ inline int launch_attn_prefill(const AttnPrefillParams& p, int B, int max_len, c
     configured = true;
   }
   dim3 grid((max_len + 63) / 64, p.nh, B);
-  attn_prefill_kernel<<<grid, kAttnThreads, kPrefillSmem, s>>>(p);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_k(attn_prefill_kernel, grid, dim3(kAttnThreads), kPrefillSmem, s, p));
   return 0;
 }
 
@@ -182,11 +208,9 @@ inline int launch_attn_decode(const AttnDecodeParams& p, int B, cudaStream_t s) 
   }
   B200_REQUIRE(p.G >= 1 && p.G <= 8, "GQA group size must be in [1, 8]");
   dim3 grid(B * p.nkv, p.splits);
-  attn_decode_kernel<<<grid, kAttnThreads, kDecodeSmem, s>>>(p);
-  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(launch_k(attn_decode_kernel, grid, dim3(kAttnThreads), kDecodeSmem, s, p));
   if (p.splits > 1) {
-    attn_combine_kernel<<<B * p.nh, 128, 0, s>>>(p.part_o, p.part_ml, p.out, p.ldo, p.nkv, p.G, p.splits);
-    B200_CUDA_OK(cudaGetLastError());
+    B200_CUDA_OK(launch_k(attn_combine_kernel, dim3(B * p.nh), dim3(128), 0, s, (const float*)p.part_o, (const float*)p.part_ml, p.out, p.ldo, p.nkv, p.G, p.splits));
   }
   return 0;
 }

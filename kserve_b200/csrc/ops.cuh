@@ -15,6 +15,9 @@ constexpr int kHeadDim = 128;
 // -------------------------------------------------------------------------------------------------
 __global__ void embed_gather_kernel(const int32_t* __restrict__ tokens, const bf16* __restrict__ table,
                                     bf16* __restrict__ x, int H, int vocab_rows) {
+  TraceScope _ts(TK_EMBED);
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x;
   int tok = tokens[t];
   tok = max(0, min(tok, vocab_rows - 1));
@@ -48,6 +51,9 @@ __global__ void __launch_bounds__(256)
 rmsnorm_kernel(bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ xn, int H, float eps,
                const float* __restrict__ partial, int splits, long long split_stride, long long ld_partial,
                const bf16* __restrict__ y) {
+  TraceScope _ts(TK_RMSNORM);
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float row[];  // H floats + 32
   float* red = row + H;
   const int r = blockIdx.x;
@@ -118,6 +124,9 @@ rmsnorm_kernel(bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restric
 // sum split-K partials into a bf16 matrix (used before the TP all-reduce): y[r][i] = bf16(sum_s p[s][r][i])
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, long long split_stride,
                                        long long ld_partial, bf16* __restrict__ y, int H) {
+  TraceScope _ts(TK_OTHER);
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x;
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     float a = 0.f;
@@ -176,6 +185,9 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
+  TraceScope _ts(TK_ROPE);
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x;
   const int pos = p.tok_pos[t];
   const int seq = p.tok_seq[t];
@@ -235,6 +247,9 @@ __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
 __global__ void __launch_bounds__(1024)
 argmax_kernel(const bf16* __restrict__ logits, long long ld, int V, int idx_offset, float* __restrict__ out_val,
               int32_t* __restrict__ out_idx) {
+  TraceScope _ts(TK_ARGMAX);
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const bf16* row = logits + (long long)b * ld;
   float best = -INFINITY;
@@ -300,6 +315,9 @@ struct StepParams {
 };
 
 __global__ void __launch_bounds__(128) step_update_kernel(const StepParams p) {
+  TraceScope _ts(TK_STEP);
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ int s_stop, s_unfinished;
   StepState* st = p.st;
   if (st->done) return;
@@ -348,6 +366,9 @@ __global__ void __launch_bounds__(128) step_update_kernel(const StepParams p) {
 // xl[b][:] = x[row_idx[b]][:]   (last prompt token of each sequence before the LM head)
 __global__ void gather_rows_kernel(const bf16* __restrict__ x, const int32_t* __restrict__ row_idx,
                                    bf16* __restrict__ out, int H) {
+  TraceScope _ts(TK_OTHER);
+  pdl_launch_dependents();
+  pdl_wait();
   const uint4* src = reinterpret_cast<const uint4*>(x + (long long)row_idx[blockIdx.x] * H);
   uint4* dst = reinterpret_cast<uint4*>(out + (long long)blockIdx.x * H);
   for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = src[i];
