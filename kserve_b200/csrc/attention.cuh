@@ -16,6 +16,7 @@
 namespace b200 {
 
 constexpr int kAttnThreads = 128;
+constexpr int kDecStages = 3;   // cp.async ring of the decode kernel: two KV tiles (64 KB) in flight per CTA
 constexpr int kTileBytes = kPageTokens * kHeadDim * 2;  // 16 KB
 
 // byte offset of 16-byte chunk `c` (0..15) of row `r` in a [rows][128] bf16 tile with XOR swizzle
@@ -194,6 +195,15 @@ struct AttnDecodeParams {
   float* part_o;                       // [B*nkv][splits][G][128]
   float* part_ml;                      // [B*nkv][splits][G][2]
   float scale_log2;
+  // Fused RoPE + KV append: when fuse_rope != 0 the kernel reads the raw QKV projection of the current token
+  // (bf16 [B][ld_qkv], or fp32 split-K partials), applies rotate-half RoPE with the same rounding points as
+  // rope_kv_kernel, uses the roped q / new k,v directly and appends k,v to the paged cache — one kernel
+  // boundary less on the decode critical path.
+  int fuse_rope;
+  const bf16* qkv; long long ld_qkv;
+  const float* qkv_partial; int qkv_splits; long long qkv_split_stride; long long ld_qkv_partial;
+  const bf16* cos_tab; const bf16* sin_tab;
+  bf16* kcache_w; bf16* vcache_w;
 };
 
 __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDecodeParams p) {
@@ -217,24 +227,112 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
     return;
   }
   const uint32_t sQ = smem_u32(smem);       // 16 rows x 256 B = 4 KB
-  const uint32_t sK = sQ + 4096;            // 2 x 16 KB
-  const uint32_t sV = sK + 2 * kTileBytes;  // 2 x 16 KB
+  const uint32_t sK = sQ + 4096;                      // kDecStages x 16 KB
+  const uint32_t sV = sK + kDecStages * kTileBytes;   // kDecStages x 16 KB
   const int32_t* pages = p.page_table + (long long)p.seq_slot[b] * p.max_pages;
   const long long tile_stride = (long long)p.nkv * kPageTokens * kHeadDim;
   const long long head_off = (long long)kvh * kPageTokens * kHeadDim;
 
-  // Q: G rows valid, the rest zero
+  const int pos = ctx - 1;
+  const int jt = pos >> 6;  // KV tile that receives the current token
+  float* s_raw = reinterpret_cast<float*>(smem + 4096 + 2 * kDecStages * kTileBytes);   // [(G+2)][128] fp32
+  bf16* s_newk = reinterpret_cast<bf16*>(s_raw + 10 * kHeadDim);           // [128]
+  bf16* s_newv = s_newk + kHeadDim;                                          // [128]
+  // fill the ring: kDecStages-1 tiles in flight before any compute (one commit group per ring slot, empty or not)
 #pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const int idx = threadIdx.x + it * kAttnThreads;
-    const int r = idx >> 4, c = idx & 15;
-    const bool valid = r < G;
-    const bf16* src = p.q + (long long)b * p.ldq + (kvh * G + (valid ? r : 0)) * kHeadDim + c * 8;
-    cp_async_16(sQ + swz(r, c), src, valid);
+  for (int st = 0; st < kDecStages - 1; ++st) {
+    if (t0 + st < t1) {
+      const long long pg = pages[t0 + st];
+      load_kv_tile(sK + st * kTileBytes, p.kcache + pg * tile_stride + head_off);
+      load_kv_tile(sV + st * kTileBytes, p.vcache + pg * tile_stride + head_off);
+    }
+    cp_async_commit();
   }
-  load_kv_tile(sK, p.kcache + (long long)pages[t0] * tile_stride + head_off);
-  load_kv_tile(sV, p.vcache + (long long)pages[t0] * tile_stride + head_off);
-  cp_async_commit();
+  if (p.fuse_rope) {
+    const int ngroups = (G + 2) * 16;
+    for (int gi = threadIdx.x; gi < ngroups; gi += kAttnThreads) {
+      const int hl = gi >> 4, c = (gi & 15) * 8;
+      const int col = (hl < G ? (kvh * G + hl) : (hl == G ? p.nh + kvh : p.nh + p.nkv + kvh)) * kHeadDim + c;
+      float f[8];
+      if (p.qkv_partial) {
+        float a[8];
+        sum_partials8(p.qkv_partial + (long long)b * p.ld_qkv_partial + col, p.qkv_splits, p.qkv_split_stride, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = bf16_round(a[i]);
+      } else {
+        uint4 u = *reinterpret_cast<const uint4*>(p.qkv + (long long)b * p.ld_qkv + col);
+        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 v2 = unpack_bf16x2(uw[i]);
+          f[2 * i] = v2.x;
+          f[2 * i + 1] = v2.y;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_raw[hl * kHeadDim + c + i] = f[i];
+    }
+    __syncthreads();
+    const int items = (G + 1) * 8 + 16;   // roped heads (q heads + k) x 8 threads, then 16 threads copy v
+    for (int it = threadIdx.x; it < items; it += kAttnThreads) {
+      if (it < (G + 1) * 8) {
+        const int hl = it >> 3, c = (it & 7) * 8;
+        float cs[8], sn[8], o1[8], o2[8];
+        {
+          uint4 cu = *reinterpret_cast<const uint4*>(p.cos_tab + (long long)pos * 64 + c);
+          uint4 su = *reinterpret_cast<const uint4*>(p.sin_tab + (long long)pos * 64 + c);
+          const uint32_t cw[4] = {cu.x, cu.y, cu.z, cu.w}, sw[4] = {su.x, su.y, su.z, su.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float2 a2 = unpack_bf16x2(cw[i]), b2 = unpack_bf16x2(sw[i]);
+            cs[2 * i] = a2.x; cs[2 * i + 1] = a2.y;
+            sn[2 * i] = b2.x; sn[2 * i + 1] = b2.y;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float x1 = s_raw[hl * kHeadDim + c + i], x2 = s_raw[hl * kHeadDim + c + 64 + i];
+          o1[i] = bf16_round(x1 * cs[i]) + bf16_round(-x2 * sn[i]);
+          o2[i] = bf16_round(x2 * cs[i]) + bf16_round(x1 * sn[i]);
+        }
+        if (hl < G) {
+          *reinterpret_cast<uint4*>(smem + swz(hl, c >> 3)) = pack8(o1);
+          *reinterpret_cast<uint4*>(smem + swz(hl, (c >> 3) + 8)) = pack8(o2);
+        } else {
+          *reinterpret_cast<uint4*>(s_newk + c) = pack8(o1);
+          *reinterpret_cast<uint4*>(s_newk + c + 64) = pack8(o2);
+        }
+      } else {
+        const int c = (it - (G + 1) * 8) * 8;
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = s_raw[(G + 1) * kHeadDim + c + i];
+        *reinterpret_cast<uint4*>(s_newv + c) = pack8(f);
+      }
+    }
+    // padding rows of the 16-row Q tile
+    for (int idx = threadIdx.x; idx < (16 - G) * 16; idx += kAttnThreads)
+      *reinterpret_cast<uint4*>(smem + swz(G + (idx >> 4), idx & 15)) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (jt >= t0 && jt < t1 && threadIdx.x < 32) {   // the split that owns the current token appends it to the cache
+      const int c = (threadIdx.x & 15) * 8, slot = pos & 63;
+      const long long off = (long long)pages[jt] * tile_stride + head_off + slot * kHeadDim + c;
+      if (threadIdx.x < 16) *reinterpret_cast<uint4*>(p.kcache_w + off) = *reinterpret_cast<const uint4*>(s_newk + c);
+      else *reinterpret_cast<uint4*>(p.vcache_w + off) = *reinterpret_cast<const uint4*>(s_newv + c);
+    }
+  } else {
+    // Q: G rows valid, the rest zero
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = threadIdx.x + it * kAttnThreads;
+      const int r = idx >> 4, c = idx & 15;
+      const bool valid = r < G;
+      const bf16* src = p.q + (long long)b * p.ldq + (kvh * G + (valid ? r : 0)) * kHeadDim + c * 8;
+      cp_async_16(sQ + swz(r, c), src, valid);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();   // (test path) keep the group accounting of the ring simple
+  }
 
   uint32_t qf[8][4];
   float o[16][4];
@@ -243,23 +341,34 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
   float m0 = -INFINITY, l0 = 0.f;  // only row g (< 8) matters: rows >= G are padding
 
   for (int j = t0; j < t1; ++j) {
-    const int buf = (j - t0) & 1;
-    if (j + 1 < t1) {
-      const long long pg = pages[j + 1];
-      load_kv_tile(sK + (buf ^ 1) * kTileBytes, p.kcache + pg * tile_stride + head_off);
-      load_kv_tile(sV + (buf ^ 1) * kTileBytes, p.vcache + pg * tile_stride + head_off);
+    const int buf = (j - t0) % kDecStages;
+    cp_async_wait<kDecStages - 2>();   // tile j has landed
+    __syncthreads();                   // ... for every thread, and everyone is done with tile j-1's slot
+    {
+      const int jn = j + kDecStages - 1;   // refill the slot tile j-1 used
+      if (jn < t1) {
+        const int nb = (jn - t0) % kDecStages;
+        const long long pg = pages[jn];
+        load_kv_tile(sK + nb * kTileBytes, p.kcache + pg * tile_stride + head_off);
+        load_kv_tile(sV + nb * kTileBytes, p.vcache + pg * tile_stride + head_off);
+      }
       cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
     }
-    __syncthreads();
     if (j == t0) {
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks)
         ldmatrix_x4(qf[ks], sQ + swz((lane & 7) + 8 * ((lane >> 3) & 1), 2 * ks + (lane >> 4)));
     }
     const uint32_t sKb = sK + buf * kTileBytes, sVb = sV + buf * kTileBytes;
+    if (p.fuse_rope && j == jt) {   // the row of the current token is not in the cache copy that was just staged
+      if (threadIdx.x < 32) {
+        const int c = threadIdx.x & 15, slot = pos & 63;
+        uint8_t* base = smem + 4096 + (threadIdx.x < 16 ? 0 : kDecStages * kTileBytes) + buf * kTileBytes;
+        *reinterpret_cast<uint4*>(base + swz(slot, c)) =
+            *reinterpret_cast<const uint4*>((threadIdx.x < 16 ? s_newk : s_newv) + c * 8);
+      }
+      __syncthreads();
+    }
     float s[2][4];
     s[0][0] = s[0][1] = s[0][2] = s[0][3] = 0.f;
     s[1][0] = s[1][1] = s[1][2] = s[1][3] = 0.f;
@@ -310,8 +419,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
       mma_m16n8k16_bf16(o[2 * dp], a, bfr[0], bfr[1]);
       mma_m16n8k16_bf16(o[2 * dp + 1], a, bfr[2], bfr[3]);
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
+  __syncthreads();   // all warps done with the ring before it is reused for the merge
   // ---- merge the 4 warps (each saw a disjoint quarter of every tile) through shared memory
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
   l0 += __shfl_xor_sync(0xffffffffu, l0, 2);

@@ -105,6 +105,9 @@ struct b200_engine {
        *qdec = nullptr, *logits = nullptr;
   float* ws = nullptr;
   size_t ws_elems = 0;
+  float* sk_ws = nullptr;   // stream-K partials / flags
+  int* sk_flags = nullptr;
+  int sk_tiles = 0;
   float *part_o = nullptr, *part_ml = nullptr;
   float* cand_val = nullptr;
   int32_t* cand_idx = nullptr;
@@ -206,8 +209,11 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
     }
     rp.kcache = kc; rp.vcache = vc; rp.page_table = e->d_page_table; rp.max_pages = e->max_pages;
     rp.cos_tab = e->cos_tab; rp.sin_tab = e->sin_tab; rp.nh = e->nh; rp.nkv = e->nkv;
-    B200_CUDA_OK(launch_k(rope_kv_kernel, dim3(T), dim3(256), 0, s, rp));
-    e->launches += 2;
+    e->launches++;
+    if (!decode) {   // decode: RoPE + KV append are fused into attn_decode_kernel
+      B200_CUDA_OK(launch_k(rope_kv_kernel, dim3(T), dim3(512), 0, s, rp));
+      e->launches++;
+    }
     // ---- attention
     if (decode) {
       AttnDecodeParams ap{};
@@ -219,6 +225,9 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
       const int ctas = B * e->nkv;
       ap.splits = ctas >= e->num_sms ? 1 : std::max(1, std::min((e->num_sms + ctas - 1) / ctas, 8));
       ap.part_o = e->part_o; ap.part_ml = e->part_ml; ap.scale_log2 = scale_log2;
+      ap.fuse_rope = 1; ap.qkv = rp.qkv; ap.ld_qkv = rp.ld; ap.qkv_partial = rp.partial; ap.qkv_splits = rp.splits;
+      ap.qkv_split_stride = rp.split_stride; ap.ld_qkv_partial = rp.ld_partial; ap.cos_tab = e->cos_tab; ap.sin_tab = e->sin_tab;
+      ap.kcache_w = kc; ap.vcache_w = vc;
       if ((rc = launch_attn_decode(ap, B, s))) return rc;
       e->launches += ap.splits > 1 ? 2 : 1;
     } else {
@@ -271,6 +280,7 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
     // ---- gate/up projection with the SwiGLU fused into the epilogue
     if (decode) {
       GemmArgs a{w.wgu, 2 * e->I, e->xn, e->cap_T, 2 * e->I, B, H, EPI_T_SWIGLU, bn, 1, e->hbuf, nullptr, e->I, 0, e->I, true};
+      a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles;
       if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
     } else {
       GemmArgs a{e->xn, e->cap_T, w.wgu, 2 * e->I, T, 2 * e->I, H, EPI_SWIGLU, 256, 1, e->hbuf, nullptr, e->I, 0, e->I, false};
@@ -289,6 +299,7 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
   int rc;
   GemmArgs a{e->lm_head, e->Vl, rows_xn, rows_cap, e->Vl, B, e->H, EPI_T_STORE, pick_block_n(B), 1,
              e->logits, nullptr, e->Vl, 0, 0, true};
+  a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles;
   if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
   B200_CUDA_OK(launch_k(argmax_kernel, dim3(B), dim3(1024), 0, s, (const bf16*)e->logits, (long long)e->Vl, e->Vl, e->v0, e->cand_val, e->cand_idx));
   e->launches += 2;
@@ -619,6 +630,10 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   B200_CUDA_OK(cudaMemset(e->xl, 0, (size_t)c->max_batch * H * 2));
   e->ws_elems = (size_t)16 * c->max_batch * std::max(e->qkv_cols, e->H);
   if ((rc = dmalloc(&e->ws, e->ws_elems))) return rc;
+  e->sk_tiles = (std::max(2 * e->I, e->Vl) + kGemmBlockM - 1) / kGemmBlockM;
+  if ((rc = dmalloc(&e->sk_ws, (size_t)e->sk_tiles * 64 * kGemmBlockM))) return rc;
+  if ((rc = dmalloc(&e->sk_flags, (size_t)e->sk_tiles))) return rc;
+  B200_CUDA_OK(cudaMemset(e->sk_flags, 0, (size_t)e->sk_tiles * sizeof(int)));
   if ((rc = dmalloc(&e->part_o, (size_t)c->max_batch * e->nkv * 8 * e->G * kHeadDim))) return rc;
   if ((rc = dmalloc(&e->part_ml, (size_t)c->max_batch * e->nkv * 8 * e->G * 2))) return rc;
   if ((rc = dmalloc(&e->cand_val, (size_t)c->max_batch))) return rc;
@@ -678,7 +693,7 @@ int b200_engine_destroy(b200_engine_t* e) {
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   if (e->comm) Nccl::get().CommDestroy(e->comm);
   void* ptrs[] = {e->embed, e->lm_head, e->final_norm, e->cos_tab, e->sin_tab, e->kcache, e->vcache, e->d_page_table,
-                  e->x, e->xn, e->qkv, e->attn, e->hbuf, e->ybuf, e->xl, e->qdec, e->logits, e->ws, e->part_o, e->part_ml,
+                  e->x, e->xn, e->qkv, e->attn, e->hbuf, e->ybuf, e->xl, e->qdec, e->logits, e->ws, e->sk_ws, e->sk_flags, e->part_o, e->part_ml,
                   e->cand_val, e->cand_idx, e->cand_val_all, e->cand_idx_all, e->d_tok, e->d_tok_seq, e->d_tok_pos, e->d_cu,
                   e->d_seq_slot, e->d_last_rows, e->d_cur_len, e->d_next_tok, e->d_dec_pos, e->d_finished, e->d_out_tokens,
                   e->d_forced, e->d_eos, e->d_stop_tok, e->d_stop_off, e->d_state};
@@ -1035,6 +1050,15 @@ int b200_op_gemm(const void* A, const void* B, void* out, const void* residual, 
   int out_cols = (epi == EPI_SWIGLU) ? N / 2 : (epi == EPI_T_SWIGLU ? M / 2 : 0);
   GemmArgs a{(const bf16*)A, M, (const bf16*)B, N, M, N, K, epi, block_n, effective_splits(K, splits), out,
              (const bf16*)residual, ldo, (long long)N * ldo, out_cols, t};
+  static float* op_sk_ws = nullptr;
+  static int* op_sk_flags = nullptr;
+  const int op_sk_tiles = 2048;
+  if (t && !op_sk_ws) {
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&op_sk_ws), (size_t)op_sk_tiles * 64 * kGemmBlockM * sizeof(float)));
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&op_sk_flags), op_sk_tiles * sizeof(int)));
+    B200_CUDA_OK(cudaMemset(op_sk_flags, 0, op_sk_tiles * sizeof(int)));
+  }
+  a.sk_ws = op_sk_ws; a.sk_flags = op_sk_flags; a.sk_tiles = op_sk_tiles;
   return launch_gemm(g_op_tmaps, a, op_sms(), (cudaStream_t)stream);
 }
 
@@ -1073,7 +1097,7 @@ int b200_op_rope_kv(const void* qkv, int64_t ld, void* q_out, int64_t ldq, void*
   p.qkv = (const bf16*)qkv; p.ld = ld; p.q_out = (bf16*)q_out; p.ldq = ldq; p.kcache = (bf16*)kcache; p.vcache = (bf16*)vcache;
   p.page_table = page_table; p.max_pages = max_pages; p.tok_seq = tok_seq; p.tok_pos = tok_pos;
   p.cos_tab = (const bf16*)cos_tab; p.sin_tab = (const bf16*)sin_tab; p.nh = nh; p.nkv = nkv;
-  rope_kv_kernel<<<T, 256, 0, (cudaStream_t)stream>>>(p);
+  rope_kv_kernel<<<T, 512, 0, (cudaStream_t)stream>>>(p);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -36,6 +36,14 @@ struct GemmParams {
   int out_cols;            // logical number of output columns (bounds for SWIGLU modes = N/2 resp. M/2)
   unsigned long long hint_a, hint_b;
   int prefetch_a;          // A (weights) does not depend on the previous kernel: stream it before griddepcontrol.wait
+  int l2_prefetch_kb;      // additional k-blocks of A to pull into L2 (beyond the smem stages) before the wait
+  // sched == 1: "stream-K" — the m_tiles * kb_total k-block iterations are cut into gridDim.x equal contiguous
+  // ranges (every SM streams the same number of weight bytes); a tile cut in two is finished by the CTA that
+  // owns its last k-block, which adds the other CTA's fp32 partial (sk_ws) once its flag is up.  Requires
+  // n_tiles == 1, splits == 1 and m_tiles >= gridDim.x (at most two pieces per tile).
+  int sched;
+  float* sk_ws;            // [m_tiles][BLOCK_N][128] fp32 head partials
+  int* sk_flags;           // [m_tiles], 0 between launches
 };
 
 constexpr int kGemmBlockM = 128;
@@ -53,7 +61,52 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// SiLU on an already bf16-rounded input whose result is rounded to bf16 again: the fast exp / divide intrinsics
+// (rel. error ~1e-6) cannot change the bf16 result except on exact rounding ties, and keep the epilogue short.
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+
+struct GemmSeg { int m_t, n_t, kb0, kb1, split, type; };  // type: 0 full, 1 head (partial -> workspace), 2 tail (adds partial)
+
+__device__ __forceinline__ bool gemm_get_seg(const GemmParams& p, int idx, GemmSeg& g) {
+  if (p.sched == 0) {
+    const int u = blockIdx.x + idx * gridDim.x;
+    if (u >= p.m_tiles * p.n_tiles * p.splits) return false;
+    const int tile = u / p.splits;
+    g.split = u - tile * p.splits;
+    const int per_group = kGemmGroupM * p.n_tiles;
+    const int grp = tile / per_group;
+    const int first_m = grp * kGemmGroupM;
+    const int gsize = min(p.m_tiles - first_m, kGemmGroupM);
+    const int r = tile - grp * per_group;
+    g.m_t = first_m + r % gsize;
+    g.n_t = r / gsize;
+    g.kb0 = g.split * p.kb_per_split;
+    g.kb1 = min(g.kb0 + p.kb_per_split, p.kb_total);
+    g.type = 0;
+    return true;
+  }
+  // stream-K: processing order is head piece first (so nobody ever waits for it), full tiles, tail piece last
+  const long long W = (long long)p.m_tiles * p.kb_total;
+  const long long lo = W * blockIdx.x / gridDim.x, hi = W * (blockIdx.x + 1) / gridDim.x;
+  if (lo >= hi) return false;
+  const int KB = p.kb_total;
+  const int t0 = (int)(lo / KB), k_lo = (int)(lo % KB);
+  const int t1 = (int)((hi - 1) / KB), k_hi = (int)((hi - 1) % KB) + 1;
+  // every range is >= kb_total long (m_tiles >= gridDim.x), so a range inside one tile is exactly that tile and a
+  // tile is never cut into more than two pieces
+  const int has_tail = (k_lo > 0) ? 1 : 0;   // our first tile was started by the previous CTA
+  const int has_head = (k_hi < KB) ? 1 : 0;  // our last tile is finished by the next CTA
+  const int f0 = t0 + has_tail, f1 = t1 - has_head;
+  const int n_full = max(0, f1 - f0 + 1);
+  g.n_t = 0; g.split = 0;
+  if (idx < has_head) { g.m_t = t1; g.kb0 = 0; g.kb1 = k_hi; g.type = 1; return true; }
+  idx -= has_head;
+  if (idx < n_full) { g.m_t = f0 + idx; g.kb0 = 0; g.kb1 = KB; g.type = 0; return true; }
+  idx -= n_full;
+  if (idx < has_tail) { g.m_t = t0; g.kb0 = k_lo; g.kb1 = KB; g.type = 2; return true; }
+  return false;
+}
 
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -73,7 +126,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_units = p.m_tiles * p.n_tiles * p.splits;
   pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
@@ -95,30 +147,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto decode_unit = [&](int u, int& m_t, int& n_t, int& kb0, int& kb1) {
-    const int tile = u / p.splits;
-    const int s = u - tile * p.splits;
-    const int per_group = kGemmGroupM * p.n_tiles;
-    const int g = tile / per_group;
-    const int first_m = g * kGemmGroupM;
-    const int gsize = min(p.m_tiles - first_m, kGemmGroupM);
-    const int r = tile - g * per_group;
-    m_t = first_m + r % gsize;
-    n_t = r / gsize;
-    kb0 = s * p.kb_per_split;
-    kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-    return s;
-  };
-
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       bool first = true;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-        int m_t, n_t, kb0, kb1;
-        decode_unit(u, m_t, n_t, kb0, kb1);
+      GemmSeg sg;
+      for (int idx = 0; gemm_get_seg(p, idx, sg); ++idx) {
+        const int m_t = sg.m_t, n_t = sg.n_t, kb0 = sg.kb0, kb1 = sg.kb1;
         int kb = kb0;
         if (first) {
           first = false;
@@ -130,6 +167,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
               tma_load_2d(smem + i * Cfg::kStageBytes, &tmap_a, &full_bar[i], (kb0 + i) * kGemmBlockK, m_t * kGemmBlockM, p.hint_a);
             }
+            const int npf = min(npre + p.l2_prefetch_kb, kb1 - kb0);
+            for (int i = npre; i < npf; ++i) tma_prefetch_l2_2d(&tmap_a, (kb0 + i) * kGemmBlockK, m_t * kGemmBlockM);
             pdl_wait();
             for (int i = 0; i < npre; ++i)
               tma_load_2d(smem + i * Cfg::kStageBytes + Cfg::kABytes, &tmap_b, &full_bar[i], (kb0 + i) * kGemmBlockK, n_t * BLOCK_N, p.hint_b);
@@ -159,9 +198,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-        int m_t, n_t, kb0, kb1;
-        decode_unit(u, m_t, n_t, kb0, kb1);
+      GemmSeg sg;
+      for (int idx = 0; gemm_get_seg(p, idx, sg); ++idx) {
+        const int kb0 = sg.kb0, kb1 = sg.kb1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -190,13 +229,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     pdl_wait();              // outputs / residual must not be touched before the previous kernel is complete
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-      int m_t, n_t, kb0, kb1;
-      const int s = decode_unit(u, m_t, n_t, kb0, kb1);
+    GemmSeg sg;
+    for (int idx = 0; gemm_get_seg(p, idx, sg); ++idx) {
+      const int m_t = sg.m_t, n_t = sg.n_t, s = sg.split;
       const int m = m_t * kGemmBlockM + q * 32 + lane;  // accumulator row of this thread
       const int n0 = n_t * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
+      float* skw = (sg.type != 0) ? p.sk_ws + ((long long)m_t * BLOCK_N) * kGemmBlockM + q * 32 + lane : nullptr;
+      if (sg.type == 2) {   // wait for the other CTA's partial of this tile
+        if (threadIdx.x == 64) {
+          uint32_t spins = 0;
+          while (*reinterpret_cast<volatile int*>(p.sk_flags + m_t) != 1) {
+            if (++spins > (1u << 28)) { printf("b200: stream-K flag timeout (tile %d)\n", m_t); __trap(); }
+          }
+          __threadfence();
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
       constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
 #pragma unroll 1
@@ -211,6 +261,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
         }
         const int nvalid = min(CH, p.N - (n0 + c0));
+        if (sg.type == 1) {          // head piece: park the fp32 accumulators, the tail owner finishes the tile
+#pragma unroll
+          for (int j = 0; j < CH; ++j) skw[(long long)(c0 + j) * kGemmBlockM] = v[j];
+          continue;
+        }
+        if (sg.type == 2) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] += __ldcg(skw + (long long)(c0 + j) * kGemmBlockM);
+        }
         if constexpr (EPI == EPI_STORE || EPI == EPI_STORE_RES) {
           if (m < p.M) {
             bf16* orow = reinterpret_cast<bf16*>(p.out) + (long long)m * p.ldo + n0 + c0;
@@ -284,11 +343,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int f = ((m_t * kGemmBlockM + q * 32) >> 1) + (lane & 15);
           bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)(n0 + c0) * p.ldo + f;
 #pragma unroll
-          for (int j = 0; j < CH; ++j) {
-            const float mine = bf16_round(v[j]);
-            const float up = __shfl_down_sync(0xffffffffu, mine, 16);
-            if (lane < 16 && j < nvalid && f < p.out_cols)
-              o[(long long)j * p.ldo] = __float2bfloat16_rn(bf16_round(silu_f(mine)) * up);
+          for (int j = 0; j < CH; j += 2) {
+            // lanes 16-31 hold `up`: hand two bf16 columns per shuffle to the gate lane 16 below
+            const uint32_t mine = pack_bf16x2(v[j], v[j + 1]);
+            const uint32_t other = __shfl_down_sync(0xffffffffu, mine, 16);
+            if (lane < 16 && f < p.out_cols) {
+              const float2 g2 = unpack_bf16x2(mine), u2 = unpack_bf16x2(other);
+              if (j < nvalid) o[(long long)j * p.ldo] = __float2bfloat16_rn(bf16_round(silu_f(g2.x)) * u2.x);
+              if (j + 1 < nvalid) o[(long long)(j + 1) * p.ldo] = __float2bfloat16_rn(bf16_round(silu_f(g2.y)) * u2.y);
+            }
           }
         } else {  // EPI_T_PARTIAL
           if (m < p.M) {
@@ -303,6 +366,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (sg.type == 1) {          // publish the partial
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) atomicExch(p.sk_flags + m_t, 1);
+      } else if (sg.type == 2) {   // consumed: leave the flag clean for the next launch / graph replay
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) atomicExch(p.sk_flags + m_t, 0);
+      }
     }
   }
 

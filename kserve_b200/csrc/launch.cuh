@@ -112,6 +112,9 @@ struct GemmArgs {
   int epi, block_n, splits;
   void* out; const bf16* residual; long long ldo; long long split_stride; int out_cols;
   bool stream_a;                    // true: A is the weight (decode) -> evict-first on A, keep B
+  float* sk_ws = nullptr;           // stream-K workspace / flags (optional): enables balanced scheduling for
+  int* sk_flags = nullptr;          // single-split swap-AB GEMMs whose tile count is not a multiple of the SM count
+  int sk_tiles = 0;                 // capacity of the workspace in tiles
 };
 
 inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStream_t s) {
@@ -134,8 +137,17 @@ inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStr
   p.hint_a = a.stream_a ? kEvictFirst : kEvictLast;
   p.hint_b = a.stream_a ? kEvictLast : kEvictNormal;
   p.prefetch_a = a.stream_a ? 1 : 0;
+  {
+    static const int l2pf = getenv("B200_L2_PREFETCH_KB") ? atoi(getenv("B200_L2_PREFETCH_KB")) : 0;
+    p.l2_prefetch_kb = a.stream_a ? l2pf : 0;
+  }
   const int units = p.m_tiles * p.n_tiles * p.splits;
   const int grid = units < num_sms ? units : num_sms;
+  static const bool sk_on = getenv("B200_NO_STREAMK") == nullptr;
+  p.sched = 0; p.sk_ws = a.sk_ws; p.sk_flags = a.sk_flags;
+  if (sk_on && a.sk_ws && a.sk_flags && a.stream_a && p.splits == 1 && p.n_tiles == 1 && p.m_tiles >= num_sms &&
+      p.m_tiles <= a.sk_tiles && (p.m_tiles % num_sms) != 0 && (a.epi == EPI_T_STORE || a.epi == EPI_T_SWIGLU))
+    p.sched = 1;
   B200_REQUIRE(p.splits == 1 || a.epi == EPI_T_PARTIAL, "split-K only with the fp32 partial epilogue");
 #define B200_GEMM_CASE(BN, E) \
   if (a.block_n == BN && a.epi == E) return launch_gemm_inst<BN, E>(ta, tb, p, grid, s);
@@ -180,14 +192,14 @@ inline int launch_rmsnorm(int mode, bf16* x, const bf16* w, bf16* xn, int rows, 
   if (rows == 0) return 0;
   const float* np = nullptr;
   const bf16* ny = nullptr;
-  if (mode == 0) B200_CUDA_OK(launch_k(rmsnorm_kernel<0>, dim3(rows), dim3(256), smem, s, x, w, xn, H, eps, np, 0, 0LL, 0LL, ny));
-  else if (mode == 1) B200_CUDA_OK(launch_k(rmsnorm_kernel<1>, dim3(rows), dim3(256), smem, s, x, w, xn, H, eps, partial, splits, split_stride, ld_partial, ny));
-  else B200_CUDA_OK(launch_k(rmsnorm_kernel<2>, dim3(rows), dim3(256), smem, s, x, w, xn, H, eps, np, 0, 0LL, 0LL, y));
+  if (mode == 0) B200_CUDA_OK(launch_k(rmsnorm_kernel<0>, dim3(rows), dim3(kNormThreads), smem, s, x, w, xn, H, eps, np, 0, 0LL, 0LL, ny));
+  else if (mode == 1) B200_CUDA_OK(launch_k(rmsnorm_kernel<1>, dim3(rows), dim3(kNormThreads), smem, s, x, w, xn, H, eps, partial, splits, split_stride, ld_partial, ny));
+  else B200_CUDA_OK(launch_k(rmsnorm_kernel<2>, dim3(rows), dim3(kNormThreads), smem, s, x, w, xn, H, eps, np, 0, 0LL, 0LL, y));
   return 0;
 }
 
 constexpr int kPrefillSmem = 5 * kTileBytes;
-constexpr int kDecodeSmem = 4096 + 4 * kTileBytes;
+constexpr int kDecodeSmem = 4096 + 2 * kDecStages * kTileBytes + 10 * kHeadDim * 4 + 2 * kHeadDim * 2;
 
 inline int launch_attn_prefill(const AttnPrefillParams& p, int B, int max_len, cudaStream_t s) {
   static bool configured = false;

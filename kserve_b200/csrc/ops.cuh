@@ -46,47 +46,82 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // In modes 1/2 the updated residual stream x is written back (bf16), then normalised.
 // One CTA per row; the row lives in shared memory as fp32 between the two passes.
 // -------------------------------------------------------------------------------------------------
+// sum of split-K partials for 8 consecutive elements; all loads of up to 4 splits are issued before the first
+// add (memory-level parallelism: this sits on the decode critical path), accumulation order is s = 0,1,2,...
+__device__ __forceinline__ void sum_partials8(const float* __restrict__ base, int splits, long long split_stride, float (&a)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 0.f;
+  for (int s0 = 0; s0 < splits; s0 += 4) {
+    float4 v[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (s0 + j < splits) {
+        const float4* pp = reinterpret_cast<const float4*>(base + (long long)(s0 + j) * split_stride);
+        v[j][0] = pp[0];
+        v[j][1] = pp[1];
+      } else {
+        v[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[j][1] = v[j][0];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (s0 + j < splits) {
+        a[0] += v[j][0].x; a[1] += v[j][0].y; a[2] += v[j][0].z; a[3] += v[j][0].w;
+        a[4] += v[j][1].x; a[5] += v[j][1].y; a[6] += v[j][1].z; a[7] += v[j][1].w;
+      }
+    }
+  }
+}
+
+constexpr int kNormThreads = 512;
+
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kNormThreads)
 rmsnorm_kernel(bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ xn, int H, float eps,
                const float* __restrict__ partial, int splits, long long split_stride, long long ld_partial,
                const bf16* __restrict__ y) {
   TraceScope _ts(TK_RMSNORM);
   pdl_launch_dependents();
-  pdl_wait();
   extern __shared__ float row[];  // H floats + 32
   float* red = row + H;
   const int r = blockIdx.x;
   bf16* xr = x + (long long)r * H;
+  // the norm weight does not depend on the previous kernel: fetch it before the dependency wait
+  const bool single = H <= (int)blockDim.x * 8;
+  uint4 wpre = make_uint4(0, 0, 0, 0);
+  if (single && (int)threadIdx.x * 8 < H) wpre = *reinterpret_cast<const uint4*>(w + threadIdx.x * 8);
+  pdl_wait();
   float ss = 0.f;
   for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
     uint4 u = *reinterpret_cast<const uint4*>(xr + i);
-    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
     float f[8];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float2 p2 = unpack_bf16x2(uw[t]);
-      f[2 * t] = p2.x;
-      f[2 * t + 1] = p2.y;
-    }
     if constexpr (MODE == 1) {
-      float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int s = 0; s < splits; ++s) {
-        const float4* pp = reinterpret_cast<const float4*>(partial + s * split_stride + (long long)r * ld_partial + i);
-        float4 p0 = pp[0], p1 = pp[1];
-        a[0] += p0.x; a[1] += p0.y; a[2] += p0.z; a[3] += p0.w;
-        a[4] += p1.x; a[5] += p1.y; a[6] += p1.z; a[7] += p1.w;
-      }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) f[t] = bf16_round(f[t] + bf16_round(a[t]));
-    } else if constexpr (MODE == 2) {
-      uint4 yu = *reinterpret_cast<const uint4*>(y + (long long)r * H + i);
-      const uint32_t yw[4] = {yu.x, yu.y, yu.z, yu.w};
+      float a[8];
+      sum_partials8(partial + (long long)r * ld_partial + i, splits, split_stride, a);
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        float2 p2 = unpack_bf16x2(yw[t]);
-        f[2 * t] = bf16_round(f[2 * t] + p2.x);
-        f[2 * t + 1] = bf16_round(f[2 * t + 1] + p2.y);
+        float2 p2 = unpack_bf16x2(uw[t]);
+        f[2 * t] = bf16_round(p2.x + bf16_round(a[2 * t]));
+        f[2 * t + 1] = bf16_round(p2.y + bf16_round(a[2 * t + 1]));
+      }
+    } else if constexpr (MODE == 2) {
+      uint4 yu = *reinterpret_cast<const uint4*>(y + (long long)r * H + i);
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w}, yw[4] = {yu.x, yu.y, yu.z, yu.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 p2 = unpack_bf16x2(uw[t]), q2 = unpack_bf16x2(yw[t]);
+        f[2 * t] = bf16_round(p2.x + q2.x);
+        f[2 * t + 1] = bf16_round(p2.y + q2.y);
+      }
+    } else {
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 p2 = unpack_bf16x2(uw[t]);
+        f[2 * t] = p2.x;
+        f[2 * t + 1] = p2.y;
       }
     }
     if constexpr (MODE != 0) {
@@ -105,7 +140,7 @@ rmsnorm_kernel(bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restric
   const float rs = 1.0f / sqrtf(tot / (float)H + eps);  // IEEE sqrt + div, as torch.rsqrt on CPU
   bf16* o = xn + (long long)r * H;
   for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
-    uint4 wu = *reinterpret_cast<const uint4*>(w + i);
+    uint4 wu = single ? wpre : *reinterpret_cast<const uint4*>(w + i);
     const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w};
     float g[8];
 #pragma unroll
@@ -157,13 +192,8 @@ struct RopeKvParams {
 
 __device__ __forceinline__ void load8(const RopeKvParams& p, int t, int col, float (&f)[8]) {
   if (p.partial) {
-    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int s = 0; s < p.splits; ++s) {
-      const float4* pp = reinterpret_cast<const float4*>(p.partial + s * p.split_stride + (long long)t * p.ld_partial + col);
-      float4 p0 = pp[0], p1 = pp[1];
-      a[0] += p0.x; a[1] += p0.y; a[2] += p0.z; a[3] += p0.w;
-      a[4] += p1.x; a[5] += p1.y; a[6] += p1.z; a[7] += p1.w;
-    }
+    float a[8];
+    sum_partials8(p.partial + (long long)t * p.ld_partial + col, p.splits, p.split_stride, a);
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = bf16_round(a[i]);
   } else {
@@ -184,7 +214,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return o;
 }
 
-__global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
+__global__ void __launch_bounds__(512) rope_kv_kernel(const RopeKvParams p) {
   TraceScope _ts(TK_ROPE);
   pdl_launch_dependents();
   pdl_wait();

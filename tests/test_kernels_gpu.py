@@ -96,6 +96,29 @@ def test_gemm_swapab_store(lib, bn, batch, nout, K):
     _cmp(f"gemm_T_store bn{bn} b{batch}", out, x.float() @ W.float().T, 2e-3, RTOL)
 
 
+@pytest.mark.parametrize("nout,K,batch,bn", [(28672, 512, 32, 32), (19072, 1024, 5, 16), (128256, 512, 33, 64), (37888, 512, 32, 32)])
+def test_gemm_streamk_store(lib, nout, K, batch, bn):
+    """>= 148 weight tiles and not a multiple of 148: balanced stream-K scheduling with cross-CTA fix-up."""
+    W, x = _rand(nout, K, scale=1 / math.sqrt(K), seed=4), _rand(batch, K, seed=5)
+    for rep in range(3):   # flags must be left clean between launches
+        out = torch.full((batch, nout), float("nan"), dtype=torch.bfloat16, device=DEV)
+        _check(lib, lib.b200_op_gemm(_ptr(W), _ptr(x), _ptr(out), None, nout, batch, K, 3, bn, 1, nout, None), "gemm")
+        torch.cuda.synchronize()
+        _cmp(f"gemm_streamk_store rep{rep}", out, x.float() @ W.float().T, 2e-3, RTOL)
+
+
+@pytest.mark.parametrize("I,K,batch,bn", [(14336, 512, 32, 32), (14336, 1024, 64, 64), (9536, 512, 3, 16)])
+def test_gemm_streamk_swiglu(lib, I, K, batch, bn):
+    x = _rand(batch, K, seed=1)
+    gate, up = _rand(I, K, scale=1 / math.sqrt(K), seed=2), _rand(I, K, scale=1 / math.sqrt(K), seed=3)
+    w = _interleave16(gate, up)
+    for rep in range(2):
+        out = torch.full((batch, I), float("nan"), dtype=torch.bfloat16, device=DEV)
+        _check(lib, lib.b200_op_gemm(_ptr(w), _ptr(x), _ptr(out), None, 2 * I, batch, K, 4, bn, 1, I, None), "gemm")
+        torch.cuda.synchronize()
+        _cmp("gemm_streamk_swiglu", out, _swiglu_ref(x, gate, up), 1e-2, 2 * RTOL)
+
+
 @pytest.mark.parametrize("bn,batch", [(16, 4), (32, 32), (64, 40)])
 def test_gemm_swapab_swiglu(lib, bn, batch):
     I, K = 1024, 512
