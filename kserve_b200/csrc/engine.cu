@@ -108,6 +108,7 @@ struct b200_engine {
   float* sk_ws = nullptr;   // stream-K partials / flags
   int* sk_flags = nullptr;
   int sk_tiles = 0;
+  size_t sk_ws_floats = 0;
   float *part_o = nullptr, *part_ml = nullptr;
   float* cand_val = nullptr;
   int32_t* cand_idx = nullptr;
@@ -191,9 +192,12 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
     RopeKvParams rp{};
     rp.ld = e->qkv_cols;
     if (decode) {
+      // uniform split-K with fp32 partials: the consumer kernel (attention prologue / rmsnorm) reduces them in
+      // parallel, which measured faster than finishing multi-piece tiles inside the GEMM (r01: 4.30 vs 4.62 ms/step)
       const int sp = pick_splits(e, e->qkv_cols, H);
       GemmArgs a{w.wqkv, e->qkv_cols, e->xn, e->cap_T, e->qkv_cols, B, H, sp > 1 ? EPI_T_PARTIAL : EPI_T_STORE, bn, sp,
                  sp > 1 ? (void*)e->ws : (void*)e->qkv, nullptr, e->qkv_cols, (long long)B * e->qkv_cols, 0, true};
+      a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
       if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
       if (sp > 1) { rp.partial = e->ws; rp.splits = sp; rp.split_stride = (long long)B * e->qkv_cols; rp.ld_partial = e->qkv_cols; }
       rp.qkv = e->qkv;
@@ -256,6 +260,7 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
           e->launches++;
         } else {
           GemmArgs a{wmat, H, act, e->cap_T, H, B, K, EPI_T_STORE, bn, 1, e->ybuf, nullptr, H, 0, 0, true};
+          a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
           if ((rc2 = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc2;
           e->launches++;
         }
@@ -280,7 +285,7 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
     // ---- gate/up projection with the SwiGLU fused into the epilogue
     if (decode) {
       GemmArgs a{w.wgu, 2 * e->I, e->xn, e->cap_T, 2 * e->I, B, H, EPI_T_SWIGLU, bn, 1, e->hbuf, nullptr, e->I, 0, e->I, true};
-      a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles;
+      a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
       if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
     } else {
       GemmArgs a{e->xn, e->cap_T, w.wgu, 2 * e->I, T, 2 * e->I, H, EPI_SWIGLU, 256, 1, e->hbuf, nullptr, e->I, 0, e->I, false};
@@ -299,7 +304,7 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
   int rc;
   GemmArgs a{e->lm_head, e->Vl, rows_xn, rows_cap, e->Vl, B, e->H, EPI_T_STORE, pick_block_n(B), 1,
              e->logits, nullptr, e->Vl, 0, 0, true};
-  a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles;
+  a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
   if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
   B200_CUDA_OK(launch_k(argmax_kernel, dim3(B), dim3(1024), 0, s, (const bf16*)e->logits, (long long)e->Vl, e->Vl, e->v0, e->cand_val, e->cand_idx));
   e->launches += 2;
@@ -631,7 +636,8 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   e->ws_elems = (size_t)16 * c->max_batch * std::max(e->qkv_cols, e->H);
   if ((rc = dmalloc(&e->ws, e->ws_elems))) return rc;
   e->sk_tiles = (std::max(2 * e->I, e->Vl) + kGemmBlockM - 1) / kGemmBlockM;
-  if ((rc = dmalloc(&e->sk_ws, (size_t)e->sk_tiles * 64 * kGemmBlockM))) return rc;
+  e->sk_ws_floats = std::max<size_t>((size_t)e->sk_tiles * 2 * 64 * kGemmBlockM, (size_t)8 << 20);   // >= 32 MB
+  if ((rc = dmalloc(&e->sk_ws, e->sk_ws_floats))) return rc;
   if ((rc = dmalloc(&e->sk_flags, (size_t)e->sk_tiles))) return rc;
   B200_CUDA_OK(cudaMemset(e->sk_flags, 0, (size_t)e->sk_tiles * sizeof(int)));
   if ((rc = dmalloc(&e->part_o, (size_t)c->max_batch * e->nkv * 8 * e->G * kHeadDim))) return rc;
@@ -1054,11 +1060,11 @@ int b200_op_gemm(const void* A, const void* B, void* out, const void* residual, 
   static int* op_sk_flags = nullptr;
   const int op_sk_tiles = 2048;
   if (t && !op_sk_ws) {
-    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&op_sk_ws), (size_t)op_sk_tiles * 64 * kGemmBlockM * sizeof(float)));
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&op_sk_ws), (size_t)op_sk_tiles * 2 * 64 * kGemmBlockM * sizeof(float)));
     B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&op_sk_flags), op_sk_tiles * sizeof(int)));
     B200_CUDA_OK(cudaMemset(op_sk_flags, 0, op_sk_tiles * sizeof(int)));
   }
-  a.sk_ws = op_sk_ws; a.sk_flags = op_sk_flags; a.sk_tiles = op_sk_tiles;
+  a.sk_ws = op_sk_ws; a.sk_flags = op_sk_flags; a.sk_tiles = op_sk_tiles; a.sk_ws_floats = (size_t)op_sk_tiles * 2 * 64 * kGemmBlockM;
   return launch_gemm(g_op_tmaps, a, op_sms(), (cudaStream_t)stream);
 }
 

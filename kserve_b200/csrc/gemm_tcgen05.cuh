@@ -38,12 +38,16 @@ struct GemmParams {
   int prefetch_a;          // A (weights) does not depend on the previous kernel: stream it before griddepcontrol.wait
   int l2_prefetch_kb;      // additional k-blocks of A to pull into L2 (beyond the smem stages) before the wait
   // sched == 1: "stream-K" — the m_tiles * kb_total k-block iterations are cut into gridDim.x equal contiguous
-  // ranges (every SM streams the same number of weight bytes); a tile cut in two is finished by the CTA that
-  // owns its last k-block, which adds the other CTA's fp32 partial (sk_ws) once its flag is up.  Requires
-  // n_tiles == 1, splits == 1 and m_tiles >= gridDim.x (at most two pieces per tile).
+  // ranges, so every SM streams the same number of weight bytes whatever the tile count (few tiles under tensor
+  // parallelism, 224 tiles on 148 SMs, ...).  A tile covered by several CTAs is finished by the CTA that owns
+  // its last k-block: the others park fp32 partials in sk_ws[tile][piece] and bump sk_flags[tile]; the owner
+  // waits for the count, adds the pieces in piece order (deterministic) and runs the normal epilogue.
+  // Each CTA processes its non-final piece first and its tile-finishing piece last, so nobody waits on a CTA
+  // that is itself waiting.  Requires n_tiles == 1 and splits == 1.
   int sched;
-  float* sk_ws;            // [m_tiles][BLOCK_N][128] fp32 head partials
-  int* sk_flags;           // [m_tiles], 0 between launches
+  int sk_slots;            // partial slots per tile
+  float* sk_ws;            // [m_tiles][sk_slots][BLOCK_N][128] fp32
+  int* sk_flags;           // [m_tiles] arrival counters, 0 between launches
 };
 
 constexpr int kGemmBlockM = 128;
@@ -66,9 +70,17 @@ struct GemmCfg {
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 
-struct GemmSeg { int m_t, n_t, kb0, kb1, split, type; };  // type: 0 full, 1 head (partial -> workspace), 2 tail (adds partial)
+struct GemmSeg { int m_t, n_t, kb0, kb1, split, type, slot; };  // type: 0 full tile, 1 partial piece -> workspace slot, 2 tile-finishing piece (adds `slot` parked pieces)
+
+__device__ __forceinline__ int sk_owner(long long it, long long W, int P) {   // CTA whose range contains iteration `it`
+  int c = (int)((it * P) / W);
+  while (W * (c + 1) / P <= it) ++c;
+  while (W * c / P > it) --c;
+  return c;
+}
 
 __device__ __forceinline__ bool gemm_get_seg(const GemmParams& p, int idx, GemmSeg& g) {
+  g.slot = 0;
   if (p.sched == 0) {
     const int u = blockIdx.x + idx * gridDim.x;
     if (u >= p.m_tiles * p.n_tiles * p.splits) return false;
@@ -86,25 +98,30 @@ __device__ __forceinline__ bool gemm_get_seg(const GemmParams& p, int idx, GemmS
     g.type = 0;
     return true;
   }
-  // stream-K: processing order is head piece first (so nobody ever waits for it), full tiles, tail piece last
-  const long long W = (long long)p.m_tiles * p.kb_total;
-  const long long lo = W * blockIdx.x / gridDim.x, hi = W * (blockIdx.x + 1) / gridDim.x;
+  const int P = gridDim.x, c = blockIdx.x, KB = p.kb_total;
+  const long long W = (long long)p.m_tiles * KB;
+  const long long lo = W * c / P, hi = W * (c + 1) / P;
   if (lo >= hi) return false;
-  const int KB = p.kb_total;
   const int t0 = (int)(lo / KB), k_lo = (int)(lo % KB);
   const int t1 = (int)((hi - 1) / KB), k_hi = (int)((hi - 1) % KB) + 1;
-  // every range is >= kb_total long (m_tiles >= gridDim.x), so a range inside one tile is exactly that tile and a
-  // tile is never cut into more than two pieces
-  const int has_tail = (k_lo > 0) ? 1 : 0;   // our first tile was started by the previous CTA
-  const int has_head = (k_hi < KB) ? 1 : 0;  // our last tile is finished by the next CTA
-  const int f0 = t0 + has_tail, f1 = t1 - has_head;
+  const int has_piece = (k_hi < KB) ? 1 : 0;                                   // last tile of the range is finished by a later CTA
+  const int has_tail = (k_lo > 0 && !(t0 == t1 && has_piece)) ? 1 : 0;          // first tile was started by an earlier CTA, we finish it
+  const int f0 = t0 + ((k_lo > 0) ? 1 : 0), f1 = t1 - has_piece;
   const int n_full = max(0, f1 - f0 + 1);
   g.n_t = 0; g.split = 0;
-  if (idx < has_head) { g.m_t = t1; g.kb0 = 0; g.kb1 = k_hi; g.type = 1; return true; }
-  idx -= has_head;
+  if (idx < has_piece) {
+    g.m_t = t1; g.kb0 = (t0 == t1) ? k_lo : 0; g.kb1 = k_hi; g.type = 1;
+    g.slot = c - sk_owner((long long)t1 * KB, W, P);
+    return true;
+  }
+  idx -= has_piece;
   if (idx < n_full) { g.m_t = f0 + idx; g.kb0 = 0; g.kb1 = KB; g.type = 0; return true; }
   idx -= n_full;
-  if (idx < has_tail) { g.m_t = t0; g.kb0 = k_lo; g.kb1 = KB; g.type = 2; return true; }
+  if (idx < has_tail) {
+    g.m_t = t0; g.kb0 = k_lo; g.kb1 = KB; g.type = 2;
+    g.slot = c - sk_owner((long long)t0 * KB, W, P);   // number of parked pieces to wait for
+    return true;
+  }
   return false;
 }
 
@@ -236,11 +253,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int n0 = n_t * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      float* skw = (sg.type != 0) ? p.sk_ws + ((long long)m_t * BLOCK_N) * kGemmBlockM + q * 32 + lane : nullptr;
-      if (sg.type == 2) {   // wait for the other CTA's partial of this tile
+      const long long sk_piece = (long long)BLOCK_N * kGemmBlockM;
+      float* skw = (sg.type != 0) ? p.sk_ws + ((long long)m_t * p.sk_slots) * sk_piece + q * 32 + lane : nullptr;
+      if (sg.type == 2) {   // wait until every other piece of this tile has been parked
         if (threadIdx.x == 64) {
           uint32_t spins = 0;
-          while (*reinterpret_cast<volatile int*>(p.sk_flags + m_t) != 1) {
+          while (*reinterpret_cast<volatile int*>(p.sk_flags + m_t) != sg.slot) {
             if (++spins > (1u << 28)) { printf("b200: stream-K flag timeout (tile %d)\n", m_t); __trap(); }
           }
           __threadfence();
@@ -261,14 +279,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
         }
         const int nvalid = min(CH, p.N - (n0 + c0));
-        if (sg.type == 1) {          // head piece: park the fp32 accumulators, the tail owner finishes the tile
+        if (sg.type == 1) {          // park the fp32 accumulators of this piece, the tile's owner finishes it
+          float* w = skw + (long long)sg.slot * sk_piece;
 #pragma unroll
-          for (int j = 0; j < CH; ++j) skw[(long long)(c0 + j) * kGemmBlockM] = v[j];
+          for (int j = 0; j < CH; ++j) w[(long long)(c0 + j) * kGemmBlockM] = v[j];
           continue;
         }
-        if (sg.type == 2) {
+        if (sg.type == 2) {          // pieces are added in piece (= k) order, then this CTA's own tail
+          float acc[CH];
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] += __ldcg(skw + (long long)(c0 + j) * kGemmBlockM);
+          for (int j = 0; j < CH; ++j) acc[j] = 0.f;
+          for (int sl = 0; sl < sg.slot; ++sl) {
+            const float* w = skw + (long long)sl * sk_piece;
+#pragma unroll
+            for (int j = 0; j < CH; ++j) acc[j] += __ldcg(w + (long long)(c0 + j) * kGemmBlockM);
+          }
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] += acc[j];
         }
         if constexpr (EPI == EPI_STORE || EPI == EPI_STORE_RES) {
           if (m < p.M) {
@@ -369,7 +396,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (sg.type == 1) {          // publish the partial
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) atomicExch(p.sk_flags + m_t, 1);
+        if (threadIdx.x == 64) atomicAdd(p.sk_flags + m_t, 1);
       } else if (sg.type == 2) {   // consumed: leave the flag clean for the next launch / graph replay
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 64) atomicExch(p.sk_flags + m_t, 0);

@@ -114,7 +114,8 @@ struct GemmArgs {
   bool stream_a;                    // true: A is the weight (decode) -> evict-first on A, keep B
   float* sk_ws = nullptr;           // stream-K workspace / flags (optional): enables balanced scheduling for
   int* sk_flags = nullptr;          // single-split swap-AB GEMMs whose tile count is not a multiple of the SM count
-  int sk_tiles = 0;                 // capacity of the workspace in tiles
+  size_t sk_ws_floats = 0;          // capacity of the workspace
+  int sk_tiles = 0;                 // capacity of the flag array
 };
 
 inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStream_t s) {
@@ -142,12 +143,22 @@ inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStr
     p.l2_prefetch_kb = a.stream_a ? l2pf : 0;
   }
   const int units = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = units < num_sms ? units : num_sms;
+  int grid = units < num_sms ? units : num_sms;
   static const bool sk_on = getenv("B200_NO_STREAMK") == nullptr;
-  p.sched = 0; p.sk_ws = a.sk_ws; p.sk_flags = a.sk_flags;
-  if (sk_on && a.sk_ws && a.sk_flags && a.stream_a && p.splits == 1 && p.n_tiles == 1 && p.m_tiles >= num_sms &&
-      p.m_tiles <= a.sk_tiles && (p.m_tiles % num_sms) != 0 && (a.epi == EPI_T_STORE || a.epi == EPI_T_SWIGLU))
-    p.sched = 1;
+  p.sched = 0; p.sk_slots = 0; p.sk_ws = a.sk_ws; p.sk_flags = a.sk_flags;
+  // only when every tile is cut into at most two pieces (m_tiles >= SMs): finishing many-piece tiles inside the
+  // kernel serialises the reduction on the tile owner and measured slower than split-K + a reducing consumer
+  const bool sk_any = getenv("B200_STREAMK_ANY") != nullptr;
+  if (sk_on && a.sk_ws && a.sk_flags && a.stream_a && p.splits == 1 && p.n_tiles == 1 && p.m_tiles <= a.sk_tiles &&
+      (p.m_tiles >= num_sms || sk_any) && (p.m_tiles % num_sms) != 0 && (a.epi == EPI_T_STORE || a.epi == EPI_T_SWIGLU)) {
+    const long long W = (long long)p.m_tiles * p.kb_total;
+    const int g2 = (int)std::min<long long>(num_sms, W);
+    const long long per_min = W / g2;                                   // >= 1
+    const int slots = (int)((p.kb_total + per_min - 1) / per_min) + 1;    // pieces a tile can be cut into, minus the owner
+    if ((size_t)p.m_tiles * slots * a.block_n * kGemmBlockM <= a.sk_ws_floats) {
+      p.sched = 1; p.sk_slots = slots; grid = g2;
+    }
+  }
   B200_REQUIRE(p.splits == 1 || a.epi == EPI_T_PARTIAL, "split-K only with the fp32 partial epilogue");
 #define B200_GEMM_CASE(BN, E) \
   if (a.block_n == BN && a.epi == E) return launch_gemm_inst<BN, E>(ta, tb, p, grid, s);

@@ -96,9 +96,13 @@ def test_gemm_swapab_store(lib, bn, batch, nout, K):
     _cmp(f"gemm_T_store bn{bn} b{batch}", out, x.float() @ W.float().T, 2e-3, RTOL)
 
 
-@pytest.mark.parametrize("nout,K,batch,bn", [(28672, 512, 32, 32), (19072, 1024, 5, 16), (128256, 512, 33, 64), (37888, 512, 32, 32)])
-def test_gemm_streamk_store(lib, nout, K, batch, bn):
-    """>= 148 weight tiles and not a multiple of 148: balanced stream-K scheduling with cross-CTA fix-up."""
+@pytest.mark.parametrize("nout,K,batch,bn", [(28672, 512, 32, 32), (19072, 1024, 5, 16), (128256, 512, 33, 64), (37888, 512, 32, 32),
+                                              (4096, 4096, 32, 32), (512, 14336, 32, 32), (6144, 4096, 64, 64), (1031, 512, 7, 16),
+                                              (128, 4096, 32, 32), (3584, 4096, 32, 32)])
+def test_gemm_streamk_store(lib, nout, K, batch, bn, monkeypatch):
+    """Balanced stream-K scheduling with cross-CTA fix-up (two pieces per tile by default; B200_STREAMK_ANY also
+    exercises the many-pieces-per-tile path on the small shapes)."""
+    monkeypatch.setenv("B200_STREAMK_ANY", "1")
     W, x = _rand(nout, K, scale=1 / math.sqrt(K), seed=4), _rand(batch, K, seed=5)
     for rep in range(3):   # flags must be left clean between launches
         out = torch.full((batch, nout), float("nan"), dtype=torch.bfloat16, device=DEV)
