@@ -51,6 +51,13 @@ int b200_engine_create(const b200_model_config_t* cfg, const void* nccl_unique_i
 int b200_engine_destroy(b200_engine_t* e);
 int b200_nccl_unique_id(void* out128);
 
+/* Tensor parallel, optional fast path: every rank exports a 64-byte IPC handle of its exchange block and imports
+ * the handles of all ranks (index = tp_rank; distributed by the host).  With it the per-layer all-reduce of the
+ * decode step runs inside one kernel over NVLink peer memory (fused with the split-K reduce, residual add and
+ * RMSNorm); without it the engine uses ncclAllReduce. */
+int b200_engine_ipc_export(b200_engine_t* e, void* handle64);
+int b200_engine_ipc_import(b200_engine_t* e, const void* handles, int32_t n);
+
 /* Weights, by HF state_dict name (what AutoModelForCausalLM.from_pretrained would load,
  * generative_model.py:249-254).  `data` is the FULL (unsharded) bf16 tensor, row-major, on the host
  * (on_device=0) or on this engine's GPU (on_device=1); the engine copies the shard of its tp_rank and

@@ -77,6 +77,8 @@ def load() -> C.CDLL:
     lib.b200_batcher_config.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     lib.b200_batcher_add.argtypes = [vp, i64, i32, C.POINTER(i64)]
     lib.b200_batcher_tick.argtypes = [vp, i64, i32, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
+    lib.b200_engine_ipc_export.argtypes = [vp, vp]
+    lib.b200_engine_ipc_import.argtypes = [vp, vp, i32]
     lib.b200_debug_trace.argtypes = [i32]
     lib.b200_debug_trace_read.argtypes = [vp, i32, C.POINTER(i32)]
     _lib = lib

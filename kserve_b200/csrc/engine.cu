@@ -147,6 +147,12 @@ struct b200_engine {
   TmapCache tmaps;
   // comm
   Nccl::Comm comm = nullptr;
+  // peer-memory exchange (decode): IPC-shared block of this rank + mapped blocks of the peers
+  unsigned char* ar_local = nullptr;
+  void* ar_peer_map[kMaxTp] = {nullptr};
+  int *row_epoch = nullptr, *cand_epoch = nullptr;
+  bool p2p_ready = false;
+  P2P p2p{};
   b200_timing_t timing{};
   int launches = 0;
 };
@@ -256,6 +262,12 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
             e->launches++;
             return 0;
           }
+          if (e->p2p_ready) {   // split-K reduce + all-reduce over peer memory + residual + RMSNorm in one kernel
+            B200_CUDA_OK(launch_k(allreduce_norm_kernel, dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, e->p2p,
+                                  e->x, next_norm, e->xn, eps, (const float*)e->ws, sp, (long long)B * H, (long long)H, (const bf16*)nullptr));
+            e->launches++;
+            return 0;
+          }
           B200_CUDA_OK(launch_k(reduce_partials_kernel, dim3(T), dim3(256), 0, s, (const float*)e->ws, sp, (long long)B * H, (long long)H, e->ybuf, H));
           e->launches++;
         } else {
@@ -263,6 +275,12 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
           a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
           if ((rc2 = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc2;
           e->launches++;
+          if (tp && e->p2p_ready) {
+            B200_CUDA_OK(launch_k(allreduce_norm_kernel, dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, e->p2p,
+                                  e->x, next_norm, e->xn, eps, (const float*)nullptr, 0, 0LL, 0LL, (const bf16*)e->ybuf));
+            e->launches++;
+            return 0;
+          }
         }
       } else {
         if (!tp) {
@@ -284,9 +302,20 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
     if ((rc = row_parallel(e->attn, e->nh * kHeadDim, w.wo, w.ln2))) return rc;
     // ---- gate/up projection with the SwiGLU fused into the epilogue
     if (decode) {
-      GemmArgs a{w.wgu, 2 * e->I, e->xn, e->cap_T, 2 * e->I, B, H, EPI_T_SWIGLU, bn, 1, e->hbuf, nullptr, e->I, 0, e->I, true};
-      a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
-      if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+      const int gu_tiles = (2 * e->I + kGemmBlockM - 1) / kGemmBlockM;
+      const int gsp = (gu_tiles * 4 >= e->num_sms * 3) ? 1 : pick_splits(e, 2 * e->I, H);
+      if (gsp > 1) {   // few tiles per GPU (tensor parallel): split-K partials + a reducing SwiGLU kernel
+        GemmArgs a{w.wgu, 2 * e->I, e->xn, e->cap_T, 2 * e->I, B, H, EPI_T_PARTIAL, bn, gsp, e->ws, nullptr, 2 * e->I,
+                   (long long)B * 2 * e->I, 0, true};
+        if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+        B200_CUDA_OK(launch_k(swiglu_reduce_kernel, dim3(B), dim3(512), 0, s, (const float*)e->ws, gsp, (long long)B * 2 * e->I,
+                              (long long)2 * e->I, e->hbuf, e->I));
+        e->launches++;
+      } else {
+        GemmArgs a{w.wgu, 2 * e->I, e->xn, e->cap_T, 2 * e->I, B, H, EPI_T_SWIGLU, bn, 1, e->hbuf, nullptr, e->I, 0, e->I, true};
+        a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
+        if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+      }
     } else {
       GemmArgs a{e->xn, e->cap_T, w.wgu, 2 * e->I, T, 2 * e->I, H, EPI_SWIGLU, 256, 1, e->hbuf, nullptr, e->I, 0, e->I, false};
       if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
@@ -306,12 +335,13 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
              e->logits, nullptr, e->Vl, 0, 0, true};
   a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
   if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
-  B200_CUDA_OK(launch_k(argmax_kernel, dim3(B), dim3(1024), 0, s, (const bf16*)e->logits, (long long)e->Vl, e->Vl, e->v0, e->cand_val, e->cand_idx));
+  const int use_p2p = (e->cfg.tp_size > 1 && e->p2p_ready) ? 1 : 0;
+  B200_CUDA_OK(launch_k(argmax_kernel, dim3(B), dim3(1024), 0, s, (const bf16*)e->logits, (long long)e->Vl, e->Vl, e->v0, e->cand_val, e->cand_idx, e->p2p, use_p2p));
   e->launches += 2;
   const float* cv = e->cand_val;
   const int32_t* ci = e->cand_idx;
   int ranks = 1;
-  if (e->cfg.tp_size > 1) {
+  if (e->cfg.tp_size > 1 && !use_p2p) {
     Nccl& n = Nccl::get();
     B200_NCCL_OK(n.AllGather(e->cand_val, e->cand_val_all, B, Nccl::kFloat, e->comm, s));
     B200_NCCL_OK(n.AllGather(e->cand_idx, e->cand_idx_all, B, Nccl::kInt32, e->comm, s));
@@ -325,6 +355,7 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
   sp.eos = e->d_eos; sp.num_eos = e->st.num_eos; sp.pad_token = e->st.pad;
   sp.stop_tok = e->d_stop_tok; sp.stop_off = e->d_stop_off; sp.num_stop = e->st.num_stop;
   sp.st = e->d_state;
+  sp.pp = e->p2p; sp.use_p2p = use_p2p;
   B200_CUDA_OK(launch_k(step_update_kernel, dim3(1), dim3(128), 0, s, sp));
   e->launches++;
   return 0;
@@ -633,7 +664,7 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   B200_CUDA_OK(cudaMemset(e->attn, 0, T * e->nh * kHeadDim * 2));
   B200_CUDA_OK(cudaMemset(e->hbuf, 0, T * e->I * 2));
   B200_CUDA_OK(cudaMemset(e->xl, 0, (size_t)c->max_batch * H * 2));
-  e->ws_elems = (size_t)16 * c->max_batch * std::max(e->qkv_cols, e->H);
+  e->ws_elems = (size_t)16 * c->max_batch * std::max(std::max(e->qkv_cols, e->H), 2 * e->I);
   if ((rc = dmalloc(&e->ws, e->ws_elems))) return rc;
   e->sk_tiles = (std::max(2 * e->I, e->Vl) + kGemmBlockM - 1) / kGemmBlockM;
   e->sk_ws_floats = std::max<size_t>((size_t)e->sk_tiles * 2 * 64 * kGemmBlockM, (size_t)8 << 20);   // >= 32 MB
@@ -680,6 +711,15 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
     B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_pred), raw * 8));
   }
   if (tp > 1) {
+    B200_REQUIRE(tp <= kMaxTp && c->max_batch <= kArRows, "tp_size / max_batch exceed the peer-exchange layout");
+    const ArLayout lay = ArLayout::make(e->H);
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->ar_local), lay.total));
+    B200_CUDA_OK(cudaMemset(e->ar_local, 0, lay.total));
+    if ((rc = dmalloc(&e->row_epoch, (size_t)kArRows))) return rc;
+    if ((rc = dmalloc(&e->cand_epoch, (size_t)kArRows))) return rc;
+    B200_CUDA_OK(cudaMemset(e->row_epoch, 0, kArRows * sizeof(int)));
+    B200_CUDA_OK(cudaMemset(e->cand_epoch, 0, kArRows * sizeof(int)));
+    e->p2p.tp = tp; e->p2p.rank = c->tp_rank; e->p2p.lay = lay; e->p2p.row_epoch = e->row_epoch; e->p2p.cand_epoch = e->cand_epoch;
     Nccl& n = Nccl::get();
     B200_REQUIRE(n.ok, "tp_size > 1 needs libnccl.so.2");
     B200_REQUIRE(nccl_id != nullptr, "tp_size > 1 needs an NCCL unique id");
@@ -698,6 +738,10 @@ int b200_engine_destroy(b200_engine_t* e) {
   cudaDeviceSynchronize();
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   if (e->comm) Nccl::get().CommDestroy(e->comm);
+  for (int r = 0; r < kMaxTp; ++r) if (e->ar_peer_map[r]) cudaIpcCloseMemHandle(e->ar_peer_map[r]);
+  if (e->ar_local) cudaFree(e->ar_local);
+  if (e->row_epoch) cudaFree(e->row_epoch);
+  if (e->cand_epoch) cudaFree(e->cand_epoch);
   void* ptrs[] = {e->embed, e->lm_head, e->final_norm, e->cos_tab, e->sin_tab, e->kcache, e->vcache, e->d_page_table,
                   e->x, e->xn, e->qkv, e->attn, e->hbuf, e->ybuf, e->xl, e->qdec, e->logits, e->ws, e->sk_ws, e->sk_flags, e->part_o, e->part_ml,
                   e->cand_val, e->cand_idx, e->cand_val_all, e->cand_idx_all, e->d_tok, e->d_tok_seq, e->d_tok_pos, e->d_cu,
@@ -1013,6 +1057,35 @@ int b200_engine_last_timing(b200_engine_t* e, b200_timing_t* out) {
   return 0;
 }
 
+// ---- peer-memory exchange setup (tensor parallel) --------------------------------------------------
+int b200_engine_ipc_export(b200_engine_t* e, void* handle64) {
+  B200_REQUIRE(e && handle64, "null argument");
+  B200_REQUIRE(e->ar_local != nullptr, "engine was created with tp_size == 1");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  cudaIpcMemHandle_t h;
+  B200_CUDA_OK(cudaIpcGetMemHandle(&h, e->ar_local));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+int b200_engine_ipc_import(b200_engine_t* e, const void* handles, int32_t n) {
+  B200_REQUIRE(e && handles, "null argument");
+  B200_REQUIRE(n == e->cfg.tp_size && e->ar_local != nullptr, "need one handle per rank");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  for (int r = 0; r < n; ++r) {
+    if (r == e->cfg.tp_rank) { e->p2p.peer[r] = e->ar_local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, reinterpret_cast<const unsigned char*>(handles) + (size_t)r * 64, 64);
+    void* p = nullptr;
+    B200_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    e->ar_peer_map[r] = p;
+    e->p2p.peer[r] = reinterpret_cast<unsigned char*>(p);
+  }
+  e->p2p_ready = getenv("B200_NO_P2P") == nullptr;
+  return 0;
+}
+
 // ---- debug timeline ---------------------------------------------------------------------------------
 static TraceRec* g_trace_dev = nullptr;
 int b200_debug_trace(int32_t capacity) {
@@ -1109,7 +1182,7 @@ int b200_op_rope_kv(const void* qkv, int64_t ld, void* q_out, int64_t ldq, void*
 }
 
 int b200_op_argmax(const void* logits, int64_t ld, int B, int V, float* out_val, int32_t* out_idx, void* stream) {
-  argmax_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, V, 0, out_val, out_idx);
+  argmax_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, V, 0, out_val, out_idx, P2P{}, 0);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "gemm_tcgen05.cuh"
 #include "ops.cuh"
+#include "p2p.cuh"
 
 namespace b200 {
 

@@ -4,6 +4,7 @@
 // modules the reference executes (modeling_llama.py:62-67 RMSNorm, :146-168 RoPE).
 #pragma once
 #include "common.cuh"
+#include "p2p_base.cuh"
 
 namespace b200 {
 
@@ -270,13 +271,37 @@ __global__ void __launch_bounds__(512) rope_kv_kernel(const RopeKvParams p) {
   }
 }
 
+// SwiGLU over split-K partials of the interleaved gate/up projection (used when the per-GPU weight has too few
+// 128-row tiles to fill the SMs without split-K, i.e. under tensor parallelism):
+//   h[r][f] = bf16( bf16(silu(bf16(sum_s gate_s))) * bf16(sum_s up_s) ),  partial columns interleaved {16 gate,16 up}
+__global__ void __launch_bounds__(512)
+swiglu_reduce_kernel(const float* __restrict__ partial, int splits, long long split_stride, long long ld_partial,
+                     bf16* __restrict__ h, int I) {
+  TraceScope _ts(TK_OTHER);
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r = blockIdx.x;
+  for (int f = threadIdx.x * 8; f < I; f += blockDim.x * 8) {
+    const int gcol = ((f >> 4) << 5) + (f & 15);
+    float g[8], u[8], o[8];
+    sum_partials8(partial + (long long)r * ld_partial + gcol, splits, split_stride, g);
+    sum_partials8(partial + (long long)r * ld_partial + gcol + 16, splits, split_stride, u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float gg = bf16_round(g[i]);
+      o[i] = bf16_round(__fdividef(gg, 1.0f + __expf(-gg))) * bf16_round(u[i]);
+    }
+    *reinterpret_cast<uint4*>(h + (long long)r * I + f) = pack8(o);
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // greedy argmax over bf16 logits (== argmax of logits.float(), transformers generation/utils.py:2762,
 // 2793); ties -> lowest index like torch.argmax on CPU.  Also emits (max, idx) for the vocab-parallel case.
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 argmax_kernel(const bf16* __restrict__ logits, long long ld, int V, int idx_offset, float* __restrict__ out_val,
-              int32_t* __restrict__ out_idx) {
+              int32_t* __restrict__ out_idx, const P2P pp, int use_p2p) {
   TraceScope _ts(TK_ARGMAX);
   pdl_launch_dependents();
   pdl_wait();
@@ -312,6 +337,7 @@ argmax_kernel(const bf16* __restrict__ logits, long long ld, int V, int idx_offs
     if (l == 0) {
       out_val[b] = best;
       out_idx[b] = bi + idx_offset;
+      if (use_p2p) push_candidate(pp, b, best, bi + idx_offset);   // vocab-parallel: hand the candidate to every rank
     }
   }
 }
@@ -342,6 +368,7 @@ struct StepParams {
   const int32_t* eos; int num_eos; int32_t pad_token;
   const int32_t* stop_tok; const int32_t* stop_off; int num_stop;  // flattened stop sequences
   StepState* st;
+  P2P pp; int use_p2p;                    // vocab-parallel candidates arrive through peer memory
 };
 
 __global__ void __launch_bounds__(128) step_update_kernel(const StepParams p) {
@@ -357,7 +384,8 @@ __global__ void __launch_bounds__(128) step_update_kernel(const StepParams p) {
   for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
     float best = p.cand_val[b];
     int tok = p.cand_idx[b];
-    for (int r = 1; r < p.ranks; ++r) {
+    if (p.use_p2p) merge_candidates(p.pp, b, best, tok);
+    for (int r = 1; r < p.ranks && !p.use_p2p; ++r) {
       const float v = p.cand_val[r * p.B + b];
       const int i = p.cand_idx[r * p.B + b];
       if (v > best || (v == best && i < tok)) { best = v; tok = i; }

@@ -73,6 +73,22 @@ class B200Engine:
         _lib.check(self.lib.b200_engine_set_rope_table(self.h, cos.data_ptr(), sin.data_ptr(), mc.max_position),
                    "b200_engine_set_rope_table")
         self._cb_keepalive = None
+        if tp_size > 1:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.setup_p2p()      # collective: every rank constructs its engine at the same point
+
+    def setup_p2p(self) -> None:
+        """Exchange the IPC handles of the peer-memory blocks (torch.distributed is only the courier)."""
+        if self.tp_size == 1:
+            return
+        import torch.distributed as dist
+        raw = C.create_string_buffer(64)
+        _lib.check(self.lib.b200_engine_ipc_export(self.h, raw), "b200_engine_ipc_export")
+        gathered = [None] * self.tp_size
+        dist.all_gather_object(gathered, bytes(raw.raw))
+        blob = C.create_string_buffer(b"".join(gathered), 64 * self.tp_size)
+        _lib.check(self.lib.b200_engine_ipc_import(self.h, blob, self.tp_size), "b200_engine_ipc_import")
 
     # ------------------------------------------------------------------ weights
     def set_weight(self, name: str, t: torch.Tensor) -> None:

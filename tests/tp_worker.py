@@ -19,11 +19,11 @@ def main():
     from kserve_b200.engine import B200Engine
     from kserve_b200.tp import broadcast_nccl_id
     from oracle import weights as W
-    nccl_id = broadcast_nccl_id(rank)
     out = {}
     for name in ("tiny_g4_ids", "tiny_g2_ids"):
         c = load_case(name)
         m = c["meta"]
+        nccl_id = broadcast_nccl_id(rank)   # an ncclUniqueId is single-use: one per communicator
         eng = B200Engine(W.CONFIGS[m["cfg"]], max_batch=8, max_seq_len=512, device=int(os.environ["LOCAL_RANK"]),
                          tp_rank=rank, tp_size=world, nccl_id=nccl_id)
         eng.load_weights(W.iter_state_dict(W.CONFIGS[m["cfg"]], m["seed"]))
