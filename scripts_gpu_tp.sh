@@ -1,13 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
 N=${1:-2}
-if [ "$N" = "2" ]; then
+if [ "$2" = "test" ]; then
 timeout 600 python -m pytest tests/test_tp_gpu.py -m gpu -q --timeout 500 > gpurun_out/tp_test.log 2>&1
-grep -vE "^\s*$|Deprecation|importlib" gpurun_out/tp_test.log | cut -c1-1500 | tail -8
+grep -vE "^\s*$|Deprecation|importlib" gpurun_out/tp_test.log | cut -c1-600 | tail -4
 fi
-for mode in p2p nccl; do
-  unset B200_NO_P2P
-  [ $mode = nccl ] && export B200_NO_P2P=1
+for mode in p2p; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_tp${N}_$mode.json 2> gpurun_out/bench_tp${N}_$mode.err
   grep -iE "error|Traceback|timeout" gpurun_out/bench_tp${N}_$mode.err | head -5
   python -c "
