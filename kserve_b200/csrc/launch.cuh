@@ -8,6 +8,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm_2cta.cuh"
 #include "ops.cuh"
 #include "p2p.cuh"
 
@@ -106,6 +107,29 @@ int launch_gemm_inst(const CUtensorMap* ta, const CUtensorMap* tb, const GemmPar
   return 0;
 }
 
+template <int EPI>
+int launch_gemm_2cta_inst(const CUtensorMap* ta, const CUtensorMap* tb, const GemmParams& p, int num_sms, cudaStream_t s) {
+  auto kern = gemm_tn_2cta_kernel<EPI>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));
+    configured = true;
+  }
+  const int units = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int clusters = std::min(units, num_sms / 2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = k2SmemBytes; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_enabled() && pdl_phase()) ? 2 : 1;
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, *ta, *tb, p));
+  return 0;
+}
+
 struct GemmArgs {
   const bf16* A; int a_rows;        // rows of the A buffer as declared to TMA (>= M)
   const bf16* B; int b_rows;        // rows of the B buffer as declared to TMA (>= N)
@@ -161,6 +185,15 @@ inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStr
     }
   }
   B200_REQUIRE(p.splits == 1 || a.epi == EPI_T_PARTIAL, "split-K only with the fp32 partial epilogue");
+  const bool use_2cta = getenv("B200_NO_2CTA") == nullptr;
+  if (use_2cta && a.block_n == 256 && a.epi <= EPI_SWIGLU) {
+    const CUtensorMap* tb2;
+    int rc2 = cache.get(a.B, a.b_rows, a.K, 128, &tb2);   // each CTA of the pair stages half of the 256 weight rows
+    if (rc2) return rc2;
+    if (a.epi == EPI_STORE) return launch_gemm_2cta_inst<EPI_STORE>(ta, tb2, p, num_sms, s);
+    if (a.epi == EPI_STORE_RES) return launch_gemm_2cta_inst<EPI_STORE_RES>(ta, tb2, p, num_sms, s);
+    return launch_gemm_2cta_inst<EPI_SWIGLU>(ta, tb2, p, num_sms, s);
+  }
 #define B200_GEMM_CASE(BN, E) \
   if (a.block_n == BN && a.epi == E) return launch_gemm_inst<BN, E>(ta, tb, p, grid, s);
   B200_GEMM_CASE(256, EPI_STORE)
