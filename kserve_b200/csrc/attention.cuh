@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_prefill_kernel(const AttnPr
   TraceScope _ts(TK_ATTN_PREFILL);
   pdl_launch_dependents();
   pdl_wait();
+  _ts.mark();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
   const int tok0 = p.cu_seqlens[b];
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
   TraceScope _ts(TK_ATTN_DECODE);
   pdl_launch_dependents();
   pdl_wait();
+  _ts.mark();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int bh = blockIdx.x, split = blockIdx.y;
   const int b = bh / p.nkv, kvh = bh - b * p.nkv;
@@ -464,6 +466,7 @@ attn_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ 
   TraceScope _ts(TK_ATTN_COMBINE);
   pdl_launch_dependents();
   pdl_wait();
+  _ts.mark();
   const int bhq = blockIdx.x;            // b * nh + head
   const int nh = nkv * G;
   const int b = bhq / nh, head = bhq - b * nh;

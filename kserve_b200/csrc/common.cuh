@@ -79,7 +79,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // Optional per-CTA timeline (debug): when enabled through b200_debug_trace(), thread 0 of every CTA appends
 // {kind, block, globaltimer at entry, at exit}; off by default (one predictable branch per CTA).
 // ---------------------------------------------------------------------------------------------
-struct TraceRec { unsigned long long t0, t1; int kind, block; };
+struct TraceRec { unsigned long long t0, t1, tmid; int kind, block; };
 __device__ TraceRec* g_trace_buf = nullptr;
 __device__ unsigned int g_trace_cap = 0;
 __device__ unsigned int g_trace_cnt = 0;
@@ -91,8 +91,9 @@ __device__ __forceinline__ unsigned long long global_timer() {
   return t;
 }
 struct TraceScope {
-  unsigned long long t0 = 0;
+  unsigned long long t0 = 0, tmid = 0;
   int kind;
+  __device__ __forceinline__ void mark() { if (threadIdx.x == 0 && t0 != 0) tmid = global_timer(); }
   __device__ __forceinline__ explicit TraceScope(int k) : kind(k) {
     if (threadIdx.x == 0 && g_trace_buf != nullptr) t0 = global_timer();
   }
@@ -100,7 +101,7 @@ struct TraceScope {
     if (threadIdx.x == 0 && t0 != 0) {
       const unsigned int i = atomicAdd(&g_trace_cnt, 1u);
       if (i < g_trace_cap) {
-        TraceRec r; r.t0 = t0; r.t1 = global_timer(); r.kind = kind; r.block = blockIdx.x;
+        TraceRec r; r.t0 = t0; r.t1 = global_timer(); r.tmid = tmid; r.kind = kind; r.block = blockIdx.x;
         g_trace_buf[i] = r;
       }
     }

@@ -187,6 +187,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int npf = min(npre + p.l2_prefetch_kb, kb1 - kb0);
             for (int i = npre; i < npf; ++i) tma_prefetch_l2_2d(&tmap_a, (kb0 + i) * kGemmBlockK, m_t * kGemmBlockM);
             pdl_wait();
+            _ts.mark();
             for (int i = 0; i < npre; ++i)
               tma_load_2d(smem + i * Cfg::kStageBytes + Cfg::kABytes, &tmap_b, &full_bar[i], (kb0 + i) * kGemmBlockK, n_t * BLOCK_N, p.hint_b);
             kb = kb0 + npre;

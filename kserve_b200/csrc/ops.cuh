@@ -19,6 +19,7 @@ __global__ void embed_gather_kernel(const int32_t* __restrict__ tokens, const bf
   TraceScope _ts(TK_EMBED);
   pdl_launch_dependents();
   pdl_wait();
+  _ts.mark();
   const int t = blockIdx.x;
   int tok = tokens[t];
   tok = max(0, min(tok, vocab_rows - 1));
@@ -93,6 +94,7 @@ rmsnorm_kernel(bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restric
   uint4 wpre = make_uint4(0, 0, 0, 0);
   if (single && (int)threadIdx.x * 8 < H) wpre = *reinterpret_cast<const uint4*>(w + threadIdx.x * 8);
   pdl_wait();
+  _ts.mark();
   float ss = 0.f;
   for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
     uint4 u = *reinterpret_cast<const uint4*>(xr + i);
@@ -163,6 +165,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int sp
   TraceScope _ts(TK_OTHER);
   pdl_launch_dependents();
   pdl_wait();
+  _ts.mark();
   const int r = blockIdx.x;
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     float a = 0.f;
@@ -219,6 +222,7 @@ __global__ void __launch_bounds__(512) rope_kv_kernel(const RopeKvParams p) {
   TraceScope _ts(TK_ROPE);
   pdl_launch_dependents();
   pdl_wait();
+  _ts.mark();
   const int t = blockIdx.x;
   const int pos = p.tok_pos[t];
   const int seq = p.tok_seq[t];
@@ -280,6 +284,7 @@ swiglu_reduce_kernel(const float* __restrict__ partial, int splits, long long sp
   TraceScope _ts(TK_OTHER);
   pdl_launch_dependents();
   pdl_wait();
+  _ts.mark();
   const int r = blockIdx.x;
   for (int f = threadIdx.x * 8; f < I; f += blockDim.x * 8) {
     const int gcol = ((f >> 4) << 5) + (f & 15);
@@ -305,6 +310,7 @@ argmax_kernel(const bf16* __restrict__ logits, long long ld, int V, int idx_offs
   TraceScope _ts(TK_ARGMAX);
   pdl_launch_dependents();
   pdl_wait();
+  _ts.mark();
   const int b = blockIdx.x;
   const bf16* row = logits + (long long)b * ld;
   float best = -INFINITY;
@@ -375,6 +381,7 @@ __global__ void __launch_bounds__(128) step_update_kernel(const StepParams p) {
   TraceScope _ts(TK_STEP);
   pdl_launch_dependents();
   pdl_wait();
+  _ts.mark();
   __shared__ int s_stop, s_unfinished;
   StepState* st = p.st;
   if (st->done) return;
@@ -427,6 +434,7 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ x, const int32_t* __
   TraceScope _ts(TK_OTHER);
   pdl_launch_dependents();
   pdl_wait();
+  _ts.mark();
   const uint4* src = reinterpret_cast<const uint4*>(x + (long long)row_idx[blockIdx.x] * H);
   uint4* dst = reinterpret_cast<uint4*>(out + (long long)blockIdx.x * H);
   for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = src[i];

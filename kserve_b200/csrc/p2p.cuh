@@ -34,6 +34,7 @@ allreduce_norm_kernel(const P2P pp, bf16* __restrict__ x, const bf16* __restrict
   const int slot = epoch & 1;
   bf16* ylocal = reinterpret_cast<bf16*>(pp.peer[pp.rank] + pp.lay.y_off) + ((long long)slot * kArRows + r) * H;
   pdl_wait();
+  _ts.mark();
   // 1. this rank's contribution, published in its own shared block
   for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
     float f[8];

@@ -31,38 +31,42 @@ def main():
     _lib.check(lib.b200_debug_trace(cap), "trace")
     eng.run_staged(False, 1)         # one traced decode step (graph replay)
     torch.cuda.synchronize()
-    buf = np.zeros((cap, 3), dtype=np.uint64)
+    buf = np.zeros((cap, 4), dtype=np.uint64)
     n = C.c_int32()
     _lib.check(lib.b200_debug_trace_read(buf.ctypes.data, cap, C.byref(n)), "read")
     lib.b200_debug_trace(0)
     rec = buf[: n.value]
     t0, t1 = rec[:, 0].astype(np.int64), rec[:, 1].astype(np.int64)
-    kind = (rec[:, 2] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    tm = rec[:, 2].astype(np.int64)
+    kind = (rec[:, 3] & np.uint64(0xFFFFFFFF)).astype(np.int64)
     order = np.argsort(t0)
-    t0, t1, kind = t0[order], t1[order], kind[order]
+    t0, t1, kind, tm = t0[order], t1[order], kind[order], tm[order]
     base = t0[0]
     # group consecutive records of the same kind into launches
     launches = []
-    for a, b, k in zip(t0, t1, kind):
+    for a, b, k, m in zip(t0, t1, kind, tm):
         if launches and launches[-1][0] == k and a <= launches[-1][2] + 20000 and (k % 100) != 0:
             launches[-1][2] = max(launches[-1][2], b)
             launches[-1][3] += 1
             launches[-1][4] = max(launches[-1][4], a)
+            if m: launches[-1][5] = min(launches[-1][5], m) if launches[-1][5] else m
+            if m: launches[-1][6] = max(launches[-1][6], m)
         else:
-            launches.append([k, a, b, 1, a])
+            launches.append([k, a, b, 1, a, m, m])
     print(f"{n.value} CTA records, {len(launches)} launches, step span {(t1.max() - base) / 1e3:.1f} us for {layers} layers")
     prev_end = base
     rows = []
-    for k, a, b, c, last_start in launches:
+    for k, a, b, c, last_start, wmin, wmax in launches:
         name = KIND.get(k % 100, "?")
         if k % 100 == 1:
             name += f":{EPI.get((k // 100) % 10)}:M{(k // 1000) * 128}"
-        rows.append((name, (a - base) / 1e3, (b - base) / 1e3, (b - a) / 1e3, (a - prev_end) / 1e3, c, (last_start - a) / 1e3))
+        rows.append((name, (a - base) / 1e3, (b - base) / 1e3, (b - a) / 1e3, (a - prev_end) / 1e3, c, (last_start - a) / 1e3,
+                     (wmin - base) / 1e3 if wmin else -1, (wmax - base) / 1e3 if wmax else -1))
         prev_end = max(prev_end, b)
     per = (len(rows) - 4) // layers if layers else len(rows)
-    print("name                          start     end     dur  gap_prev  ctas  cta_start_spread")
+    print("name                          start     end     dur  gap_prev  ctas  cta_start_spread  wait_done(min,max)")
     for r in rows[: 2 + 2 * per + 6]:
-        print(f"{r[0]:28s} {r[1]:7.1f} {r[2]:7.1f} {r[3]:7.1f} {r[4]:8.1f} {r[5]:5d} {r[6]:8.1f}")
+        print(f"{r[0]:28s} {r[1]:7.1f} {r[2]:7.1f} {r[3]:7.1f} {r[4]:8.1f} {r[5]:5d} {r[6]:8.1f}   {r[7]:7.1f} {r[8]:7.1f}")
     eng.close()
 
 
