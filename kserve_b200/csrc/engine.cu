@@ -1092,6 +1092,7 @@ int b200_debug_trace(int32_t capacity) {
   if (g_trace_dev) { cudaFree(g_trace_dev); g_trace_dev = nullptr; }
   TraceRec* nullp = nullptr;
   unsigned int zero = 0, cap = (unsigned int)std::max(capacity, 0);
+  { int sp = getenv("B200_TRACE_SPLIT") ? 1 : 0; cudaMemcpyToSymbol(g_trace_split, &sp, sizeof(sp)); }
   if (capacity > 0) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&g_trace_dev), sizeof(TraceRec) * capacity));
   B200_CUDA_OK(cudaMemcpyToSymbol(g_trace_cnt, &zero, sizeof(zero)));
   B200_CUDA_OK(cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap)));

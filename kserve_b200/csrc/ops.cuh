@@ -77,6 +77,8 @@ __device__ __forceinline__ void sum_partials8(const float* __restrict__ base, in
 }
 
 constexpr int kNormThreads = 512;
+__device__ int g_trace_split = 0;
+__device__ __forceinline__ bool getenv_trace_split() { return g_trace_split != 0; }
 
 template <int MODE>
 __global__ void __launch_bounds__(kNormThreads)
@@ -139,6 +141,7 @@ rmsnorm_kernel(bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restric
       ss += f[t] * f[t];
     }
   }
+  if (getenv_trace_split()) _ts.mark();
   const float tot = block_sum(ss, red);
   const float rs = 1.0f / sqrtf(tot / (float)H + eps);  // IEEE sqrt + div, as torch.rsqrt on CPU
   bf16* o = xn + (long long)r * H;

@@ -74,6 +74,34 @@ def build_llama(cfg: dict, state_dict: Dict[str, torch.Tensor], dtype=torch.bflo
     return model
 
 
+def build_mixtral(cfg: dict, state_dict: Dict[str, torch.Tensor], dtype=torch.bfloat16):
+    """MixtralForCausalLM from config + seeded weights (BASELINE configs[3] architecture)."""
+    from transformers import MixtralConfig, MixtralForCausalLM
+    hf_cfg = MixtralConfig(**cfg, tie_word_embeddings=False, eos_token_id=None, bos_token_id=None, pad_token_id=None,
+                           sliding_window=None, router_jitter_noise=0.0)
+    with torch.device("meta"):
+        model = MixtralForCausalLM(hf_cfg)
+    model = model.to_empty(device="cpu").to(dtype)
+    missing, unexpected = model.load_state_dict(state_dict, strict=False, assign=True)
+    assert not unexpected, unexpected
+    n_fixed = 0
+    for mod in model.modules():
+        if hasattr(mod, "inv_freq"):
+            inv_freq, scaling = type(mod).compute_default_rope_parameters(mod.config, "cpu")
+            mod.register_buffer("inv_freq", inv_freq.float(), persistent=False)
+            mod.register_buffer("original_inv_freq", inv_freq.float().clone(), persistent=False)
+            mod.attention_scaling = scaling
+            n_fixed += 1
+    assert n_fixed >= 1
+    assert not [m for m in missing if "inv_freq" not in m], missing
+    model.eval()
+    return model
+
+
+def build_model(cfg: dict, state_dict, dtype=torch.bfloat16):
+    return build_mixtral(cfg, state_dict, dtype) if "num_local_experts" in cfg else build_llama(cfg, state_dict, dtype)
+
+
 @dataclass
 class OracleResult:
     output_ids: torch.Tensor            # [B, S+T] what generate() returned (prompt echoed)

@@ -20,7 +20,7 @@ import torch
 import transformers
 
 from . import weights as W
-from .hf_oracle import OracleGenerativeModel, build_llama
+from .hf_oracle import OracleGenerativeModel, build_llama, build_model
 
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -70,7 +70,7 @@ def gen_case(name, cfg_name, seed, prompt, max_tokens, stop=(), tokenizer=None, 
              full_logits=True, echo=False, stop_from=None):
     cfg = W.CONFIGS[cfg_name]
     sd = W.synth_state_dict(cfg, seed)
-    model = build_llama(cfg, sd)
+    model = build_model(cfg, sd)
     orc = OracleGenerativeModel(model, tokenizer=tokenizer, pad_token_id=pad_token_id)
     if stop_from is not None:  # derive a stop sequence that is guaranteed to occur: (row, i, j) of a free run
         row, i, j = stop_from
@@ -94,6 +94,23 @@ def gen_case(name, cfg_name, seed, prompt, max_tokens, stop=(), tokenizer=None, 
             transformers=transformers.__version__, torch=torch.__version__,
             threads=torch.get_num_threads())),
     )
+    if "num_local_experts" in cfg:
+        # router decisiveness per position (min over layers of p(2nd) - p(3rd)): a flipped expert choice is a discrete
+        # change, so logits are only comparable up to the first position whose margin is inside bf16 noise
+        with torch.no_grad():
+            fw = model(input_ids=res.output_ids, output_router_logits=True)
+        risk = []
+        for rl in fw.router_logits:            # [B*S_total, E] bf16 logits per layer
+            pr = rl.float()                       # transformers 5.x returns the softmaxed router output here
+            if not torch.allclose(pr.sum(-1), torch.ones(pr.shape[0]), atol=1e-3):
+                pr = torch.softmax(pr, -1)
+            pr = pr.view(res.output_ids.shape[0], res.output_ids.shape[1], -1)
+            top = torch.topk(pr, 3, dim=-1).values
+            margin = top[..., 1] - top[..., 2]                 # 2nd vs 3rd expert probability
+            w2 = top[..., 1] / (top[..., 0] + top[..., 1])     # renormalised weight the 2nd expert carries
+            # a flip between the 2nd and 3rd expert matters iff the margin is inside bf16 noise AND the expert has weight
+            risk.append(torch.where(w2 > 0.01, margin, torch.ones_like(margin)))
+        out["router_margin"] = torch.stack(risk, 0).min(0).values.numpy().astype(np.float32)   # [B, S+T]
     if full_logits:
         out["step_logits"] = torch.stack(res.step_logits, 1).numpy().astype(np.float32)  # [B, T, V]
     else:
@@ -102,6 +119,45 @@ def gen_case(name, cfg_name, seed, prompt, max_tokens, stop=(), tokenizer=None, 
     np.savez_compressed(path, **out)
     print(f"wrote {path}: ids {out['output_ids'].shape} finish={res.finish_reason} "
           f"{res.seconds:.2f}s  margins(top1-top2) min={float((tv[..., 0]-tv[..., 1]).min()):.4f}")
+
+
+MOE_DECISIVE = 0.005  # 2nd-vs-3rd expert probability margin regarded as safely above bf16 noise (~0.003)
+
+
+def _moe_risk(model, ids):
+    with torch.no_grad():
+        fw = model(input_ids=ids, output_router_logits=True)
+    risk = []
+    for rl in fw.router_logits:
+        pr = rl.float()
+        if not torch.allclose(pr.sum(-1), torch.ones(pr.shape[0]), atol=1e-3):
+            pr = torch.softmax(pr, -1)
+        pr = pr.view(ids.shape[0], ids.shape[1], -1)
+        top = torch.topk(pr, 3, dim=-1).values
+        margin = top[..., 1] - top[..., 2]
+        w2 = top[..., 1] / (top[..., 0] + top[..., 1])
+        m12 = top[..., 0] - top[..., 1]     # order of the two chosen experts decides the accumulation order only
+        risk.append(torch.where(w2 > 0.01, margin, torch.ones_like(margin)))
+    return torch.stack(risk, 0).min(0).values
+
+
+def find_decisive_moe_prompt(cfg_name, seed, B, S, T, vocab_hi, pad):
+    cfg = W.CONFIGS[cfg_name]
+    model = build_model(cfg, W.synth_state_dict(cfg, seed))
+    orc = OracleGenerativeModel(model, pad_token_id=pad)
+    good = []
+    for trial in range(8000):
+        row = ids_prompt(1, S, vocab_hi, 100000 + trial)
+        out = orc.create_completion(row, max_tokens=T).output_ids
+        if float(_moe_risk(model, out).min()) >= 1.5 * MOE_DECISIVE:
+            good.append(row[0])
+            if len(good) >= B:
+                batch = good[-B:]
+                outb = orc.create_completion(batch, max_tokens=T).output_ids
+                if float(_moe_risk(model, outb).min()) >= MOE_DECISIVE:
+                    print(f"{cfg_name}: decisive batch found after {trial + 1} candidate prompts")
+                    return batch
+    raise RuntimeError("no decisive MoE prompt found")
 
 
 def ids_prompt(B, S, vocab_hi, seed):
@@ -135,6 +191,16 @@ def main():
     p = ids_prompt(2, 32, 1000, 77)
     p[0][:5] = [1030] * 5
     gen_case("tiny_g2_padinfer", "tiny_g2", 0, p, 8, pad_token_id=1030)
+    # (g) Mixtral-style sparse MoE (BASELINE configs[3] architecture at test size).  An expert choice is a discrete
+    # decision: where the oracle's own 2nd/3rd-expert margin is inside bf16 noise the two bf16 pipelines may
+    # legitimately route differently.  The fixtures therefore use prompts (searched here, deterministically) on
+    # which every position of every row is decisive, so the full logits comparison applies to them.
+    for name, cfg_name, seed, B, S, T, vhi, pad in (("tiny_moe_ids", "tiny_moe", 3, 3, 14, 6, 1000, 1030),
+                                                     ("tiny_moe8_ids", "tiny_moe8", 4, 2, 12, 6, 2048, 0)):
+        prompt = find_decisive_moe_prompt(cfg_name, seed, B, S, T, vhi, pad)
+        gen_case(name, cfg_name, seed, prompt, T, pad_token_id=pad)
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        assert float(z["router_margin"].min()) >= MOE_DECISIVE, "search result is not decisive in the batched run"
     if args.big:
         gen_case("llama3_8b_2l_ids", "llama3_8b_2l", 0, ids_prompt(2, 96, 128000, 1234), 8,
                  pad_token_id=128255, full_logits=False)

@@ -42,10 +42,45 @@ CONFIGS: Dict[str, dict] = {
 }
 
 
+MOE_CONFIGS: Dict[str, dict] = {
+    # Mixtral-style sparse MoE (BASELINE.json configs[3]) at test size: 4 experts, top-2
+    "tiny_moe": dict(vocab_size=1031, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                     num_attention_heads=4, num_key_value_heads=2, head_dim=128, max_position_embeddings=2048,
+                     rms_norm_eps=1e-5, rope_theta=1000000.0, num_local_experts=4, num_experts_per_tok=2),
+    "tiny_moe8": dict(vocab_size=2048, hidden_size=1024, intermediate_size=1536, num_hidden_layers=2,
+                      num_attention_heads=8, num_key_value_heads=2, head_dim=128, max_position_embeddings=2048,
+                      rms_norm_eps=1e-5, rope_theta=1000000.0, num_local_experts=8, num_experts_per_tok=2),
+}
+CONFIGS.update(MOE_CONFIGS)
+
+
+def moe_tensor_specs(cfg: dict) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
+    """HF MixtralForCausalLM state_dict (transformers 5.x fused-expert layout)."""
+    H, I, V, E = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"], cfg["num_local_experts"]
+    nh, nkv, d = cfg["num_attention_heads"], cfg["num_key_value_heads"], cfg["head_dim"]
+    yield "model.embed_tokens.weight", (V, H), "embed"
+    for i in range(cfg["num_hidden_layers"]):
+        p = f"model.layers.{i}."
+        yield p + "input_layernorm.weight", (H,), "norm"
+        yield p + "self_attn.q_proj.weight", (nh * d, H), "linear"
+        yield p + "self_attn.k_proj.weight", (nkv * d, H), "linear"
+        yield p + "self_attn.v_proj.weight", (nkv * d, H), "linear"
+        yield p + "self_attn.o_proj.weight", (H, nh * d), "linear"
+        yield p + "post_attention_layernorm.weight", (H,), "norm"
+        yield p + "mlp.gate.weight", (E, H), "router"
+        yield p + "mlp.experts.gate_up_proj", (E, 2 * I, H), "linear"
+        yield p + "mlp.experts.down_proj", (E, H, I), "linear"
+    yield "model.norm.weight", (H,), "norm"
+    yield "lm_head.weight", (V, H), "linear"
+
+
 def tensor_specs(cfg: dict) -> Iterator[Tuple[str, Tuple[int, ...], str]]:
     """Yield (name, shape, kind) in canonical order. kind in {embed, linear, norm}."""
     H, I, V = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"]
     nh, nkv, d = cfg["num_attention_heads"], cfg["num_key_value_heads"], cfg["head_dim"]
+    if "num_local_experts" in cfg:
+        yield from moe_tensor_specs(cfg)
+        return
     yield "model.embed_tokens.weight", (V, H), "embed"
     for i in range(cfg["num_hidden_layers"]):
         p = f"model.layers.{i}."
@@ -69,6 +104,8 @@ def synth_tensor(index: int, shape, kind: str, seed: int, dtype=torch.bfloat16) 
         t = 1.0 + 0.1 * torch.randn(shape, generator=g, dtype=torch.float32)
     elif kind == "embed":
         t = torch.randn(shape, generator=g, dtype=torch.float32)
+    elif kind == "router":  # moderately peaky routing: the 2nd expert carries real weight, 2nd/3rd margins mostly above bf16 noise
+        t = torch.randn(shape, generator=g, dtype=torch.float32) * (2.5 / math.sqrt(shape[-1]))
     else:  # linear: variance preserving, so attention / logits are not near-uniform
         t = torch.randn(shape, generator=g, dtype=torch.float32) * (1.0 / math.sqrt(shape[-1]))
     return t.to(dtype)
@@ -87,7 +124,7 @@ def synth_state_dict(cfg: dict, seed: int = 0, dtype=torch.bfloat16) -> Dict[str
 def checksum(sd: Dict[str, torch.Tensor]) -> float:
     """Cheap fingerprint recorded in golden files to prove both sides loaded the same bytes."""
     s = 0.0
-    for name in ("model.embed_tokens.weight", "lm_head.weight", "model.layers.0.mlp.down_proj.weight"):
+    for name in ("model.embed_tokens.weight", "lm_head.weight", "model.layers.0.self_attn.o_proj.weight"):
         t = sd[name]
         s += float(t[: 64].float().sum()) + float(t[-1].float().abs().sum())
     return s

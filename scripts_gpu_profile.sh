@@ -1,13 +1,17 @@
 #!/bin/bash
-# ncu evidence: launch list of one full step + full-set captures of the dominant kernels
+# ncu evidence for round 1 (final kernels): launch list of one full request + full-set captures per kernel family
 mkdir -p gpurun_out
 B="python bench.py --steps 1 --warmup 1 --gen-len 3 --no-cpu-baseline"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1000 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/b_ncu.log 2>&1
-echo "launch list rc=$? lines=$(wc -l < gpurun_out/launches.csv)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tn_kernel -s 129 -c 5 -o gpurun_out/prof_gemm_decode $B > gpurun_out/p1.log 2>&1
-echo "gemm decode rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tn_kernel -s 0 -c 4 -o gpurun_out/prof_gemm_prefill $B > gpurun_out/p2.log 2>&1
-echo "gemm prefill rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_ -s 31 -c 3 -o gpurun_out/prof_attn $B > gpurun_out/p3.log 2>&1
-echo "attn rc=$?"
-ls -la gpurun_out/
+ALL='regex:gemm_tn|attn_|rmsnorm|rope_kv|argmax|step_update|embed_gather|pack_|gather_rows|swiglu_reduce'
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$ALL" -c 1200 --csv --log-file gpurun_out/r01f_launches.csv $B > gpurun_out/pf0.log 2>&1
+echo "launch list rc=$? lines=$(wc -l < gpurun_out/r01f_launches.csv)"
+cap() { # name regex skip count
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c $4 -o gpurun_out/r01f_$1 $B > gpurun_out/pf_$1.log 2>&1
+  echo "$1 rc=$?"
+}
+cap gemm2cta gemm_tn_2cta 0 4
+cap gemm_decode 'gemm_tn_kernel' 0 6
+cap attn 'attn_prefill|attn_decode' 31 2
+cap small 'rmsnorm_kernel|rope_kv' 64 4
+cap misc 'argmax|step_update|embed_gather|pack_padded|gather_rows' 0 6
+ls -la gpurun_out/ | grep r01f
