@@ -43,6 +43,8 @@ typedef struct b200_model_config {
   int32_t tp_rank;
   int32_t tp_size;             /* 1, 2, 4 or 8; heads, kv heads and intermediate must divide */
   int32_t device;              /* CUDA device ordinal */
+  int32_t num_experts;         /* 0 = dense MLP; > 0 = Mixtral-style sparse MoE (modeling_mixtral.py:62-135) */
+  int32_t num_experts_per_tok; /* must be 2 when num_experts > 0 */
 } b200_model_config_t;
 
 /* Creates the engine on cfg->device. nccl_unique_id: 128 bytes shared by all ranks (from
@@ -61,7 +63,9 @@ int b200_engine_ipc_import(b200_engine_t* e, const void* handles, int32_t n);
 /* Weights, by HF state_dict name (what AutoModelForCausalLM.from_pretrained would load,
  * generative_model.py:249-254).  `data` is the FULL (unsharded) bf16 tensor, row-major, on the host
  * (on_device=0) or on this engine's GPU (on_device=1); the engine copies the shard of its tp_rank and
- * fuses q/k/v and gate/up.  b200_engine_finalize_weights fails if a tensor is missing. */
+ * fuses q/k/v and gate/up.  MoE checkpoints use the fused-expert names `mlp.gate.weight` [E,H],
+ * `mlp.experts.gate_up_proj` [E,2I,H] and `mlp.experts.down_proj` [E,H,I].  b200_engine_finalize_weights fails if
+ * a tensor is missing. */
 int b200_engine_set_weight(b200_engine_t* e, const char* hf_name, const void* data, int on_device,
                            int ndim, const int64_t* shape);
 int b200_engine_finalize_weights(b200_engine_t* e);
@@ -162,6 +166,12 @@ int b200_op_rope_kv(const void* qkv, int64_t ld, void* q_out, int64_t ldq, void*
                     const int32_t* page_table, int max_pages, const int32_t* tok_seq, const int32_t* tok_pos,
                     const void* cos_tab, const void* sin_tab, int T, int nh, int nkv, void* stream);
 int b200_op_argmax(const void* logits, int64_t ld, int B, int V, float* out_val, int32_t* out_idx, void* stream);
+
+/* Host-DRAM KV tier (BASELINE.json configs[3]): move all KV pages of staged sequence `slot` to pinned host memory /
+ * back to the device, asynchronously on the engine stream.  scrub != 0 overwrites the device pages after the copy
+ * (tests).  Decoding after swap_in continues exactly as if the sequence had stayed resident. */
+int b200_kv_swap_out(b200_engine_t* e, int32_t slot, int32_t scrub);
+int b200_kv_swap_in(b200_engine_t* e, int32_t slot);
 
 /* Debug timeline: capacity > 0 enables per-CTA {t0, t1 (globaltimer ns), kind, block} records (24 bytes each),
  * 0 disables; read drains up to `capacity` records into `out`. */

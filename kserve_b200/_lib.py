@@ -14,7 +14,7 @@ class ModelConfig(C.Structure):
         "vocab_size", "hidden_size", "intermediate_size", "num_layers", "num_heads", "num_kv_heads",
         "head_dim", "max_position")] + [("rms_eps", C.c_float), ("rope_theta", C.c_float)] + [
         (n, C.c_int32) for n in ("max_batch", "max_seq_len", "max_prefill_tokens", "num_kv_pages",
-                                 "tp_rank", "tp_size", "device")]
+                                 "tp_rank", "tp_size", "device", "num_experts", "num_experts_per_tok")]
 
 
 class GenParams(C.Structure):
@@ -79,6 +79,8 @@ def load() -> C.CDLL:
     lib.b200_batcher_tick.argtypes = [vp, i64, i32, vp, vp, vp, C.POINTER(i32), C.POINTER(i32)]
     lib.b200_engine_ipc_export.argtypes = [vp, vp]
     lib.b200_engine_ipc_import.argtypes = [vp, vp, i32]
+    lib.b200_kv_swap_out.argtypes = [vp, i32, i32]
+    lib.b200_kv_swap_in.argtypes = [vp, i32]
     lib.b200_debug_trace.argtypes = [i32]
     lib.b200_debug_trace_read.argtypes = [vp, i32, C.POINTER(i32)]
     _lib = lib

@@ -74,6 +74,7 @@ static int dmalloc(T** p, size_t n) {
 
 struct LayerW {
   bf16 *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wdown = nullptr, *ln1 = nullptr, *ln2 = nullptr;
+  bf16 *wr = nullptr, *wgu_e = nullptr, *wdown_e = nullptr;   // MoE: router [E][H], experts [E][2I][H] / [E][H][I]
 };
 
 }  // namespace b200
@@ -87,6 +88,12 @@ struct b200_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   // per-rank dims
   int H, nh, nkv, G, I, V, Vl, v0, qkv_cols, L;
+  int E = 0;   // experts (0 = dense)
+  // MoE dispatch state / grouped buffers
+  int32_t *tok_expert = nullptr, *tok_row = nullptr, *e_count = nullptr, *e_off = nullptr;
+  float* tok_weight = nullptr;
+  bf16 *xg = nullptr, *hg = nullptr, *yg = nullptr;
+  int g_rows = 0;
   // weights
   bf16 *embed = nullptr, *lm_head = nullptr, *final_norm = nullptr;
   std::vector<LayerW> layers;
@@ -139,7 +146,11 @@ struct b200_engine {
     int num_eos = 0, num_stop = 0;
     bool forced = false;
     bool prefilled = false;
+    int per_seq_pages = 0;
   } st;
+  // host-DRAM KV tier: pinned copies of the pages of swapped-out sequences (slot -> buffer)
+  std::unordered_map<int, bf16*> host_kv;
+  std::unordered_map<int, size_t> host_kv_bytes;
   bool staged_mask = false;
   // graphs per batch size
   std::unordered_map<int, cudaGraphExec_t> graphs;
@@ -300,6 +311,52 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
       return 0;
     };
     if ((rc = row_parallel(e->attn, e->nh * kHeadDim, w.wo, w.ln2))) return rc;
+    const bf16* next_norm = (l + 1 < e->L) ? e->layers[l + 1].ln1 : e->final_norm;
+    if (e->E > 0) {
+      // ---- sparse MoE: route, group rows per expert, run the expert GEMMs bounded by the device-side counts, combine
+      B200_CUDA_OK(launch_k(moe_router_kernel, dim3((T + 3) / 4), dim3(128), 0, s, (const bf16*)e->xn, (const bf16*)w.wr, T, H, e->E,
+                            e->tok_expert, e->tok_weight));
+      B200_CUDA_OK(launch_k(moe_offsets_kernel, dim3(1), dim3(1024), 0, s, (const int32_t*)e->tok_expert, T, e->E, e->e_count, e->e_off, e->tok_row));
+      B200_CUDA_OK(launch_k(moe_gather_kernel, dim3(T), dim3(128), 0, s, (const bf16*)e->xn, (const int32_t*)e->tok_row, e->xg, H));
+      e->launches += 3;
+      const int dsp = decode ? pick_splits(e, H, e->I) : 1;
+      for (int x = 0; x < e->E; ++x) {
+        const bf16* wgu = w.wgu_e + (long long)x * 2 * e->I * H;
+        const bf16* wdn = w.wdown_e + (long long)x * H * e->I;
+        if (decode) {
+          GemmArgs a{wgu, 2 * e->I, e->xg, e->g_rows, 2 * e->I, B, H, EPI_T_SWIGLU, bn, 1, e->hg, nullptr, e->I, 0, e->I, true};
+          a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
+          a.n_rt = e->e_count + x; a.row_off = e->e_off + x;
+          if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+          GemmArgs d{wdn, H, e->hg, e->g_rows, H, B, e->I, dsp > 1 ? EPI_T_PARTIAL : EPI_T_STORE, bn, dsp,
+                     dsp > 1 ? (void*)(e->ws + (size_t)x * dsp * B * H) : (void*)e->yg, nullptr, H, (long long)B * H, 0, true};
+          d.n_rt = e->e_count + x; d.row_off = e->e_off + x;
+          if ((rc = launch_gemm(e->tmaps, d, e->num_sms, s))) return rc;
+        } else {
+          GemmArgs a{e->xg, e->g_rows, wgu, 2 * e->I, T, 2 * e->I, H, EPI_SWIGLU, 256, 1, e->hg, nullptr, e->I, 0, e->I, false};
+          a.m_rt = e->e_count + x; a.row_off = e->e_off + x;
+          if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+          GemmArgs d{e->hg, e->g_rows, wdn, H, T, H, e->I, EPI_STORE, 256, 1, e->yg, nullptr, H, 0, 0, false};
+          d.m_rt = e->e_count + x; d.row_off = e->e_off + x;
+          if ((rc = launch_gemm(e->tmaps, d, e->num_sms, s))) return rc;
+        }
+        e->launches += 2;
+      }
+      MoeCombineParams cp{};
+      cp.x = e->x; cp.w = next_norm; cp.xn = e->xn; cp.H = H; cp.eps = eps;
+      cp.tok_expert = e->tok_expert; cp.tok_weight = e->tok_weight; cp.tok_row = e->tok_row; cp.off = e->e_off;
+      cp.yg = e->yg;
+      if (decode && dsp > 1) { cp.part = e->ws; cp.splits = dsp; cp.expert_stride = (long long)dsp * B * H; cp.split_stride = (long long)B * H; }
+      cp.ysum = tp ? e->ybuf : nullptr;
+      B200_CUDA_OK(launch_k(moe_combine_norm_kernel, dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, cp));
+      e->launches++;
+      if (tp) {
+        if ((rc = allreduce_bf16(e, e->ybuf, (size_t)T * H))) return rc;
+        if ((rc = launch_rmsnorm(2, e->x, next_norm, e->xn, T, H, eps, nullptr, 0, 0, 0, e->ybuf, s))) return rc;
+        e->launches++;
+      }
+      continue;
+    }
     // ---- gate/up projection with the SwiGLU fused into the epilogue
     if (decode) {
       const int gu_tiles = (2 * e->I + kGemmBlockM - 1) / kGemmBlockM;
@@ -321,7 +378,6 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
       if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
     }
     e->launches++;
-    const bf16* next_norm = (l + 1 < e->L) ? e->layers[l + 1].ln1 : e->final_norm;
     if ((rc = row_parallel(e->hbuf, e->I, w.wdown, next_norm))) return rc;
   }
   return 0;
@@ -431,6 +487,7 @@ static int stage_common(b200_engine* e, int B, int S, const std::vector<int>& le
   // page allocation: sequence b owns a contiguous run of pages (fresh allocator per call)
   const int per_seq = (width + gp->max_new_tokens + kPageTokens - 1) / kPageTokens;
   B200_REQUIRE(per_seq <= e->max_pages && (long long)per_seq * B <= e->num_pages, "KV page pool too small");
+  st.per_seq_pages = per_seq;
   std::fill(e->h_page_table.begin(), e->h_page_table.end(), 0);
   for (int b = 0; b < B; ++b)
     for (int i = 0; i < per_seq; ++i) e->h_page_table[(size_t)b * e->max_pages + i] = b * per_seq + i;
@@ -595,6 +652,8 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   const int tp = c->tp_size;
   e->H = c->hidden_size; e->nh = c->num_heads / tp; e->nkv = c->num_kv_heads / tp; e->G = c->num_heads / c->num_kv_heads;
   e->I = c->intermediate_size / tp; e->V = c->vocab_size; e->L = c->num_layers;
+  e->E = c->num_experts;
+  B200_REQUIRE(e->E == 0 || (e->E <= kMaxExperts && e->E >= 2 && c->num_experts_per_tok == kTopK), "MoE needs 2..16 experts and top-2 routing");
   const int vper = (c->vocab_size + tp - 1) / tp;
   e->v0 = vper * c->tp_rank;
   e->Vl = std::max(0, std::min(vper, c->vocab_size - e->v0));
@@ -614,8 +673,14 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   for (auto& w : e->layers) {
     if ((rc = dmalloc(&w.wqkv, (size_t)e->qkv_cols * H))) return rc;
     if ((rc = dmalloc(&w.wo, H * e->nh * kHeadDim))) return rc;
-    if ((rc = dmalloc(&w.wgu, (size_t)2 * e->I * H))) return rc;
-    if ((rc = dmalloc(&w.wdown, H * e->I))) return rc;
+    if (e->E == 0) {
+      if ((rc = dmalloc(&w.wgu, (size_t)2 * e->I * H))) return rc;
+      if ((rc = dmalloc(&w.wdown, H * e->I))) return rc;
+    } else {
+      if ((rc = dmalloc(&w.wr, (size_t)e->E * H))) return rc;
+      if ((rc = dmalloc(&w.wgu_e, (size_t)e->E * 2 * e->I * H))) return rc;
+      if ((rc = dmalloc(&w.wdown_e, (size_t)e->E * H * e->I))) return rc;
+    }
     if ((rc = dmalloc(&w.ln1, H))) return rc;
     if ((rc = dmalloc(&w.ln2, H))) return rc;
   }
@@ -665,6 +730,20 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   B200_CUDA_OK(cudaMemset(e->hbuf, 0, T * e->I * 2));
   B200_CUDA_OK(cudaMemset(e->xl, 0, (size_t)c->max_batch * H * 2));
   e->ws_elems = (size_t)16 * c->max_batch * std::max(std::max(e->qkv_cols, e->H), 2 * e->I);
+  if (e->E) {
+    e->ws_elems = std::max(e->ws_elems, (size_t)e->E * 16 * c->max_batch * e->H);
+    e->g_rows = 2 * e->cap_T + 8 * e->E + 256;
+    if ((rc = dmalloc(&e->tok_expert, (size_t)2 * T))) return rc;
+    if ((rc = dmalloc(&e->tok_row, (size_t)2 * T))) return rc;
+    if ((rc = dmalloc(&e->tok_weight, (size_t)2 * T))) return rc;
+    if ((rc = dmalloc(&e->e_count, (size_t)kMaxExperts))) return rc;
+    if ((rc = dmalloc(&e->e_off, (size_t)kMaxExperts + 1))) return rc;
+    if ((rc = dmalloc(&e->xg, (size_t)e->g_rows * H))) return rc;
+    if ((rc = dmalloc(&e->hg, (size_t)e->g_rows * e->I))) return rc;
+    if ((rc = dmalloc(&e->yg, (size_t)e->g_rows * H))) return rc;
+    B200_CUDA_OK(cudaMemset(e->xg, 0, (size_t)e->g_rows * H * 2));
+    B200_CUDA_OK(cudaMemset(e->hg, 0, (size_t)e->g_rows * e->I * 2));
+  }
   if ((rc = dmalloc(&e->ws, e->ws_elems))) return rc;
   e->sk_tiles = (std::max(2 * e->I, e->Vl) + kGemmBlockM - 1) / kGemmBlockM;
   e->sk_ws_floats = std::max<size_t>((size_t)e->sk_tiles * 2 * 64 * kGemmBlockM, (size_t)8 << 20);   // >= 32 MB
@@ -743,15 +822,17 @@ int b200_engine_destroy(b200_engine_t* e) {
   if (e->row_epoch) cudaFree(e->row_epoch);
   if (e->cand_epoch) cudaFree(e->cand_epoch);
   void* ptrs[] = {e->embed, e->lm_head, e->final_norm, e->cos_tab, e->sin_tab, e->kcache, e->vcache, e->d_page_table,
-                  e->x, e->xn, e->qkv, e->attn, e->hbuf, e->ybuf, e->xl, e->qdec, e->logits, e->ws, e->sk_ws, e->sk_flags, e->part_o, e->part_ml,
+                  e->x, e->xn, e->qkv, e->attn, e->hbuf, e->ybuf, e->xl, e->qdec, e->logits, e->ws, e->sk_ws, e->sk_flags,
+                  e->tok_expert, e->tok_row, e->tok_weight, e->e_count, e->e_off, e->xg, e->hg, e->yg, e->part_o, e->part_ml,
                   e->cand_val, e->cand_idx, e->cand_val_all, e->cand_idx_all, e->d_tok, e->d_tok_seq, e->d_tok_pos, e->d_cu,
                   e->d_seq_slot, e->d_last_rows, e->d_cur_len, e->d_next_tok, e->d_dec_pos, e->d_finished, e->d_out_tokens,
                   e->d_forced, e->d_eos, e->d_stop_tok, e->d_stop_off, e->d_state};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& w : e->layers) {
-    void* lp[] = {w.wqkv, w.wo, w.wgu, w.wdown, w.ln1, w.ln2};
+    void* lp[] = {w.wqkv, w.wo, w.wgu, w.wdown, w.ln1, w.ln2, w.wr, w.wgu_e, w.wdown_e};
     for (void* p : lp) if (p) cudaFree(p);
   }
+  for (auto& kv : e->host_kv) cudaFreeHost(kv.second);
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->h_state) cudaFreeHost(e->h_state);
   if (e->h_out_tokens) cudaFreeHost(e->h_out_tokens);
@@ -823,6 +904,22 @@ int b200_engine_set_weight(b200_engine_t* e, const char* name, const void* data,
     } else if (rest == "mlp.down_proj.weight") {
       B200_REQUIRE(expect(H, If), "shape mismatch for " + n);
       rc = copy_cols(w.wdown, src, H, If, r * Il, Il, dev);
+    } else if (rest == "mlp.gate.weight") {
+      B200_REQUIRE(e->E > 0 && expect(e->E, H), "shape mismatch for " + n);
+      rc = copy_rows(w.wr, src, 0, e->E, H, dev);
+    } else if (rest == "mlp.experts.gate_up_proj") {
+      B200_REQUIRE(e->E > 0 && ndim == 3 && shape[0] == e->E && shape[1] == 2 * If && shape[2] == H, "shape mismatch for " + n);
+      for (int x = 0; x < e->E; ++x) {   // per expert: rows [0,I) gate, [I,2I) up -> 16-row interleave of this rank's slice
+        const bf16* g0 = src + ((long long)x * 2 * If + (long long)r * Il) * H;
+        const bf16* u0 = src + ((long long)x * 2 * If + If + (long long)r * Il) * H;
+        bf16* dst = w.wgu_e + (long long)x * 2 * Il * H;
+        B200_CUDA_OK(cudaMemcpy2D(dst, 32 * H * 2, g0, 16 * H * 2, 16 * H * 2, Il / 16, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+        B200_CUDA_OK(cudaMemcpy2D(dst + 16 * H, 32 * H * 2, u0, 16 * H * 2, 16 * H * 2, Il / 16, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+      }
+    } else if (rest == "mlp.experts.down_proj") {
+      B200_REQUIRE(e->E > 0 && ndim == 3 && shape[0] == e->E && shape[1] == H && shape[2] == If, "shape mismatch for " + n);
+      for (int x = 0; x < e->E && rc == 0; ++x)
+        rc = copy_cols(w.wdown_e + (long long)x * H * Il, src + (long long)x * H * If, H, If, r * Il, Il, dev);
     } else if (rest == "self_attn.rotary_emb.inv_freq") {
       return 0;
     } else {
@@ -1056,6 +1153,51 @@ int b200_engine_last_timing(b200_engine_t* e, b200_timing_t* out) {
   *out = e->timing;
   return 0;
 }
+
+// ---- host-DRAM KV tier (BASELINE.json configs[3]: "paged-KV with host-DRAM KV-offload tier") ----------
+// Moves every KV page of one staged sequence (all layers, K and V) to pinned host memory and back, asynchronously on
+// the engine stream.  While a sequence is swapped out its device pages may be overwritten (scrub = 1 does so, for
+// tests); after swap-in decoding continues bit-identically.
+static int kv_swap(b200_engine_t* e, int32_t slot, bool out, int scrub) {
+  auto& st = e->st;
+  B200_REQUIRE(st.prefilled && slot >= 0 && slot < st.B, "no such staged sequence");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  const size_t page_elems = (size_t)e->nkv * kPageTokens * kHeadDim;
+  const size_t seq_elems = (size_t)st.per_seq_pages * page_elems;          // per layer, per K or V
+  const size_t bytes = seq_elems * 2 * 2 * e->L;
+  if (out) {
+    if (!e->host_kv.count(slot) || e->host_kv_bytes[slot] < bytes) {
+      if (e->host_kv.count(slot)) cudaFreeHost(e->host_kv[slot]);
+      bf16* h = nullptr;
+      B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&h), bytes));
+      e->host_kv[slot] = h; e->host_kv_bytes[slot] = bytes;
+    }
+  } else {
+    B200_REQUIRE(e->host_kv.count(slot), "sequence is not swapped out");
+  }
+  bf16* h = e->host_kv[slot];
+  const size_t first = (size_t)slot * st.per_seq_pages * page_elems;
+  for (int l = 0; l < e->L; ++l) {
+    bf16* kd = e->kcache + (size_t)l * e->layer_stride + first;
+    bf16* vd = e->vcache + (size_t)l * e->layer_stride + first;
+    bf16* kh = h + ((size_t)l * 2) * seq_elems;
+    bf16* vh = kh + seq_elems;
+    if (out) {
+      B200_CUDA_OK(cudaMemcpyAsync(kh, kd, seq_elems * 2, cudaMemcpyDeviceToHost, e->stream));
+      B200_CUDA_OK(cudaMemcpyAsync(vh, vd, seq_elems * 2, cudaMemcpyDeviceToHost, e->stream));
+      if (scrub) {
+        B200_CUDA_OK(cudaMemsetAsync(kd, 0x7f, seq_elems * 2, e->stream));
+        B200_CUDA_OK(cudaMemsetAsync(vd, 0x7f, seq_elems * 2, e->stream));
+      }
+    } else {
+      B200_CUDA_OK(cudaMemcpyAsync(kd, kh, seq_elems * 2, cudaMemcpyHostToDevice, e->stream));
+      B200_CUDA_OK(cudaMemcpyAsync(vd, vh, seq_elems * 2, cudaMemcpyHostToDevice, e->stream));
+    }
+  }
+  return 0;
+}
+int b200_kv_swap_out(b200_engine_t* e, int32_t slot, int32_t scrub) { B200_REQUIRE(e, "null engine"); return kv_swap(e, slot, true, scrub); }
+int b200_kv_swap_in(b200_engine_t* e, int32_t slot) { B200_REQUIRE(e, "null engine"); return kv_swap(e, slot, false, 0); }
 
 // ---- peer-memory exchange setup (tensor parallel) --------------------------------------------------
 int b200_engine_ipc_export(b200_engine_t* e, void* handle64) {

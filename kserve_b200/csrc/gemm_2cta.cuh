@@ -67,8 +67,8 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive o
 }
 
 struct Gemm2Unit { int m_pair, n_t; };
-__device__ __forceinline__ bool gemm2_get_unit(const GemmParams& p, int idx, int cluster_id, int num_clusters, Gemm2Unit& u) {
-  const int m_pairs = (p.m_tiles + 1) >> 1;
+__device__ __forceinline__ bool gemm2_get_unit(const GemmParams& p, int idx, int cluster_id, int num_clusters, Gemm2Unit& u, int m_tiles_rt) {
+  const int m_pairs = (m_tiles_rt + 1) >> 1;
   const int t = cluster_id + idx * num_clusters;
   if (t >= m_pairs * p.n_tiles) return false;
   constexpr int G = kGemmGroupM / 2;            // 8 pairs = 16 m-tiles per raster group
@@ -122,6 +122,14 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  int M_rt = p.M;
+  if (p.m_rt != nullptr) {   // rows produced by the previous kernel (tokens routed to this MoE expert)
+    pdl_wait();
+    M_rt = min(p.M, *p.m_rt);
+  }
+  const int m_tiles_rt = M_rt <= 0 ? 0 : (M_rt + kGemmBlockM - 1) / kGemmBlockM;
+  const int roff = p.row_off ? *p.row_off : 0;
+
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (both CTAs)
     if (lane == 0) {
@@ -129,14 +137,14 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       Gemm2Unit u;
-      for (int idx = 0; gemm2_get_unit(p, idx, cluster_id, num_clusters, u); ++idx) {
+      for (int idx = 0; gemm2_get_unit(p, idx, cluster_id, num_clusters, u, m_tiles_rt); ++idx) {
         const int m0 = u.m_pair * 256 + (int)rank * kGemmBlockM;
         const int n0 = u.n_t * k2BlockN + (int)rank * 128;
         for (int kb = 0; kb < p.kb_total; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * k2StageBytes;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * k2StageBytes);
-          tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m0, p.hint_a);
+          tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m0 + roff, p.hint_a);
           tma_load_2d_2sm(sa + kGemmBlockM * kGemmBlockK * 2, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n0, p.hint_b);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -152,7 +160,7 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int acc = 0;
       uint32_t acc_phase = 0;
       Gemm2Unit u;
-      for (int idx = 0; gemm2_get_unit(p, idx, cluster_id, num_clusters, u); ++idx) {
+      for (int idx = 0; gemm2_get_unit(p, idx, cluster_id, num_clusters, u, m_tiles_rt); ++idx) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * k2BlockN;
@@ -180,7 +188,7 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     Gemm2Unit u;
-    for (int idx = 0; gemm2_get_unit(p, idx, cluster_id, num_clusters, u); ++idx) {
+    for (int idx = 0; gemm2_get_unit(p, idx, cluster_id, num_clusters, u, m_tiles_rt); ++idx) {
       const int m = u.m_pair * 256 + (int)rank * kGemmBlockM + q * 32 + lane;
       const int n0 = u.n_t * k2BlockN;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -199,10 +207,10 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
         }
         const int nvalid = min(CH, p.N - (n0 + c0));
-        if (m >= p.M) continue;
+        if (m >= M_rt) continue;
         if constexpr (EPI == EPI_STORE || EPI == EPI_STORE_RES) {
-          bf16* orow = reinterpret_cast<bf16*>(p.out) + (long long)m * p.ldo + n0 + c0;
-          const bf16* rrow = (EPI == EPI_STORE_RES) ? p.residual + (long long)m * p.ldo + n0 + c0 : nullptr;
+          bf16* orow = reinterpret_cast<bf16*>(p.out) + (long long)(m + roff) * p.ldo + n0 + c0;
+          const bf16* rrow = (EPI == EPI_STORE_RES) ? p.residual + (long long)(m + roff) * p.ldo + n0 + c0 : nullptr;
           const bool vec = (nvalid == CH) && ((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
           if (vec) {
 #pragma unroll
@@ -234,7 +242,7 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         } else {  // EPI_SWIGLU: columns [c0,c0+16) gate, [c0+16,c0+32) up
           const int oc = (n0 + c0) >> 1;
-          bf16* orow = reinterpret_cast<bf16*>(p.out) + (long long)m * p.ldo + oc;
+          bf16* orow = reinterpret_cast<bf16*>(p.out) + (long long)(m + roff) * p.ldo + oc;
           float h[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) h[j] = bf16_round(silu_f(bf16_round(v[j]))) * bf16_round(v[16 + j]);

@@ -44,6 +44,12 @@ struct GemmParams {
   // waits for the count, adds the pieces in piece order (deterministic) and runs the normal epilogue.
   // Each CTA processes its non-final piece first and its tile-finishing piece last, so nobody waits on a CTA
   // that is itself waiting.  Requires n_tiles == 1 and splits == 1.
+  // runtime extents (device counters, e.g. tokens routed to one MoE expert): when set they replace M (row-major
+  // kernels) / N (swap-AB kernels) and the kernel first waits for its predecessor to read them; 0 => nothing to do
+  const int* m_rt;
+  const int* n_rt;
+  const int* row_off;      // device row offset of the activation / output rows inside a grouped (per-expert) buffer
+  int swap_ab;             // 1: A is the weight (decode kernels) -> row_off applies to B and to the output rows n
   int sched;
   int sk_slots;            // partial slots per tile
   float* sk_ws;            // [m_tiles][sk_slots][BLOCK_N][128] fp32
@@ -79,17 +85,18 @@ __device__ __forceinline__ int sk_owner(long long it, long long W, int P) {   //
   return c;
 }
 
-__device__ __forceinline__ bool gemm_get_seg(const GemmParams& p, int idx, GemmSeg& g) {
+__device__ __forceinline__ bool gemm_get_seg(const GemmParams& p, int idx, GemmSeg& g, int m_tiles_rt) {
   g.slot = 0;
+  if (m_tiles_rt <= 0) return false;
   if (p.sched == 0) {
     const int u = blockIdx.x + idx * gridDim.x;
-    if (u >= p.m_tiles * p.n_tiles * p.splits) return false;
+    if (u >= m_tiles_rt * p.n_tiles * p.splits) return false;
     const int tile = u / p.splits;
     g.split = u - tile * p.splits;
     const int per_group = kGemmGroupM * p.n_tiles;
     const int grp = tile / per_group;
     const int first_m = grp * kGemmGroupM;
-    const int gsize = min(p.m_tiles - first_m, kGemmGroupM);
+    const int gsize = min(m_tiles_rt - first_m, kGemmGroupM);
     const int r = tile - grp * per_group;
     g.m_t = first_m + r % gsize;
     g.n_t = r / gsize;
@@ -164,6 +171,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  int M_rt = p.M, N_rt = p.N;
+  if (p.m_rt != nullptr || p.n_rt != nullptr) {   // extents produced by the previous kernel
+    pdl_wait();
+    if (p.m_rt) M_rt = min(p.M, *p.m_rt);
+    if (p.n_rt) N_rt = min(p.N, *p.n_rt);
+  }
+  const int m_tiles_rt = (M_rt <= 0 || N_rt <= 0) ? 0 : (M_rt + kGemmBlockM - 1) / kGemmBlockM;
+  const int roff = p.row_off ? *p.row_off : 0;   // (read after the wait above: set together with m_rt / n_rt)
+  const int roff_a = p.swap_ab ? 0 : roff, roff_b = p.swap_ab ? roff : 0;
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -171,7 +188,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       bool first = true;
       GemmSeg sg;
-      for (int idx = 0; gemm_get_seg(p, idx, sg); ++idx) {
+      for (int idx = 0; gemm_get_seg(p, idx, sg, m_tiles_rt); ++idx) {
         const int m_t = sg.m_t, n_t = sg.n_t, kb0 = sg.kb0, kb1 = sg.kb1;
         int kb = kb0;
         if (first) {
@@ -182,14 +199,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int npre = min(STAGES, kb1 - kb0);
             for (int i = 0; i < npre; ++i) {
               mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
-              tma_load_2d(smem + i * Cfg::kStageBytes, &tmap_a, &full_bar[i], (kb0 + i) * kGemmBlockK, m_t * kGemmBlockM, p.hint_a);
+              tma_load_2d(smem + i * Cfg::kStageBytes, &tmap_a, &full_bar[i], (kb0 + i) * kGemmBlockK, m_t * kGemmBlockM + roff_a, p.hint_a);
             }
             const int npf = min(npre + p.l2_prefetch_kb, kb1 - kb0);
             for (int i = npre; i < npf; ++i) tma_prefetch_l2_2d(&tmap_a, (kb0 + i) * kGemmBlockK, m_t * kGemmBlockM);
             pdl_wait();
             _ts.mark();
             for (int i = 0; i < npre; ++i)
-              tma_load_2d(smem + i * Cfg::kStageBytes + Cfg::kABytes, &tmap_b, &full_bar[i], (kb0 + i) * kGemmBlockK, n_t * BLOCK_N, p.hint_b);
+              tma_load_2d(smem + i * Cfg::kStageBytes + Cfg::kABytes, &tmap_b, &full_bar[i], (kb0 + i) * kGemmBlockK, n_t * BLOCK_N + roff_b, p.hint_b);
             kb = kb0 + npre;
             if (npre == STAGES) { stage = 0; phase = 1; } else { stage = npre; }
           } else {
@@ -201,8 +218,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m_t * kGemmBlockM, p.hint_a);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n_t * BLOCK_N, p.hint_b);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m_t * kGemmBlockM + roff_a, p.hint_a);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n_t * BLOCK_N + roff_b, p.hint_b);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -217,7 +234,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       GemmSeg sg;
-      for (int idx = 0; gemm_get_seg(p, idx, sg); ++idx) {
+      for (int idx = 0; gemm_get_seg(p, idx, sg, m_tiles_rt); ++idx) {
         const int kb0 = sg.kb0, kb1 = sg.kb1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -248,7 +265,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     GemmSeg sg;
-    for (int idx = 0; gemm_get_seg(p, idx, sg); ++idx) {
+    for (int idx = 0; gemm_get_seg(p, idx, sg, m_tiles_rt); ++idx) {
       const int m_t = sg.m_t, n_t = sg.n_t, s = sg.split;
       const int m = m_t * kGemmBlockM + q * 32 + lane;  // accumulator row of this thread
       const int n0 = n_t * BLOCK_N;
@@ -270,7 +287,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       constexpr int CH = (BLOCK_N >= 32) ? 32 : 16;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += CH) {
-        if (n0 + c0 >= p.N) break;  // warp-uniform: nothing valid in this chunk
+        if (n0 + c0 >= N_rt) break;  // warp-uniform: nothing valid in this chunk
         float v[CH];
         {
           uint32_t r[CH];
@@ -279,7 +296,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(r[j]);
         }
-        const int nvalid = min(CH, p.N - (n0 + c0));
+        const int nvalid = min(CH, N_rt - (n0 + c0));
         if (sg.type == 1) {          // park the fp32 accumulators of this piece, the tile's owner finishes it
           float* w = skw + (long long)sg.slot * sk_piece;
 #pragma unroll
@@ -299,9 +316,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int j = 0; j < CH; ++j) v[j] += acc[j];
         }
         if constexpr (EPI == EPI_STORE || EPI == EPI_STORE_RES) {
-          if (m < p.M) {
-            bf16* orow = reinterpret_cast<bf16*>(p.out) + (long long)m * p.ldo + n0 + c0;
-            const bf16* rrow = (EPI == EPI_STORE_RES) ? p.residual + (long long)m * p.ldo + n0 + c0 : nullptr;
+          if (m < M_rt) {
+            bf16* orow = reinterpret_cast<bf16*>(p.out) + (long long)(m + roff_a) * p.ldo + n0 + c0;
+            const bf16* rrow = (EPI == EPI_STORE_RES) ? p.residual + (long long)(m + roff_a) * p.ldo + n0 + c0 : nullptr;
             const bool vec = (nvalid == CH) && ((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
             if (vec) {
 #pragma unroll
@@ -337,9 +354,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         } else if constexpr (EPI == EPI_SWIGLU) {
           // columns [c0, c0+16) = gate, [c0+16, c0+32) = up of output columns (n0+c0)/2 + j
           static_assert(EPI != EPI_SWIGLU || CH == 32, "SWIGLU needs 32-column chunks");
-          if (m < p.M) {
+          if (m < M_rt) {
             const int oc = (n0 + c0) >> 1;
-            bf16* orow = reinterpret_cast<bf16*>(p.out) + (long long)m * p.ldo + oc;
+            bf16* orow = reinterpret_cast<bf16*>(p.out) + (long long)(m + roff_a) * p.ldo + oc;
             float h[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -360,8 +377,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         } else if constexpr (EPI == EPI_T_STORE) {
-          if (m < p.M) {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)(n0 + c0) * p.ldo + m;
+          if (m < M_rt) {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)(n0 + c0 + roff_b) * p.ldo + m;
 #pragma unroll
             for (int j = 0; j < CH; ++j)
               if (j < nvalid) o[(long long)j * p.ldo] = __float2bfloat16_rn(v[j]);
@@ -369,7 +386,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         } else if constexpr (EPI == EPI_T_SWIGLU) {
           // rows of a 32-row warp slab: lanes 0-15 gate, lanes 16-31 up, for output feature (slab/2 + lane)
           const int f = ((m_t * kGemmBlockM + q * 32) >> 1) + (lane & 15);
-          bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)(n0 + c0) * p.ldo + f;
+          bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)(n0 + c0 + roff_b) * p.ldo + f;
 #pragma unroll
           for (int j = 0; j < CH; j += 2) {
             // lanes 16-31 hold `up`: hand two bf16 columns per shuffle to the gate lane 16 below
@@ -382,7 +399,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         } else {  // EPI_T_PARTIAL
-          if (m < p.M) {
+          if (m < M_rt) {
             float* o = reinterpret_cast<float*>(p.out) + (long long)s * p.split_stride +
                        (long long)(n0 + c0) * p.ldo + m;
 #pragma unroll

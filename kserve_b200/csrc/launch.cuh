@@ -11,6 +11,7 @@
 #include "gemm_2cta.cuh"
 #include "ops.cuh"
 #include "p2p.cuh"
+#include "moe.cuh"
 
 namespace b200 {
 
@@ -141,6 +142,9 @@ struct GemmArgs {
   int* sk_flags = nullptr;          // single-split swap-AB GEMMs whose tile count is not a multiple of the SM count
   size_t sk_ws_floats = 0;          // capacity of the workspace
   int sk_tiles = 0;                 // capacity of the flag array
+  const int* m_rt = nullptr;        // device-side runtime bounds (MoE expert token counts)
+  const int* n_rt = nullptr;
+  const int* row_off = nullptr;
 };
 
 inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStream_t s) {
@@ -162,7 +166,8 @@ inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStr
   p.out = a.out; p.residual = a.residual; p.ldo = a.ldo; p.split_stride = a.split_stride; p.out_cols = a.out_cols;
   p.hint_a = a.stream_a ? kEvictFirst : kEvictLast;
   p.hint_b = a.stream_a ? kEvictLast : kEvictNormal;
-  p.prefetch_a = a.stream_a ? 1 : 0;
+  p.m_rt = a.m_rt; p.n_rt = a.n_rt; p.row_off = a.row_off; p.swap_ab = a.stream_a ? 1 : 0;
+  p.prefetch_a = (a.stream_a && !a.n_rt && !a.m_rt) ? 1 : 0;
   {
     static const int l2pf = getenv("B200_L2_PREFETCH_KB") ? atoi(getenv("B200_L2_PREFETCH_KB")) : 0;
     p.l2_prefetch_kb = a.stream_a ? l2pf : 0;

@@ -63,6 +63,8 @@ class B200Engine:
         mc.max_prefill_tokens = max_prefill_tokens or max_batch * max_seq_len
         mc.num_kv_pages = num_kv_pages
         mc.tp_rank, mc.tp_size, mc.device = tp_rank, tp_size, device
+        mc.num_experts = int(cfg.get("num_local_experts", 0) or 0)
+        mc.num_experts_per_tok = int(cfg.get("num_experts_per_tok", 0) or 0) if mc.num_experts else 0
         self.device = device
         self.tp_size = tp_size
         h = C.c_void_p()
@@ -212,6 +214,12 @@ class B200Engine:
         tm = _lib.Timing()
         self.lib.b200_engine_last_timing(self.h, C.byref(tm))
         return tm.kernel_launches
+
+    def kv_swap_out(self, slot: int, scrub: bool = False) -> None:
+        _lib.check(self.lib.b200_kv_swap_out(self.h, slot, 1 if scrub else 0), "b200_kv_swap_out")
+
+    def kv_swap_in(self, slot: int) -> None:
+        _lib.check(self.lib.b200_kv_swap_in(self.h, slot), "b200_kv_swap_in")
 
     def fetch_staged(self) -> torch.Tensor:
         B, S, T = self._staged_shape

@@ -143,8 +143,8 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                 self.model_config = json.load(f)
         cfg = self.model_config
         arch = (cfg.get("architectures") or ["LlamaForCausalLM"])[0]
-        if not arch.endswith("ForCausalLM") or cfg.get("model_type", "llama") not in ("llama", "mistral"):
-            raise OpenAIError(f"architecture {arch} is not supported by the B200 runtime (Llama-family decoders only)")
+        if not arch.endswith("ForCausalLM") or cfg.get("model_type", "llama") not in ("llama", "mistral", "mixtral"):
+            raise OpenAIError(f"architecture {arch} is not supported by the B200 runtime (Llama / Mistral / Mixtral decoders only)")
         if self._tokenizer is None and self.model_id_or_path and os.path.exists(
                 os.path.join(self.model_id_or_path, "tokenizer.json")):
             from transformers import AutoTokenizer

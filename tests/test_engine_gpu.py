@@ -27,7 +27,8 @@ def _record(name, **kw):
         json.dump(STATS, f, indent=1)
 
 
-CASES = ["tiny_g2_ids", "tiny_g2_text", "tiny_g2_padinfer", "tiny_g4_ids", "tiny_g4_b1"]
+CASES = ["tiny_g2_ids", "tiny_g2_text", "tiny_g2_padinfer", "tiny_g4_ids", "tiny_g4_b1",
+         "tiny_moe_ids", "tiny_moe8_ids"]   # the last two: Mixtral-style sparse MoE (BASELINE configs[3] architecture)
 
 
 @pytest.fixture(scope="module")
@@ -162,3 +163,22 @@ def test_llama3_8b_shapes_two_layers():
         _record("llama3_8b_2l:greedy_tf", steps=int(pred.numel()), agree=int((pred == c["gen"]).sum()), decisive=int(decisive.sum()))
     finally:
         eng.close()
+
+
+def test_kv_host_offload_tier_roundtrip(engines):
+    """BASELINE configs[3] 'host-DRAM KV-offload tier': swap every sequence's KV pages out to pinned host memory
+    (scrubbing the device copy), swap them back in, and decoding continues bit-identically."""
+    c = load_case("tiny_g4_ids")
+    eng = engines(c)
+    T = 24
+    eng.stage(c["input_ids"], None, max_new_tokens=T, pad_token_id=0)
+    eng.run_staged(True, T - 1)
+    ref = eng.fetch_staged().clone()
+    eng.stage(c["input_ids"], None, max_new_tokens=T, pad_token_id=0)
+    eng.run_staged(True, 9)
+    for b in range(c["input_ids"].shape[0]):
+        eng.kv_swap_out(b, scrub=True)
+    for b in range(c["input_ids"].shape[0]):
+        eng.kv_swap_in(b)
+    eng.run_staged(False, T - 1 - 9)
+    assert torch.equal(eng.fetch_staged(), ref)
