@@ -158,6 +158,11 @@ int b200_op_attn_prefill(const void* q, int64_t ldq, void* out, int64_t ldo, con
                          const void* vcache, const int32_t* page_table, int max_pages,
                          const int32_t* cu_seqlens, const int32_t* seq_slot, int B, int max_len, int nh, int nkv,
                          void* stream);
+/* tcgen05/TMEM prefill attention (the engine's default); q_rows = rows of the q buffer, num_pages = pages of the caches */
+int b200_op_attn_prefill_tc(const void* q, int64_t ldq, int q_rows, void* out, int64_t ldo, const void* kcache,
+                            const void* vcache, int num_pages, const int32_t* page_table, int max_pages,
+                            const int32_t* cu_seqlens, const int32_t* seq_slot, int B, int max_len, int nh, int nkv,
+                            void* stream);
 int b200_op_attn_decode(const void* q, int64_t ldq, void* out, int64_t ldo, const void* kcache,
                         const void* vcache, const int32_t* page_table, int max_pages, const int32_t* seq_slot,
                         const int32_t* tok_pos, int B, int nh, int nkv, int splits, float* part_o, float* part_ml,

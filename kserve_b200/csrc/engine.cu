@@ -256,7 +256,15 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
       ap.q = e->qkv; ap.ldq = e->qkv_cols; ap.out = e->attn; ap.ldo = e->nh * kHeadDim;
       ap.kcache = kc; ap.vcache = vc; ap.page_table = e->d_page_table; ap.max_pages = e->max_pages;
       ap.cu_seqlens = e->d_cu; ap.seq_slot = e->d_seq_slot; ap.nh = e->nh; ap.nkv = e->nkv; ap.scale_log2 = scale_log2;
-      if ((rc = launch_attn_prefill(ap, B, max_len, s))) return rc;
+      static const bool attn_mma = getenv("B200_ATTN_MMA") != nullptr;   // legacy mma.sync kernel for A/B runs
+      if (attn_mma) {
+        if ((rc = launch_attn_prefill(ap, B, max_len, s))) return rc;
+      } else {
+        AttnTcParams tp_{};
+        tp_.out = e->attn; tp_.ldo = e->nh * kHeadDim; tp_.page_table = e->d_page_table; tp_.max_pages = e->max_pages;
+        tp_.cu_seqlens = e->d_cu; tp_.seq_slot = e->d_seq_slot; tp_.nh = e->nh; tp_.nkv = e->nkv; tp_.scale_log2 = scale_log2;
+        if ((rc = launch_attn_prefill_tc(e->tmaps, e->qkv, e->cap_T, e->qkv_cols, kc, vc, e->num_pages, tp_, B, max_len, s))) return rc;
+      }
       e->launches++;
     }
     // ---- row-parallel projections (o_proj, down_proj) followed by residual add + next RMSNorm
@@ -392,11 +400,13 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
   a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
   if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
   const int use_p2p = (e->cfg.tp_size > 1 && e->p2p_ready) ? 1 : 0;
-  B200_CUDA_OK(launch_k(argmax_kernel, dim3(B), dim3(1024), 0, s, (const bf16*)e->logits, (long long)e->Vl, e->Vl, e->v0, e->cand_val, e->cand_idx, e->p2p, use_p2p));
+  // one GPU: 16 CTAs per row scan slices of the 128k-entry row (a single CTA per row took 65 us of the 4.3 ms step)
+  const int chunks = (e->cfg.tp_size == 1 && e->Vl >= 16384) ? 16 : 1;
+  B200_CUDA_OK(launch_k(argmax_kernel, dim3(B, chunks), dim3(1024), 0, s, (const bf16*)e->logits, (long long)e->Vl, e->Vl, e->v0, e->cand_val, e->cand_idx, e->p2p, use_p2p));
   e->launches += 2;
   const float* cv = e->cand_val;
   const int32_t* ci = e->cand_idx;
-  int ranks = 1;
+  int ranks = chunks;
   if (e->cfg.tp_size > 1 && !use_p2p) {
     Nccl& n = Nccl::get();
     B200_NCCL_OK(n.AllGather(e->cand_val, e->cand_val_all, B, Nccl::kFloat, e->comm, s));
@@ -752,8 +762,8 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   B200_CUDA_OK(cudaMemset(e->sk_flags, 0, (size_t)e->sk_tiles * sizeof(int)));
   if ((rc = dmalloc(&e->part_o, (size_t)c->max_batch * e->nkv * 8 * e->G * kHeadDim))) return rc;
   if ((rc = dmalloc(&e->part_ml, (size_t)c->max_batch * e->nkv * 8 * e->G * 2))) return rc;
-  if ((rc = dmalloc(&e->cand_val, (size_t)c->max_batch))) return rc;
-  if ((rc = dmalloc(&e->cand_idx, (size_t)c->max_batch))) return rc;
+  if ((rc = dmalloc(&e->cand_val, (size_t)c->max_batch * 16))) return rc;
+  if ((rc = dmalloc(&e->cand_idx, (size_t)c->max_batch * 16))) return rc;
   if ((rc = dmalloc(&e->cand_val_all, (size_t)c->max_batch * tp))) return rc;
   if ((rc = dmalloc(&e->cand_idx_all, (size_t)c->max_batch * tp))) return rc;
   // bookkeeping
@@ -1301,6 +1311,18 @@ int b200_op_attn_prefill(const void* q, int64_t ldq, void* out, int64_t ldo, con
   return launch_attn_prefill(p, B, max_len, (cudaStream_t)stream);
 }
 
+int b200_op_attn_prefill_tc(const void* q, int64_t ldq, int q_rows, void* out, int64_t ldo, const void* kcache,
+                            const void* vcache, int num_pages, const int32_t* page_table, int max_pages,
+                            const int32_t* cu_seqlens, const int32_t* seq_slot, int B, int max_len, int nh, int nkv,
+                            void* stream) {
+  g_op_tmaps.maps.clear();
+  AttnTcParams p{};
+  p.out = (bf16*)out; p.ldo = ldo; p.page_table = page_table; p.max_pages = max_pages; p.cu_seqlens = cu_seqlens;
+  p.seq_slot = seq_slot; p.nh = nh; p.nkv = nkv; p.scale_log2 = (1.0f / sqrtf((float)kHeadDim)) * 1.4426950408889634f;
+  return launch_attn_prefill_tc(g_op_tmaps, (const bf16*)q, q_rows, ldq, (const bf16*)kcache, (const bf16*)vcache, num_pages, p, B,
+                                max_len, (cudaStream_t)stream);
+}
+
 int b200_op_attn_decode(const void* q, int64_t ldq, void* out, int64_t ldo, const void* kcache, const void* vcache,
                         const int32_t* page_table, int max_pages, const int32_t* seq_slot, const int32_t* tok_pos, int B,
                         int nh, int nkv, int splits, float* part_o, float* part_ml, void* stream) {
@@ -1325,7 +1347,7 @@ int b200_op_rope_kv(const void* qkv, int64_t ld, void* q_out, int64_t ldq, void*
 }
 
 int b200_op_argmax(const void* logits, int64_t ld, int B, int V, float* out_val, int32_t* out_idx, void* stream) {
-  argmax_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, V, 0, out_val, out_idx, P2P{}, 0);
+  argmax_kernel<<<dim3(B, 1), 1024, 0, (cudaStream_t)stream>>>((const bf16*)logits, ld, V, 0, out_val, out_idx, P2P{}, 0);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }

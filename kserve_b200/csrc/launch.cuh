@@ -6,6 +6,7 @@
 #include <tuple>
 
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "common.cuh"
 #include "gemm_tcgen05.cuh"
 #include "gemm_2cta.cuh"
@@ -259,6 +260,25 @@ inline int launch_attn_prefill(const AttnPrefillParams& p, int B, int max_len, c
   }
   dim3 grid((max_len + 63) / 64, p.nh, B);
   B200_CUDA_OK(launch_k(attn_prefill_kernel, grid, dim3(kAttnThreads), kPrefillSmem, s, p));
+  return 0;
+}
+
+// tcgen05 prefill attention: q rows [q_rows][ldq] (head h at column h*128), paged caches [num_pages][nkv][64][128]
+inline int launch_attn_prefill_tc(TmapCache& cache, const bf16* q, int q_rows, long long ldq, const bf16* kcache,
+                                  const bf16* vcache, int num_pages, const AttnTcParams& p, int B, int max_len, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA_OK(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+    configured = true;
+  }
+  const CUtensorMap *tq, *tk, *tv;
+  int rc = cache.get(q, (uint64_t)q_rows, (uint64_t)ldq, 128, &tq);
+  if (rc) return rc;
+  const uint64_t kv_rows = (uint64_t)num_pages * p.nkv * kPageTokens;
+  if ((rc = cache.get(kcache, kv_rows, kHeadDim, 64, &tk))) return rc;
+  if ((rc = cache.get(vcache, kv_rows, kHeadDim, 64, &tv))) return rc;
+  dim3 grid((max_len + kTcQ - 1) / kTcQ, p.nh, B);
+  B200_CUDA_OK(launch_k(attn_prefill_tc_kernel, grid, dim3(kTcThreads), kTcSmem, s, *tq, *tk, *tv, p));
   return 0;
 }
 

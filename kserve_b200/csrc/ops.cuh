@@ -314,11 +314,15 @@ argmax_kernel(const bf16* __restrict__ logits, long long ld, int V, int idx_offs
   pdl_launch_dependents();
   pdl_wait();
   _ts.mark();
-  const int b = blockIdx.x;
+  // grid = (B, chunks): chunk c scans [c*per, (c+1)*per) of the row and writes candidate slot [c][b]; the step
+  // kernel merges the slots exactly like the per-rank candidates of the vocabulary-parallel case
+  const int b = blockIdx.x, B = gridDim.x;
+  const int per = (V + gridDim.y - 1) / gridDim.y;
+  const int v0 = blockIdx.y * per, v1 = min(V, v0 + per);
   const bf16* row = logits + (long long)b * ld;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+  for (int i = v0 + threadIdx.x; i < v1; i += blockDim.x) {
     const float v = __bfloat162float(row[i]);
     if (v > best || (v == best && i < bi)) { best = v; bi = i; }
   }
@@ -344,9 +348,10 @@ argmax_kernel(const bf16* __restrict__ logits, long long ld, int V, int idx_offs
       if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
     if (l == 0) {
-      out_val[b] = best;
-      out_idx[b] = bi + idx_offset;
-      if (use_p2p) push_candidate(pp, b, best, bi + idx_offset);   // vocab-parallel: hand the candidate to every rank
+      const int gi = (bi == 0x7fffffff) ? bi : bi + idx_offset;
+      out_val[blockIdx.y * B + b] = best;
+      out_idx[blockIdx.y * B + b] = gi;
+      if (use_p2p) push_candidate(pp, b, best, gi);   // vocab-parallel (single chunk): hand the candidate to every rank
     }
   }
 }

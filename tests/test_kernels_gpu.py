@@ -243,6 +243,28 @@ def test_attn_prefill(lib, nh, nkv, lens):
 
 
 @pytest.mark.parametrize("nh,nkv", [(4, 2), (8, 2), (32, 8)])
+@pytest.mark.parametrize("lens", [[5], [64, 1, 130], [200, 63, 65, 128, 129], [700, 257]])
+def test_attn_prefill_tcgen05(lib, nh, nkv, lens):
+    """The tcgen05 / TMEM prefill attention (engine default) against the fp32 statement of causal GQA attention."""
+    B = len(lens)
+    kc, vc, pt, max_pages, kd, vd = _build_cache(B, lens, nkv, seed=21)
+    T = sum(lens)
+    q = _rand(T + 130, nh * 128, seed=22)      # rows beyond T exist so a 128-row TMA box never leaves the buffer
+    out = torch.zeros((T, nh * 128), dtype=torch.bfloat16, device=DEV)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=DEV)
+    slot = torch.arange(B, dtype=torch.int32, device=DEV)
+    _check(lib, lib.b200_op_attn_prefill_tc(_ptr(q), nh * 128, q.shape[0], _ptr(out), nh * 128, _ptr(kc), _ptr(vc), kc.shape[0],
+                                            _ptr(pt), max_pages, _ptr(cu), _ptr(slot), B, max(lens), nh, nkv, None), "attn_prefill_tc")
+    torch.cuda.synchronize()
+    t0 = 0
+    for b, l in enumerate(lens):
+        qb = q[t0:t0 + l].view(l, nh, 128).transpose(0, 1)
+        ref = _attn_ref(qb, kd[b, :, :l], vd[b, :, :l], causal_offset=0)
+        _cmp(f"attn_prefill_tc b{b} len{l}", out[t0:t0 + l], ref, 2e-2, 2e-2)
+        t0 += l
+
+
+@pytest.mark.parametrize("nh,nkv", [(4, 2), (8, 2), (32, 8)])
 @pytest.mark.parametrize("splits", [1, 2, 5])
 def test_attn_decode(lib, nh, nkv, splits):
     lens = [1, 64, 65, 200, 1000, 17]
