@@ -124,7 +124,10 @@ def synth_state_dict(cfg: dict, seed: int = 0, dtype=torch.bfloat16) -> Dict[str
 def checksum(sd: Dict[str, torch.Tensor]) -> float:
     """Cheap fingerprint recorded in golden files to prove both sides loaded the same bytes."""
     s = 0.0
-    for name in ("model.embed_tokens.weight", "lm_head.weight", "model.layers.0.self_attn.o_proj.weight"):
+    third = "model.layers.0.mlp.down_proj.weight"
+    if third not in sd:   # MoE checkpoints have fused expert tensors instead
+        third = "model.layers.0.self_attn.o_proj.weight"
+    for name in ("model.embed_tokens.weight", "lm_head.weight", third):
         t = sd[name]
         s += float(t[: 64].float().sum()) + float(t[-1].float().abs().sum())
     return s
