@@ -22,7 +22,7 @@ def test_tp2_matches_oracle_fixture():
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     line = [l for l in res.stdout.splitlines() if l.startswith("TPRESULT ")][0]
     ret = {k: torch.tensor(v) for k, v in json.loads(line[len("TPRESULT "):]).items()}
-    for name in ("tiny_g4_ids", "tiny_g2_ids"):
+    for name in ("tiny_g4_ids", "tiny_g2_ids", "tiny_moe8_ids"):
         c = load_case(name)
         tol = logits_tol(c["step_logits"])
         assert torch.equal(ret[name + ":forced"], c["output_ids"])

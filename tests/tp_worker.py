@@ -20,7 +20,7 @@ def main():
     from kserve_b200.tp import broadcast_nccl_id
     from oracle import weights as W
     out = {}
-    for name in ("tiny_g4_ids", "tiny_g2_ids"):
+    for name in ("tiny_g4_ids", "tiny_g2_ids", "tiny_moe8_ids"):
         c = load_case(name)
         m = c["meta"]
         nccl_id = broadcast_nccl_id(rank)   # an ncclUniqueId is single-use: one per communicator
