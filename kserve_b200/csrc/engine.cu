@@ -162,6 +162,7 @@ struct b200_engine {
   unsigned char* ar_local = nullptr;
   void* ar_peer_map[kMaxTp] = {nullptr};
   int *row_epoch = nullptr, *cand_epoch = nullptr;
+  int ar_index = 0;   // index of the next peer all-reduce inside the forward pass being recorded
   bool p2p_ready = false;
   P2P p2p{};
   b200_timing_t timing{};
@@ -197,6 +198,7 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
   const bool tp = e->cfg.tp_size > 1;
   int rc;
   pdl_phase() = decode;
+  e->ar_index = 0;
   B200_CUDA_OK(launch_k(embed_gather_kernel, dim3(T), dim3(128), 0, s, (const int32_t*)(decode ? e->d_next_tok : e->d_tok), (const bf16*)e->embed, e->x, H, e->V));
   e->launches++;
   if ((rc = launch_rmsnorm(0, e->x, e->layers[0].ln1, e->xn, T, H, eps, nullptr, 0, 0, 0, nullptr, s))) return rc;
@@ -283,7 +285,8 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
           }
           if (e->p2p_ready) {   // split-K reduce + all-reduce over peer memory + residual + RMSNorm in one kernel
             B200_CUDA_OK(launch_k(allreduce_norm_kernel, dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, e->p2p,
-                                  e->x, next_norm, e->xn, eps, (const float*)e->ws, sp, (long long)B * H, (long long)H, (const bf16*)nullptr));
+                                  e->x, next_norm, e->xn, eps, (const float*)e->ws, sp, (long long)B * H, (long long)H, (const bf16*)nullptr,
+                                  e->ar_index++, 2 * e->L));
             e->launches++;
             return 0;
           }
@@ -296,7 +299,8 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
           e->launches++;
           if (tp && e->p2p_ready) {
             B200_CUDA_OK(launch_k(allreduce_norm_kernel, dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, e->p2p,
-                                  e->x, next_norm, e->xn, eps, (const float*)nullptr, 0, 0LL, 0LL, (const bf16*)e->ybuf));
+                                  e->x, next_norm, e->xn, eps, (const float*)nullptr, 0, 0LL, 0LL, (const bf16*)e->ybuf,
+                                  e->ar_index++, 2 * e->L));
             e->launches++;
             return 0;
           }
@@ -358,7 +362,12 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
       cp.ysum = tp ? e->ybuf : nullptr;
       B200_CUDA_OK(launch_k(moe_combine_norm_kernel, dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, cp));
       e->launches++;
-      if (tp) {
+      if (tp && decode && e->p2p_ready) {   // all-reduce of the combined expert outputs + residual + next norm, over peer memory
+        B200_CUDA_OK(launch_k(allreduce_norm_kernel, dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, e->p2p,
+                              e->x, next_norm, e->xn, eps, (const float*)nullptr, 0, 0LL, 0LL, (const bf16*)e->ybuf,
+                              e->ar_index++, 2 * e->L));
+        e->launches++;
+      } else if (tp) {
         if ((rc = allreduce_bf16(e, e->ybuf, (size_t)T * H))) return rc;
         if ((rc = launch_rmsnorm(2, e->x, next_norm, e->xn, T, H, eps, nullptr, 0, 0, 0, e->ybuf, s))) return rc;
         e->launches++;
@@ -388,6 +397,7 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
     e->launches++;
     if ((rc = row_parallel(e->hbuf, e->I, w.wdown, next_norm))) return rc;
   }
+  B200_REQUIRE(e->ar_index == 0 || e->ar_index == 2 * e->L, "peer all-reduce count per step must be 2 per layer");
   return 0;
 }
 

@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(128) step_update_kernel(const StepParams p) {
   _ts.mark();
   __shared__ int s_stop, s_unfinished;
   StepState* st = p.st;
+  if (p.use_p2p && threadIdx.x == 0) p.pp.row_epoch[0] += 1;   // epoch base of the next step's peer all-reduces
   if (st->done) return;
   const int step = st->step;
   if (threadIdx.x == 0) { s_stop = 0; s_unfinished = 0; }

@@ -26,8 +26,8 @@ struct ArLayout {
   __host__ __device__ static ArLayout make(int H) {
     ArLayout l;
     l.H = H;
-    l.y_off = 0;                                                   // bf16 y[2][kArRows][H]
-    l.flag_off = (size_t)2 * kArRows * H * 2;                      // int flag[2][kMaxTp][kArRows]
+    l.y_off = 0;                                                   // u64 ll[2][kMaxTp][kArRows][H/2]: (epoch << 32) | bf16x2
+    l.flag_off = (size_t)2 * kMaxTp * kArRows * (H / 2) * 8;       // int flag[2][kMaxTp][kArRows] (unused by the LL path)
     l.cval_off = l.flag_off + (size_t)2 * kMaxTp * kArRows * 4;    // float cand_val[2][kMaxTp][kArRows]
     l.cidx_off = l.cval_off + (size_t)2 * kMaxTp * kArRows * 4;    // int cand_idx[2][kMaxTp][kArRows]
     l.cflag_off = l.cidx_off + (size_t)2 * kMaxTp * kArRows * 4;   // int cand_flag[2][kMaxTp][kArRows]
@@ -40,7 +40,7 @@ struct P2P {
   unsigned char* peer[kMaxTp];   // peer[rank] == local block
   int tp, rank;
   ArLayout lay;
-  int* row_epoch;                // [kArRows] local, all-reduce epochs
+  int* row_epoch;                // [0]: decode steps completed (all-reduce epoch base), written by step_update_kernel
   int* cand_epoch;               // [kArRows] local, candidate-exchange epochs
 };
 
@@ -60,6 +60,16 @@ __device__ __forceinline__ uint4 ld_sys_v4(const void* p) {
   uint4 r;
   asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
   return r;
+}
+// "LL" packets: every 8-byte word carries 4 bytes of payload and the 4-byte epoch, so that the arrival of the
+// word itself is the synchronisation (one NVLink one-way store latency, no fence + flag round).  64-bit scalar
+// elements are single-copy atomic; the .v2 form only groups two of them into one transaction.
+__device__ __forceinline__ void st_ll2(void* p, uint32_t d0, uint32_t d1, uint32_t epoch) {
+  const unsigned long long a = ((unsigned long long)epoch << 32) | d0, b = ((unsigned long long)epoch << 32) | d1;
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_ll2(const void* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void spin_until(const int* flag, int want) {
   uint32_t spins = 0;

@@ -21,8 +21,17 @@ def main():
     cfg = dict(LLAMA3_8B, num_hidden_layers=layers)
     B, S, T = 32, 1024, 8
     lib = _lib.load()
-    eng = B200Engine(cfg, max_batch=B, max_seq_len=S + T + 8, max_prefill_tokens=B * S)
-    eng.load_weights(gpu_weights(cfg, torch.device("cuda")))
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+        from kserve_b200.tp import broadcast_nccl_id
+        dist.init_process_group("gloo")
+        nccl_id = broadcast_nccl_id(rank)
+    eng = B200Engine(cfg, max_batch=B, max_seq_len=S + T + 8, max_prefill_tokens=B * S, device=local, tp_rank=rank, tp_size=world,
+                     nccl_id=nccl_id)
+    eng.load_weights(gpu_weights(cfg, torch.device("cuda", local)))
     ids = torch.randint(3, 128000, (B, S), dtype=torch.int64)
     eng.stage(ids, None, max_new_tokens=T, pad_token_id=0)
     eng.run_staged(True, 4)          # warm: graph captured
@@ -35,6 +44,9 @@ def main():
     n = C.c_int32()
     _lib.check(lib.b200_debug_trace_read(buf.ctypes.data, cap, C.byref(n)), "read")
     lib.b200_debug_trace(0)
+    if rank != 0:
+        eng.close()
+        return
     rec = buf[: n.value]
     t0, t1 = rec[:, 0].astype(np.int64), rec[:, 1].astype(np.int64)
     tm = rec[:, 2].astype(np.int64)
