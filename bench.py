@@ -29,6 +29,13 @@ LLAMA3_8B = dict(vocab_size=128256, hidden_size=4096, intermediate_size=14336, n
                  rms_norm_eps=1e-5, rope_theta=500000.0)
 
 
+# Mixtral-8x7B dims (8 experts, top-2), run with --model mixtral_8x7b at TP=4
+MIXTRAL_8X7B = dict(vocab_size=32000, hidden_size=4096, intermediate_size=14336, num_hidden_layers=32,
+                    num_attention_heads=32, num_key_value_heads=8, head_dim=128, max_position_embeddings=8192,
+                    rms_norm_eps=1e-5, rope_theta=1000000.0, num_local_experts=8, num_experts_per_tok=2)
+MODELS = {"llama3_8b": ("Llama-3-8B", LLAMA3_8B), "mixtral_8x7b": ("Mixtral-8x7B", MIXTRAL_8X7B)}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -41,8 +48,12 @@ def algorithmic(cfg, B, S_in, S_out, tp=1):
     """SURVEY.md §8(d) figures, computed from the config (per GPU when tp > 1)."""
     H, I, V, L = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"], cfg["num_hidden_layers"]
     nh, nkv, d = cfg["num_attention_heads"], cfg["num_key_value_heads"], cfg["head_dim"]
-    layer_params = H * (nh + 2 * nkv) * d + nh * d * H + 3 * H * I
-    weight_bytes = (L * layer_params + V * H) * 2 / tp
+    E, topk = int(cfg.get("num_local_experts", 0) or 0), int(cfg.get("num_experts_per_tok", 0) or 0)
+    attn_params = H * (nh + 2 * nkv) * d + nh * d * H
+    # MoE decode streams every expert once B * top_k picks cover them all (SURVEY.md §8d); flops count the top-k only
+    layer_stream = attn_params + (E * 3 * H * I + E * H if E else 3 * H * I)
+    layer_params = attn_params + (topk * 3 * H * I + E * H if E else 3 * H * I)
+    weight_bytes = (L * layer_stream + V * H) * 2 / tp
     kv_per_tok = L * 2 * nkv * d * 2 / tp
     mean_ctx = S_in + (S_out - 1) / 2 + 1
     decode_bytes = weight_bytes + B * mean_ctx * kv_per_tok
@@ -198,14 +209,14 @@ def run_b200(args):
         dist.broadcast(buf, 0)
         nccl_id = bytes(buf.cpu().tolist())
 
-    cfg = LLAMA3_8B
+    model_name, cfg = MODELS[args.model]
     B, S, T = args.batch, args.prompt_len, args.gen_len
     eng = B200Engine(cfg, max_batch=B, max_seq_len=S + T, max_prefill_tokens=B * S, device=local,
                      tp_rank=rank, tp_size=world, nccl_id=nccl_id)
     eng.load_weights(gpu_weights(cfg, dev))
     torch.cuda.empty_cache()
     g = torch.Generator().manual_seed(1234)
-    ids = torch.randint(3, 128000, (B, S), generator=g, dtype=torch.int64).pin_memory()
+    ids = torch.randint(3, min(128000, cfg["vocab_size"] - 8), (B, S), generator=g, dtype=torch.int64).pin_memory()
     pad = cfg["vocab_size"] - 1
 
     def barrier():
@@ -270,10 +281,10 @@ def run_b200(args):
         "metric": "output tokens/s", "value": round(value, 1), "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"Llama-3-8B (random-init, bf16) {S}-in/{T}-out batch {B}, greedy, "
+        "config": {"workload": f"{model_name} (random-init, bf16) {S}-in/{T}-out batch {B}, greedy, "
                                f"{'TP=' + str(world) if world > 1 else '1 GPU'}",
                    "global_batch": B, "prompt_len": S, "gen_len": T, "parallelism": f"tp{world}",
-                   "l2": "weights 16 GB / N per GPU >> 126 MB L2: no flush needed", "timer": "CUDA events on the engine stream, max over ranks"},
+                   "l2": f"weights {alg['weight_bytes'] / 1e9:.1f} GB per GPU >> 126 MB L2: no flush needed", "timer": "CUDA events on the engine stream, max over ranks"},
         "ttft_p50_ms": round(ttft_p50, 2),
         "decode_ms_per_token_step": round(dec_step_ms, 4),
         "wall_s": round(wall, 3),
@@ -290,7 +301,7 @@ def run_b200(args):
                              "frac": round(ach_tf / peaks["tf_sustained"], 4), "peak_src": peaks["src"],
                              "algorithmic_flops_per_launch": alg["prefill_flops"]},
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.model == "llama3_8b":
         eng.close()
         del eng
         torch.cuda.empty_cache()
@@ -320,6 +331,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="llama3_8b", choices=sorted(MODELS))
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--prompt-len", type=int, default=1024)
     ap.add_argument("--gen-len", type=int, default=128)

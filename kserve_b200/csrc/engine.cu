@@ -85,6 +85,8 @@ struct b200_engine {
   b200_model_config_t cfg;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;            // second micro-batch of a tensor-parallel prefill
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   // per-rank dims
   int H, nh, nkv, G, I, V, Vl, v0, qkv_cols, L;
@@ -180,30 +182,61 @@ static int pick_splits(const b200_engine* e, int n_out, int K) {
   return effective_splits(K, s);
 }
 
-static int allreduce_bf16(b200_engine* e, bf16* buf, size_t count) {
+static int allreduce_bf16(b200_engine* e, bf16* buf, size_t count, cudaStream_t s) {
   if (e->cfg.tp_size == 1) return 0;
   Nccl& n = Nccl::get();
-  B200_NCCL_OK(n.AllReduce(buf, buf, count, Nccl::kBf16, Nccl::kSum, e->comm, e->stream));
+  B200_NCCL_OK(n.AllReduce(buf, buf, count, Nccl::kBf16, Nccl::kSum, e->comm, s));
   return 0;
 }
 
 // ---- one transformer stack pass over T token rows --------------------------------------------------
 // decode == true : T == B rows, swap-AB GEMMs (+ split-K), flash-decoding attention
 // decode == false: packed prompt tokens, row-major GEMMs, causal flash attention
-static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode) {
-  cudaStream_t s = e->stream;
-  const int H = e->H, bn = pick_block_n(B);
+static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, bool decode) {
+  const int H = e->H, bn = pick_block_n(B_all);
   const float eps = e->cfg.rms_eps;
   const float scale_log2 = (1.0f / sqrtf((float)kHeadDim)) * 1.4426950408889634f;
   const bool tp = e->cfg.tp_size > 1;
   int rc;
   pdl_phase() = decode;
   e->ar_index = 0;
-  B200_CUDA_OK(launch_k(embed_gather_kernel, dim3(T), dim3(128), 0, s, (const int32_t*)(decode ? e->d_next_tok : e->d_tok), (const bf16*)e->embed, e->x, H, e->V));
-  e->launches++;
-  if ((rc = launch_rmsnorm(0, e->x, e->layers[0].ln1, e->xn, T, H, eps, nullptr, 0, 0, 0, nullptr, s))) return rc;
-  e->launches++;
-  for (int l = 0; l < e->L; ++l) {
+  if (!decode) e->tmaps.trim();
+  // Tensor-parallel prefill runs as two micro-batches (halves of the sequences = two row ranges of the packed
+  // buffers) on two streams, issued layer by layer: while one half's 256 MiB all-reduce is on the wire the other
+  // half's GEMMs / attention own the SMs (SURVEY.md §8e "prefill ... overlap by token-chunking").
+  struct View { long long r0; int T, b0, B; cudaStream_t s; };
+  View views[2] = {{0, T_all, 0, B_all, e->stream}, {0, 0, 0, 0, e->stream2}};
+  int nv = 1, gsms = e->num_sms;   // SMs the GEMM grids are sized for
+  static const bool mb_off = getenv("B200_NO_PREFILL_OVERLAP") != nullptr;
+  static const int mb_min_t = getenv("B200_PREFILL_OVERLAP_MIN_T") ? atoi(getenv("B200_PREFILL_OVERLAP_MIN_T")) : 2048;
+  if (!decode && tp && e->E == 0 && B_all >= 2 && T_all >= mb_min_t && !mb_off) {
+    const int b0 = B_all / 2;
+    long long r0 = 0;
+    for (int b = 0; b < b0; ++b) r0 += e->st.lens[b];
+    views[0] = View{0, (int)r0, 0, b0, e->stream};
+    views[1] = View{r0, (int)(T_all - r0), b0, B_all - b0, e->stream2};
+    nv = 2;
+    // leave a few SMs to the collective: the persistent GEMM grids would otherwise wait for them tile-round after tile-round
+    static const int reserve = getenv("B200_PREFILL_RESERVE_SMS") ? atoi(getenv("B200_PREFILL_RESERVE_SMS")) : 0;
+    static const int mult = getenv("B200_PREFILL_GRID_MULT") ? atoi(getenv("B200_PREFILL_GRID_MULT")) : 1;
+    gsms = std::max(2, e->num_sms - reserve) * std::max(1, mult);
+    B200_CUDA_OK(cudaEventRecord(e->ev_fork, e->stream));
+    B200_CUDA_OK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+  }
+  for (int v = 0; v < nv; ++v) {
+    const View& vw = views[v];
+    B200_CUDA_OK(launch_k(embed_gather_kernel, dim3(vw.T), dim3(128), 0, vw.s, (const int32_t*)(decode ? e->d_next_tok : e->d_tok + vw.r0),
+                          (const bf16*)e->embed, e->x + vw.r0 * H, H, e->V));
+    e->launches++;
+    if ((rc = launch_rmsnorm(0, e->x + vw.r0 * H, e->layers[0].ln1, e->xn + vw.r0 * H, vw.T, H, eps, nullptr, 0, 0, 0, nullptr, vw.s))) return rc;
+    e->launches++;
+  }
+  for (int l = 0; l < e->L; ++l)
+  for (int v = 0; v < nv; ++v) {
+    const View& vw = views[v];
+    const int T = vw.T, B = vw.B;
+    const long long r0 = vw.r0;        // first row of this micro-batch in the packed activation buffers (0 in decode)
+    cudaStream_t s = vw.s;
     const LayerW& w = e->layers[l];
     bf16* kc = e->kcache + (long long)l * e->layer_stride;
     bf16* vc = e->vcache + (long long)l * e->layer_stride;
@@ -223,12 +256,12 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
       rp.q_out = e->qdec; rp.ldq = e->nh * kHeadDim;
       rp.tok_seq = e->d_seq_slot; rp.tok_pos = e->d_dec_pos;
     } else {
-      GemmArgs a{e->xn, e->cap_T, w.wqkv, e->qkv_cols, T, e->qkv_cols, H, EPI_STORE, 256, 1,
-                 e->qkv, nullptr, e->qkv_cols, 0, 0, false};
-      if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
-      rp.qkv = e->qkv;
-      rp.q_out = e->qkv; rp.ldq = e->qkv_cols;  // in place
-      rp.tok_seq = e->d_tok_seq; rp.tok_pos = e->d_tok_pos;
+      GemmArgs a{e->xn + r0 * H, e->cap_T - (int)r0, w.wqkv, e->qkv_cols, T, e->qkv_cols, H, EPI_STORE, 256, 1,
+                 e->qkv + r0 * e->qkv_cols, nullptr, e->qkv_cols, 0, 0, false};
+      if ((rc = launch_gemm(e->tmaps, a, gsms, s))) return rc;
+      rp.qkv = e->qkv + r0 * e->qkv_cols;
+      rp.q_out = e->qkv + r0 * e->qkv_cols; rp.ldq = e->qkv_cols;  // in place
+      rp.tok_seq = e->d_tok_seq + r0; rp.tok_pos = e->d_tok_pos + r0;
     }
     rp.kcache = kc; rp.vcache = vc; rp.page_table = e->d_page_table; rp.max_pages = e->max_pages;
     rp.cos_tab = e->cos_tab; rp.sin_tab = e->sin_tab; rp.nh = e->nh; rp.nkv = e->nkv;
@@ -257,14 +290,14 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
       AttnPrefillParams ap{};
       ap.q = e->qkv; ap.ldq = e->qkv_cols; ap.out = e->attn; ap.ldo = e->nh * kHeadDim;
       ap.kcache = kc; ap.vcache = vc; ap.page_table = e->d_page_table; ap.max_pages = e->max_pages;
-      ap.cu_seqlens = e->d_cu; ap.seq_slot = e->d_seq_slot; ap.nh = e->nh; ap.nkv = e->nkv; ap.scale_log2 = scale_log2;
+      ap.cu_seqlens = e->d_cu + vw.b0; ap.seq_slot = e->d_seq_slot + vw.b0; ap.nh = e->nh; ap.nkv = e->nkv; ap.scale_log2 = scale_log2;
       static const bool attn_mma = getenv("B200_ATTN_MMA") != nullptr;   // legacy mma.sync kernel for A/B runs
       if (attn_mma) {
         if ((rc = launch_attn_prefill(ap, B, max_len, s))) return rc;
       } else {
         AttnTcParams tp_{};
         tp_.out = e->attn; tp_.ldo = e->nh * kHeadDim; tp_.page_table = e->d_page_table; tp_.max_pages = e->max_pages;
-        tp_.cu_seqlens = e->d_cu; tp_.seq_slot = e->d_seq_slot; tp_.nh = e->nh; tp_.nkv = e->nkv; tp_.scale_log2 = scale_log2;
+        tp_.cu_seqlens = e->d_cu + vw.b0; tp_.seq_slot = e->d_seq_slot + vw.b0; tp_.nh = e->nh; tp_.nkv = e->nkv; tp_.scale_log2 = scale_log2;
         if ((rc = launch_attn_prefill_tc(e->tmaps, e->qkv, e->cap_T, e->qkv_cols, kc, vc, e->num_pages, tp_, B, max_len, s))) return rc;
       }
       e->launches++;
@@ -307,18 +340,18 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
         }
       } else {
         if (!tp) {
-          GemmArgs a{act, e->cap_T, wmat, H, T, H, K, EPI_STORE_RES, 256, 1, e->x, e->x, H, 0, 0, false};
-          if ((rc2 = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc2;
+          GemmArgs a{act, e->cap_T, wmat, H, T, H, K, EPI_STORE_RES, 256, 1, e->x, e->x, H, 0, 0, false};   // (r0 == 0: one GPU)
+          if ((rc2 = launch_gemm(e->tmaps, a, gsms, s))) return rc2;
           if ((rc2 = launch_rmsnorm(0, e->x, next_norm, e->xn, T, H, eps, nullptr, 0, 0, 0, nullptr, s))) return rc2;
           e->launches += 2;
           return 0;
         }
-        GemmArgs a{act, e->cap_T, wmat, H, T, H, K, EPI_STORE, 256, 1, e->ybuf, nullptr, H, 0, 0, false};
-        if ((rc2 = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc2;
+        GemmArgs a{act + r0 * K, e->cap_T - (int)r0, wmat, H, T, H, K, EPI_STORE, 256, 1, e->ybuf + r0 * H, nullptr, H, 0, 0, false};
+        if ((rc2 = launch_gemm(e->tmaps, a, gsms, s))) return rc2;
         e->launches++;
       }
-      if ((rc2 = allreduce_bf16(e, e->ybuf, (size_t)T * H))) return rc2;
-      if ((rc2 = launch_rmsnorm(2, e->x, next_norm, e->xn, T, H, eps, nullptr, 0, 0, 0, e->ybuf, s))) return rc2;
+      if ((rc2 = allreduce_bf16(e, e->ybuf + r0 * H, (size_t)T * H, s))) return rc2;
+      if ((rc2 = launch_rmsnorm(2, e->x + r0 * H, next_norm, e->xn + r0 * H, T, H, eps, nullptr, 0, 0, 0, e->ybuf + r0 * H, s))) return rc2;
       e->launches++;
       return 0;
     };
@@ -347,10 +380,10 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
         } else {
           GemmArgs a{e->xg, e->g_rows, wgu, 2 * e->I, T, 2 * e->I, H, EPI_SWIGLU, 256, 1, e->hg, nullptr, e->I, 0, e->I, false};
           a.m_rt = e->e_count + x; a.row_off = e->e_off + x;
-          if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+          if ((rc = launch_gemm(e->tmaps, a, gsms, s))) return rc;
           GemmArgs d{e->hg, e->g_rows, wdn, H, T, H, e->I, EPI_STORE, 256, 1, e->yg, nullptr, H, 0, 0, false};
           d.m_rt = e->e_count + x; d.row_off = e->e_off + x;
-          if ((rc = launch_gemm(e->tmaps, d, e->num_sms, s))) return rc;
+          if ((rc = launch_gemm(e->tmaps, d, gsms, s))) return rc;
         }
         e->launches += 2;
       }
@@ -368,7 +401,7 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
                               e->ar_index++, 2 * e->L));
         e->launches++;
       } else if (tp) {
-        if ((rc = allreduce_bf16(e, e->ybuf, (size_t)T * H))) return rc;
+        if ((rc = allreduce_bf16(e, e->ybuf, (size_t)T * H, s))) return rc;
         if ((rc = launch_rmsnorm(2, e->x, next_norm, e->xn, T, H, eps, nullptr, 0, 0, 0, e->ybuf, s))) return rc;
         e->launches++;
       }
@@ -377,7 +410,8 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
     // ---- gate/up projection with the SwiGLU fused into the epilogue
     if (decode) {
       const int gu_tiles = (2 * e->I + kGemmBlockM - 1) / kGemmBlockM;
-      const int gsp = (gu_tiles * 4 >= e->num_sms * 3) ? 1 : pick_splits(e, 2 * e->I, H);
+      static const bool gu_sk = getenv("B200_GU_STREAMK") != nullptr;
+      const int gsp = (gu_sk || gu_tiles * 4 >= e->num_sms * 3) ? 1 : pick_splits(e, 2 * e->I, H);
       if (gsp > 1) {   // few tiles per GPU (tensor parallel): split-K partials + a reducing SwiGLU kernel
         GemmArgs a{w.wgu, 2 * e->I, e->xn, e->cap_T, 2 * e->I, B, H, EPI_T_PARTIAL, bn, gsp, e->ws, nullptr, 2 * e->I,
                    (long long)B * 2 * e->I, 0, true};
@@ -391,13 +425,17 @@ static int forward_layers(b200_engine* e, int T, int B, int max_len, bool decode
         if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
       }
     } else {
-      GemmArgs a{e->xn, e->cap_T, w.wgu, 2 * e->I, T, 2 * e->I, H, EPI_SWIGLU, 256, 1, e->hbuf, nullptr, e->I, 0, e->I, false};
-      if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+      GemmArgs a{e->xn + r0 * H, e->cap_T - (int)r0, w.wgu, 2 * e->I, T, 2 * e->I, H, EPI_SWIGLU, 256, 1, e->hbuf + r0 * e->I, nullptr, e->I, 0, e->I, false};
+      if ((rc = launch_gemm(e->tmaps, a, gsms, s))) return rc;
     }
     e->launches++;
     if ((rc = row_parallel(e->hbuf, e->I, w.wdown, next_norm))) return rc;
   }
   B200_REQUIRE(e->ar_index == 0 || e->ar_index == 2 * e->L, "peer all-reduce count per step must be 2 per layer");
+  if (nv == 2) {
+    B200_CUDA_OK(cudaEventRecord(e->ev_join, e->stream2));
+    B200_CUDA_OK(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+  }
   return 0;
 }
 
@@ -680,6 +718,9 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   B200_REQUIRE(e->Vl > 0, "empty vocabulary shard");
   e->qkv_cols = (e->nh + 2 * e->nkv) * kHeadDim;
   B200_CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  B200_CUDA_OK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  B200_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  B200_CUDA_OK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   B200_CUDA_OK(cudaEventCreate(&e->ev0));
   B200_CUDA_OK(cudaEventCreate(&e->ev1));
   B200_CUDA_OK(cudaEventCreate(&e->ev2));
@@ -859,6 +900,9 @@ int b200_engine_destroy(b200_engine_t* e) {
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->ev2) cudaEventDestroy(e->ev2);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
   return 0;

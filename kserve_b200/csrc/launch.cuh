@@ -69,6 +69,11 @@ struct TmapCache {
     *out = &it->second;
     return 0;
   }
+  // called between forward passes (no descriptor pointer outstanding): micro-batch views of ragged prompts key new
+  // maps by their row offset, so the table is bounded here
+  void trim(size_t max_entries = 2048) {
+    if (maps.size() > max_entries) maps.clear();
+  }
 };
 
 // Every kernel of the forward path is launched with programmatic stream serialization so that its prologue
@@ -179,7 +184,8 @@ inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStr
   p.sched = 0; p.sk_slots = 0; p.sk_ws = a.sk_ws; p.sk_flags = a.sk_flags;
   // only when every tile is cut into at most two pieces (m_tiles >= SMs): finishing many-piece tiles inside the
   // kernel serialises the reduction on the tile owner and measured slower than split-K + a reducing consumer
-  const bool sk_any = getenv("B200_STREAMK_ANY") != nullptr;
+  static const bool gu_sk = getenv("B200_GU_STREAMK") != nullptr;
+  const bool sk_any = getenv("B200_STREAMK_ANY") != nullptr || (gu_sk && a.epi == EPI_T_SWIGLU);
   if (sk_on && a.sk_ws && a.sk_flags && a.stream_a && p.splits == 1 && p.n_tiles == 1 && p.m_tiles <= a.sk_tiles &&
       (p.m_tiles >= num_sms || sk_any) && (p.m_tiles % num_sms) != 0 && (a.epi == EPI_T_STORE || a.epi == EPI_T_SWIGLU)) {
     const long long W = (long long)p.m_tiles * p.kb_total;

@@ -11,14 +11,16 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_tp2_matches_oracle_fixture():
+@pytest.mark.parametrize("overlap_min_t", ["2048", "1"])   # "1": force the two-micro-batch prefill on the tiny prompts
+def test_tp2_matches_oracle_fixture(overlap_min_t):
     import json
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29633", os.path.join(here, "tp_worker.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, B200_PREFILL_OVERLAP_MIN_T=overlap_min_t))
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     line = [l for l in res.stdout.splitlines() if l.startswith("TPRESULT ")][0]
     ret = {k: torch.tensor(v) for k, v in json.loads(line[len("TPRESULT "):]).items()}
