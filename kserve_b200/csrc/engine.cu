@@ -364,8 +364,21 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
       B200_CUDA_OK(launch_k(moe_offsets_kernel, dim3(1), dim3(1024), 0, s, (const int32_t*)e->tok_expert, T, e->E, e->e_count, e->e_off, e->tok_row));
       B200_CUDA_OK(launch_k(moe_gather_kernel, dim3(T), dim3(128), 0, s, (const bf16*)e->xn, (const int32_t*)e->tok_row, e->xg, H));
       e->launches += 3;
-      const int dsp = decode ? pick_splits(e, H, e->I) : 1;
-      for (int x = 0; x < e->E; ++x) {
+      // decode: ONE grouped launch per projection over all experts (E * tiles fill the SMs; the weights of experts
+      // without tokens are skipped).  B200_MOE_PER_EXPERT=1 restores one launch per expert (A/B).
+      static const bool per_expert = getenv("B200_MOE_PER_EXPERT") != nullptr;
+      const bool grouped = decode && !per_expert;
+      const int dsp = (decode && !grouped) ? pick_splits(e, H, e->I) : 1;
+      if (grouped) {
+        GemmArgs a{w.wgu_e, e->E * 2 * e->I, e->xg, e->g_rows, 2 * e->I, B, H, EPI_T_SWIGLU, bn, 1, e->hg, nullptr, e->I, 0, e->I, true};
+        a.n_rt = e->e_count; a.row_off = e->e_off; a.groups = e->E;
+        if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+        GemmArgs d{w.wdown_e, e->E * H, e->hg, e->g_rows, H, B, e->I, EPI_T_STORE, bn, 1, e->yg, nullptr, H, 0, 0, true};
+        d.n_rt = e->e_count; d.row_off = e->e_off; d.groups = e->E;
+        if ((rc = launch_gemm(e->tmaps, d, e->num_sms, s))) return rc;
+        e->launches += 2;
+      }
+      for (int x = 0; x < e->E && !grouped; ++x) {
         const bf16* wgu = w.wgu_e + (long long)x * 2 * e->I * H;
         const bf16* wdn = w.wdown_e + (long long)x * H * e->I;
         if (decode) {

@@ -50,6 +50,11 @@ struct GemmParams {
   const int* n_rt;
   const int* row_off;      // device row offset of the activation / output rows inside a grouped (per-expert) buffer
   int swap_ab;             // 1: A is the weight (decode kernels) -> row_off applies to B and to the output rows n
+  // grouped (per-expert) swap-AB problem in ONE launch: A = [groups][M][K] stacked weights, m_tiles = groups * group_m_tiles;
+  // tile m_t belongs to group g = m_t / group_m_tiles whose activation rows are row_off[g] .. + n_rt[g] (tiles of
+  // empty groups are skipped: their weights are never streamed) and whose outputs start at out + g * group_out_stride
+  int group_m_tiles;
+  long long group_out_stride;
   int sched;
   int sk_slots;            // partial slots per tile
   float* sk_ws;            // [m_tiles][sk_slots][BLOCK_N][128] fp32
@@ -172,14 +177,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   int M_rt = p.M, N_rt = p.N;
+  const int gmt = p.group_m_tiles;
   if (p.m_rt != nullptr || p.n_rt != nullptr) {   // extents produced by the previous kernel
     pdl_wait();
     if (p.m_rt) M_rt = min(p.M, *p.m_rt);
-    if (p.n_rt) N_rt = min(p.N, *p.n_rt);
+    if (p.n_rt && !gmt) N_rt = min(p.N, *p.n_rt);
   }
-  const int m_tiles_rt = (M_rt <= 0 || N_rt <= 0) ? 0 : (M_rt + kGemmBlockM - 1) / kGemmBlockM;
-  const int roff = p.row_off ? *p.row_off : 0;   // (read after the wait above: set together with m_rt / n_rt)
-  const int roff_a = p.swap_ab ? 0 : roff, roff_b = p.swap_ab ? roff : 0;
+  const int m_tiles_rt = gmt ? p.m_tiles : ((M_rt <= 0 || N_rt <= 0) ? 0 : (M_rt + kGemmBlockM - 1) / kGemmBlockM);
+  const int roff = (p.row_off && !gmt) ? *p.row_off : 0;   // (read after the wait above: set together with m_rt / n_rt)
+  const int roff_a = p.swap_ab ? 0 : roff;
+  int roff_b = p.swap_ab ? roff : 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -190,6 +197,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       GemmSeg sg;
       for (int idx = 0; gemm_get_seg(p, idx, sg, m_tiles_rt); ++idx) {
         const int m_t = sg.m_t, n_t = sg.n_t, kb0 = sg.kb0, kb1 = sg.kb1;
+        int a_row = m_t * kGemmBlockM + roff_a, b_off = roff_b;
+        if (gmt) {
+          const int g = m_t / gmt;
+          if (p.n_rt[g] <= 0) continue;
+          a_row = g * p.M + (m_t - g * gmt) * kGemmBlockM;
+          b_off = p.row_off[g];
+        }
         int kb = kb0;
         if (first) {
           first = false;
@@ -199,14 +213,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int npre = min(STAGES, kb1 - kb0);
             for (int i = 0; i < npre; ++i) {
               mbar_arrive_expect_tx(&full_bar[i], Cfg::kStageBytes);
-              tma_load_2d(smem + i * Cfg::kStageBytes, &tmap_a, &full_bar[i], (kb0 + i) * kGemmBlockK, m_t * kGemmBlockM + roff_a, p.hint_a);
+              tma_load_2d(smem + i * Cfg::kStageBytes, &tmap_a, &full_bar[i], (kb0 + i) * kGemmBlockK, a_row, p.hint_a);
             }
             const int npf = min(npre + p.l2_prefetch_kb, kb1 - kb0);
             for (int i = npre; i < npf; ++i) tma_prefetch_l2_2d(&tmap_a, (kb0 + i) * kGemmBlockK, m_t * kGemmBlockM);
             pdl_wait();
             _ts.mark();
             for (int i = 0; i < npre; ++i)
-              tma_load_2d(smem + i * Cfg::kStageBytes + Cfg::kABytes, &tmap_b, &full_bar[i], (kb0 + i) * kGemmBlockK, n_t * BLOCK_N + roff_b, p.hint_b);
+              tma_load_2d(smem + i * Cfg::kStageBytes + Cfg::kABytes, &tmap_b, &full_bar[i], (kb0 + i) * kGemmBlockK, n_t * BLOCK_N + b_off, p.hint_b);
             kb = kb0 + npre;
             if (npre == STAGES) { stage = 0; phase = 1; } else { stage = npre; }
           } else {
@@ -218,8 +232,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m_t * kGemmBlockM + roff_a, p.hint_a);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n_t * BLOCK_N + roff_b, p.hint_b);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBlockK, a_row, p.hint_a);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n_t * BLOCK_N + b_off, p.hint_b);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -236,6 +250,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       GemmSeg sg;
       for (int idx = 0; gemm_get_seg(p, idx, sg, m_tiles_rt); ++idx) {
         const int kb0 = sg.kb0, kb1 = sg.kb1;
+        if (gmt && p.n_rt[sg.m_t / gmt] <= 0) continue;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -266,18 +281,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t acc_phase = 0;
     GemmSeg sg;
     for (int idx = 0; gemm_get_seg(p, idx, sg, m_tiles_rt); ++idx) {
-      const int m_t = sg.m_t, n_t = sg.n_t, s = sg.split;
+      const int n_t = sg.n_t, s = sg.split;
+      int m_t = sg.m_t;
+      long long out_off = 0;   // elements
+      if (gmt) {
+        const int g = m_t / gmt;
+        N_rt = min(p.N, p.n_rt[g]);
+        if (N_rt <= 0) continue;
+        roff_b = p.row_off[g];
+        m_t -= g * gmt;         // tile index inside the group: output features are per expert
+        out_off = (long long)g * p.group_out_stride;
+      }
       const int m = m_t * kGemmBlockM + q * 32 + lane;  // accumulator row of this thread
       const int n0 = n_t * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const long long sk_piece = (long long)BLOCK_N * kGemmBlockM;
-      float* skw = (sg.type != 0) ? p.sk_ws + ((long long)m_t * p.sk_slots) * sk_piece + q * 32 + lane : nullptr;
+      float* skw = (sg.type != 0) ? p.sk_ws + ((long long)sg.m_t * p.sk_slots) * sk_piece + q * 32 + lane : nullptr;
       if (sg.type == 2) {   // wait until every other piece of this tile has been parked
         if (threadIdx.x == 64) {
           uint32_t spins = 0;
-          while (*reinterpret_cast<volatile int*>(p.sk_flags + m_t) != sg.slot) {
-            if (++spins > (1u << 28)) { printf("b200: stream-K flag timeout (tile %d)\n", m_t); __trap(); }
+          while (*reinterpret_cast<volatile int*>(p.sk_flags + sg.m_t) != sg.slot) {
+            if (++spins > (1u << 28)) { printf("b200: stream-K flag timeout (tile %d)\n", sg.m_t); __trap(); }
           }
           __threadfence();
         }
@@ -378,7 +403,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         } else if constexpr (EPI == EPI_T_STORE) {
           if (m < M_rt) {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)(n0 + c0 + roff_b) * p.ldo + m;
+            bf16* o = reinterpret_cast<bf16*>(p.out) + out_off + (long long)(n0 + c0 + roff_b) * p.ldo + m;
 #pragma unroll
             for (int j = 0; j < CH; ++j)
               if (j < nvalid) o[(long long)j * p.ldo] = __float2bfloat16_rn(v[j]);
@@ -386,7 +411,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         } else if constexpr (EPI == EPI_T_SWIGLU) {
           // rows of a 32-row warp slab: lanes 0-15 gate, lanes 16-31 up, for output feature (slab/2 + lane)
           const int f = ((m_t * kGemmBlockM + q * 32) >> 1) + (lane & 15);
-          bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)(n0 + c0 + roff_b) * p.ldo + f;
+          bf16* o = reinterpret_cast<bf16*>(p.out) + out_off + (long long)(n0 + c0 + roff_b) * p.ldo + f;
 #pragma unroll
           for (int j = 0; j < CH; j += 2) {
             // lanes 16-31 hold `up`: hand two bf16 columns per shuffle to the gate lane 16 below
@@ -400,7 +425,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         } else {  // EPI_T_PARTIAL
           if (m < M_rt) {
-            float* o = reinterpret_cast<float*>(p.out) + (long long)s * p.split_stride +
+            float* o = reinterpret_cast<float*>(p.out) + out_off + (long long)s * p.split_stride +
                        (long long)(n0 + c0) * p.ldo + m;
 #pragma unroll
             for (int j = 0; j < CH; ++j)
@@ -414,10 +439,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (sg.type == 1) {          // publish the partial
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) atomicAdd(p.sk_flags + m_t, 1);
+        if (threadIdx.x == 64) atomicAdd(p.sk_flags + sg.m_t, 1);
       } else if (sg.type == 2) {   // consumed: leave the flag clean for the next launch / graph replay
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) atomicExch(p.sk_flags + m_t, 0);
+        if (threadIdx.x == 64) atomicExch(p.sk_flags + sg.m_t, 0);
       }
     }
   }

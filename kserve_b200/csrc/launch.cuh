@@ -151,6 +151,8 @@ struct GemmArgs {
   const int* m_rt = nullptr;        // device-side runtime bounds (MoE expert token counts)
   const int* n_rt = nullptr;
   const int* row_off = nullptr;
+  int groups = 0;                   // > 0: grouped swap-AB problem (see GemmParams::group_m_tiles); A rows = groups * M,
+  long long group_out_stride = 0;   // n_rt / row_off are arrays of `groups` entries
 };
 
 inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStream_t s) {
@@ -173,6 +175,12 @@ inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStr
   p.hint_a = a.stream_a ? kEvictFirst : kEvictLast;
   p.hint_b = a.stream_a ? kEvictLast : kEvictNormal;
   p.m_rt = a.m_rt; p.n_rt = a.n_rt; p.row_off = a.row_off; p.swap_ab = a.stream_a ? 1 : 0;
+  p.group_m_tiles = 0; p.group_out_stride = a.group_out_stride;
+  if (a.groups > 0) {
+    B200_REQUIRE(a.stream_a && a.n_rt && a.row_off && !a.m_rt && a.N <= a.block_n, "grouped GEMM: swap-AB with per-group n_rt / row_off");
+    p.group_m_tiles = p.m_tiles;
+    p.m_tiles *= a.groups;
+  }
   p.prefetch_a = (a.stream_a && !a.n_rt && !a.m_rt) ? 1 : 0;
   {
     static const int l2pf = getenv("B200_L2_PREFETCH_KB") ? atoi(getenv("B200_L2_PREFETCH_KB")) : 0;
@@ -186,7 +194,7 @@ inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStr
   // kernel serialises the reduction on the tile owner and measured slower than split-K + a reducing consumer
   static const bool gu_sk = getenv("B200_GU_STREAMK") != nullptr;
   const bool sk_any = getenv("B200_STREAMK_ANY") != nullptr || (gu_sk && a.epi == EPI_T_SWIGLU);
-  if (sk_on && a.sk_ws && a.sk_flags && a.stream_a && p.splits == 1 && p.n_tiles == 1 && p.m_tiles <= a.sk_tiles &&
+  if (sk_on && a.groups == 0 && a.sk_ws && a.sk_flags && a.stream_a && p.splits == 1 && p.n_tiles == 1 && p.m_tiles <= a.sk_tiles &&
       (p.m_tiles >= num_sms || sk_any) && (p.m_tiles % num_sms) != 0 && (a.epi == EPI_T_STORE || a.epi == EPI_T_SWIGLU)) {
     const long long W = (long long)p.m_tiles * p.kb_total;
     const int g2 = (int)std::min<long long>(num_sms, W);
