@@ -359,11 +359,19 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
     const bf16* next_norm = (l + 1 < e->L) ? e->layers[l + 1].ln1 : e->final_norm;
     if (e->E > 0) {
       // ---- sparse MoE: route, group rows per expert, run the expert GEMMs bounded by the device-side counts, combine
-      B200_CUDA_OK(launch_k(moe_router_kernel, dim3((T + 3) / 4), dim3(128), 0, s, (const bf16*)e->xn, (const bf16*)w.wr, T, H, e->E,
-                            e->tok_expert, e->tok_weight));
-      B200_CUDA_OK(launch_k(moe_offsets_kernel, dim3(1), dim3(1024), 0, s, (const int32_t*)e->tok_expert, T, e->E, e->e_count, e->e_off, e->tok_row));
-      B200_CUDA_OK(launch_k(moe_gather_kernel, dim3(T), dim3(128), 0, s, (const bf16*)e->xn, (const int32_t*)e->tok_row, e->xg, H));
-      e->launches += 3;
+      if (decode && T <= kMoeDecodeMaxT) {
+        B200_CUDA_OK(launch_k(moe_router_decode_kernel, dim3(T), dim3(32 * e->E), 0, s, (const bf16*)e->xn, (const bf16*)w.wr, H, e->E,
+                              e->tok_expert, e->tok_weight));
+        B200_CUDA_OK(launch_k(moe_place_gather_kernel, dim3(T), dim3(256), 0, s, (const bf16*)e->xn, (const int32_t*)e->tok_expert, T, H, e->E,
+                              e->e_count, e->e_off, e->tok_row, e->xg));
+        e->launches += 2;
+      } else {
+        B200_CUDA_OK(launch_k(moe_router_kernel, dim3((T + 3) / 4), dim3(128), 0, s, (const bf16*)e->xn, (const bf16*)w.wr, T, H, e->E,
+                              e->tok_expert, e->tok_weight));
+        B200_CUDA_OK(launch_k(moe_offsets_kernel, dim3(1), dim3(1024), 0, s, (const int32_t*)e->tok_expert, T, e->E, e->e_count, e->e_off, e->tok_row));
+        B200_CUDA_OK(launch_k(moe_gather_kernel, dim3(T), dim3(128), 0, s, (const bf16*)e->xn, (const int32_t*)e->tok_row, e->xg, H));
+        e->launches += 3;
+      }
       // decode: ONE grouped launch per projection over all experts (E * tiles fill the SMs; the weights of experts
       // without tokens are skipped).  B200_MOE_PER_EXPERT=1 restores one launch per expert (A/B).
       static const bool per_expert = getenv("B200_MOE_PER_EXPERT") != nullptr;

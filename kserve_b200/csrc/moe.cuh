@@ -130,6 +130,104 @@ moe_gather_kernel(const bf16* __restrict__ xn, const int32_t* __restrict__ tok_r
   }
 }
 
+// Decode (T <= 64 rows).  r01 timeline: the one-warp-per-token router walked E dependent dot products (47 us per
+// layer at T = 32), and a variant in which every CTA recomputed all T * E logits pulled 4 MB per CTA through L2
+// (58 us).  Here: one CTA per token with one warp per expert (8 KB of x + 8 KB of router row per warp, loads
+// batched 8 deep), then one kernel that rebuilds the (tiny) placement tables in every CTA and copies its token.
+// Same arithmetic and the same deterministic token-order placement as the prefill kernels above.
+constexpr int kMoeDecodeMaxT = 64;
+__global__ void __launch_bounds__(32 * kMaxExperts)
+moe_router_decode_kernel(const bf16* __restrict__ xn, const bf16* __restrict__ wr, int H, int E,
+                         int32_t* __restrict__ tok_expert, float* __restrict__ tok_weight) {
+  TraceScope _ts(TK_OTHER);
+  pdl_launch_dependents();
+  __shared__ float s_logit[kMaxExperts];
+  const int e = threadIdx.x >> 5, lane = threadIdx.x & 31, t = blockIdx.x;
+  pdl_wait();
+  _ts.mark();
+  {
+    const bf16* xr = xn + (long long)t * H;
+    const bf16* w = wr + (long long)e * H;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int i = lane * 8; i < H; i += 256) {
+      const uint4 xu = *reinterpret_cast<const uint4*>(xr + i), wu = *reinterpret_cast<const uint4*>(w + i);
+      const uint32_t xw[4] = {xu.x, xu.y, xu.z, xu.w}, ww[4] = {wu.x, wu.y, wu.z, wu.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = unpack_bf16x2(xw[j]), b = unpack_bf16x2(ww[j]);
+        acc += a.x * b.x + a.y * b.y;
+      }
+    }
+    acc = bf16_round(warp_sum(acc));   // F.linear output is bf16
+    if (lane == 0) s_logit[e] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mx = -INFINITY;
+    for (int x = 0; x < E; ++x) mx = fmaxf(mx, s_logit[x]);
+    float p[kMaxExperts], sum = 0.f;
+    for (int x = 0; x < E; ++x) { p[x] = expf(s_logit[x] - mx); sum += p[x]; }
+    for (int x = 0; x < E; ++x) p[x] /= sum;
+    int i0 = 0;
+    for (int x = 1; x < E; ++x) if (p[x] > p[i0]) i0 = x;           // lowest index wins ties
+    int i1 = (i0 == 0) ? 1 : 0;
+    for (int x = 0; x < E; ++x) if (x != i0 && p[x] > p[i1]) i1 = x;
+    const float s2 = p[i0] + p[i1];
+    tok_expert[t * 2] = i0; tok_expert[t * 2 + 1] = i1;
+    tok_weight[t * 2] = p[i0] / s2; tok_weight[t * 2 + 1] = p[i1] / s2;
+  }
+}
+
+// grid T: every CTA rebuilds count / off / tok_row from the 2T expert picks (ballot prefix per expert), CTA t
+// copies token t into its two expert segments, CTA 0 publishes the tables.
+__global__ void __launch_bounds__(256)
+moe_place_gather_kernel(const bf16* __restrict__ xn, const int32_t* __restrict__ tok_expert, int T, int H, int E,
+                        int32_t* __restrict__ count, int32_t* __restrict__ off, int32_t* __restrict__ tok_row,
+                        bf16* __restrict__ xg) {
+  TraceScope _ts(TK_OTHER);
+  pdl_launch_dependents();
+  __shared__ int s_e[kMoeDecodeMaxT * 2], s_rel[kMoeDecodeMaxT * 2];
+  __shared__ int s_cnt[kMaxExperts], s_off[kMaxExperts + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int A = T * 2;
+  pdl_wait();
+  _ts.mark();
+  for (int a = threadIdx.x; a < kMoeDecodeMaxT * 2; a += blockDim.x) s_e[a] = a < A ? tok_expert[a] : -1;
+  __syncthreads();
+  for (int e = warp; e < E; e += 8) {
+    int base = 0;
+    for (int c = 0; c < kMoeDecodeMaxT * 2; c += 32) {
+      const bool hit = s_e[c + lane] == e;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) s_rel[c + lane] = base + __popc(m & ((1u << lane) - 1u));
+      base += __popc(m);
+    }
+    if (lane == 0) s_cnt[e] = base;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int o = 0;
+    for (int e = 0; e < E; ++e) { s_off[e] = o; o += (s_cnt[e] + 7) & ~7; }
+    s_off[E] = o;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int a = threadIdx.x; a < A; a += blockDim.x) tok_row[a] = s_off[s_e[a]] + s_rel[a];
+    if ((int)threadIdx.x < E) count[threadIdx.x] = s_cnt[threadIdx.x];
+    if ((int)threadIdx.x <= E) off[threadIdx.x] = s_off[threadIdx.x];
+  }
+  const int t = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(xn + (long long)t * H);
+  uint4* d0 = reinterpret_cast<uint4*>(xg + (long long)(s_off[s_e[t * 2]] + s_rel[t * 2]) * H);
+  uint4* d1 = reinterpret_cast<uint4*>(xg + (long long)(s_off[s_e[t * 2 + 1]] + s_rel[t * 2 + 1]) * H);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = src[i];
+    d0[i] = v;
+    d1[i] = v;
+  }
+}
+
 // Combine + residual + next RMSNorm.  Expert outputs are either bf16 rows yg[row][H] (prefill) or fp32 split-K
 // partials part[e][split][n][H] with n = row - off[e] (decode).  TP: writes the per-rank partial sum to `ysum`
 // instead (the caller all-reduces it and applies the residual / norm afterwards).

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import LLAMA3_8B, gpu_weights  # noqa: E402
+from bench import MODELS, gpu_weights  # noqa: E402
 from kserve_b200 import _lib  # noqa: E402
 from kserve_b200.engine import B200Engine  # noqa: E402
 
@@ -18,7 +18,7 @@ EPI = {3: "T_STORE", 4: "T_SWIGLU", 5: "T_PARTIAL", 0: "STORE", 1: "STORE_RES", 
 
 def main():
     layers = int(os.environ.get("LAYERS", "4"))
-    cfg = dict(LLAMA3_8B, num_hidden_layers=layers)
+    cfg = dict(MODELS[os.environ.get("MODEL", "llama3_8b")][1], num_hidden_layers=layers)
     B, S, T = 32, 1024, 8
     lib = _lib.load()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -32,7 +32,7 @@ def main():
     eng = B200Engine(cfg, max_batch=B, max_seq_len=S + T + 8, max_prefill_tokens=B * S, device=local, tp_rank=rank, tp_size=world,
                      nccl_id=nccl_id)
     eng.load_weights(gpu_weights(cfg, torch.device("cuda", local)))
-    ids = torch.randint(3, 128000, (B, S), dtype=torch.int64)
+    ids = torch.randint(3, min(128000, cfg["vocab_size"] - 8), (B, S), dtype=torch.int64)
     eng.stage(ids, None, max_new_tokens=T, pad_token_id=0)
     eng.run_staged(True, 4)          # warm: graph captured
     torch.cuda.synchronize()
