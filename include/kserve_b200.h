@@ -178,6 +178,33 @@ int b200_op_argmax(const void* logits, int64_t ld, int B, int V, float* out_val,
 int b200_kv_swap_out(b200_engine_t* e, int32_t slot, int32_t scrub);
 int b200_kv_swap_in(b200_engine_t* e, int32_t slot);
 
+/* Continuous (iteration-level) batching — SURVEY.md §8(f) rank 1.  Replaces the reference's strictly serial request
+ * loop (python/huggingfaceserver/huggingfaceserver/generative_model.py:341-354: one `generate` at a time) and the
+ * throughput role of the Go batcher (pkg/batcher/handler.go:157-188): sequences join and leave the running batch
+ * between decode steps.  One engine, one scheduler thread (calls are not re-entrant); tp_size must be 1.
+ *
+ *   b200_cb_begin   enter the mode (slot s owns KV pages [s * pages_per_seq, (s+1) * pages_per_seq)); eos ids apply to
+ *                   every sequence, as `generation_config.eos_token_id` does in the reference
+ *   b200_cb_admit   prefill n new prompts (host int64 token rows) into free slots and emit their first token;
+ *                   per-sequence max_new and up to 4 stop sequences of <= 8 tokens each:
+ *                   stop_count[i] sequences for prompt i, stop_offsets = running offsets (sum(stop_count) + 1 entries)
+ *                   into stop_tokens; slots_out[i] receives the slot of prompt i
+ *   b200_cb_step    n decode iterations over every running slot (CUDA graph per row count); finished sequences are
+ *                   frozen on the device until released
+ *   b200_cb_poll    per slot: tokens generated so far, finished flag, stop-sequence flag ([max_batch] each)
+ *   b200_cb_read    generated tokens [first, first + cap) of a slot (for streaming reads as well as final results)
+ *   b200_cb_release free the slot (its row leaves the decode batch at the next step)
+ *   b200_cb_end     leave the mode
+ * Greedy results per sequence are identical to b200_generate on that prompt alone. */
+int b200_cb_begin(b200_engine_t* e, int64_t pad_token_id, const int64_t* eos_token_ids, int32_t num_eos);
+int b200_cb_admit(b200_engine_t* e, int32_t n, const int64_t* const* rows, const int32_t* lens, const int32_t* max_new,
+                  const int32_t* stop_count, const int32_t* stop_offsets, const int64_t* stop_tokens, int32_t* slots_out);
+int b200_cb_step(b200_engine_t* e, int32_t n_steps);
+int b200_cb_poll(b200_engine_t* e, int32_t* n_gen, int32_t* finished, int32_t* stop_hit);
+int b200_cb_read(b200_engine_t* e, int32_t slot, int32_t first, int64_t* out, int32_t cap, int32_t* n_out);
+int b200_cb_release(b200_engine_t* e, int32_t slot);
+int b200_cb_end(b200_engine_t* e);
+
 /* Debug timeline: capacity > 0 enables per-CTA {t0, t1 (globaltimer ns), kind, block} records (24 bytes each),
  * 0 disables; read drains up to `capacity` records into `out`. */
 int b200_debug_trace(int32_t capacity);

@@ -18,6 +18,8 @@ def main(argv=None):
     parser.add_argument("--dtype", default="auto", choices=["auto", "bfloat16"], help="the B200 engine computes in bf16")
     parser.add_argument("--backend", default="b200", choices=["b200"])
     parser.add_argument("--max_batch", type=int, default=32)
+    parser.add_argument("--continuous_batching", action="store_true",
+                        help="iteration-level batching: requests join / leave the running decode batch between steps")
     parser.add_argument("--tensor_parallel_size", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
     parser.add_argument("--enable_batcher", action="store_true", help="batch V1 :predict like the Go agent (--max-batchsize/--max-latency)")
     parser.add_argument("--max-batchsize", dest="max_batchsize", type=int, default=32)
@@ -35,7 +37,7 @@ def main(argv=None):
         nccl_id = broadcast_nccl_id(rank)
     model = B200GenerativeModel(args.model_name, path, max_model_len=args.max_model_len, max_batch=args.max_batch,
                                 device=int(os.environ.get("LOCAL_RANK", "0")), tensor_parallel_size=args.tensor_parallel_size,
-                                tp_rank=rank, nccl_id=nccl_id)
+                                tp_rank=rank, nccl_id=nccl_id, continuous_batching=args.continuous_batching)
     model.load()
     if rank != 0:
         from .tp import follower_loop

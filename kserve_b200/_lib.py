@@ -83,6 +83,14 @@ def load() -> C.CDLL:
     lib.b200_engine_ipc_import.argtypes = [vp, vp, i32]
     lib.b200_kv_swap_out.argtypes = [vp, i32, i32]
     lib.b200_kv_swap_in.argtypes = [vp, i32]
+    lib.b200_cb_begin.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64), i32]
+    lib.b200_cb_admit.argtypes = [vp, i32, C.POINTER(C.POINTER(C.c_int64)), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
+                                  C.POINTER(i32), C.POINTER(C.c_int64), C.POINTER(i32)]
+    lib.b200_cb_step.argtypes = [vp, i32]
+    lib.b200_cb_poll.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.b200_cb_read.argtypes = [vp, i32, i32, C.POINTER(C.c_int64), i32, C.POINTER(i32)]
+    lib.b200_cb_release.argtypes = [vp, i32]
+    lib.b200_cb_end.argtypes = [vp]
     lib.b200_debug_trace.argtypes = [i32]
     lib.b200_debug_trace_read.argtypes = [vp, i32, C.POINTER(i32)]
     _lib = lib

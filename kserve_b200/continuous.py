@@ -1,0 +1,218 @@
+"""Iteration-level ("continuous") batching scheduler over one B200Engine — SURVEY.md §8(f) rank 1.
+
+The reference executes requests strictly one at a time (`_process_requests`,
+python/huggingfaceserver/huggingfaceserver/generative_model.py:341-354; quirk q10) and relies on the Go batcher
+(pkg/batcher/handler.go:157-188) to merge concurrent clients into one `generate`.  Here every request joins the
+running decode batch at the next step boundary and leaves it as soon as it is finished; the per-request semantics
+of the reference are preserved:
+
+  * the rows of ONE request advance in lockstep (they are admitted together) and the request ends when all of its
+    rows are finished; finished rows are padded with pad_token_id up to the longest row (utils.py:2796-2797, q3)
+  * a stop sequence that matches in ANY row ends the whole request at that step
+    (stop_sequence_stopping_criteria.py:36-48, q6) and reports stop_triggered
+  * greedy tokens per row are those of `engine.generate` on that request alone.
+
+The scheduler owns the engine: all b200_cb_* calls are made from its thread (the C ABI is not re-entrant).
+"""
+from __future__ import annotations
+
+import asyncio
+import threading
+import time
+from collections import deque
+from dataclasses import dataclass, field
+from typing import Callable, Deque, Dict, List, Optional, Sequence
+
+import torch
+
+from .engine import B200Engine, GenerateResult
+
+
+@dataclass
+class _Request:
+    prompts: List[List[int]]                 # un-padded token rows
+    padded: torch.Tensor                     # int64 [B, S] as it arrived (echoed in output_ids)
+    max_new: int
+    stops: List[List[int]]
+    pad: int
+    done: Callable[[Optional[GenerateResult], Optional[BaseException]], None]
+    on_tokens: Optional[Callable[[int, List[int]], None]] = None   # (step, one token per row) for streaming
+    slots: List[int] = field(default_factory=list)
+    streamed: int = 0
+    t_submit: float = field(default_factory=time.perf_counter)
+    t_first: float = 0.0
+
+
+class ContinuousBatcher:
+    def __init__(self, engine: B200Engine, pad_token_id: int = 0, eos_token_ids: Sequence[int] = (),
+                 steps_per_poll: int = 4, max_prefill_tokens: Optional[int] = None):
+        self.engine = engine
+        self.pad = int(pad_token_id or 0)
+        self.eos = [int(e) for e in eos_token_ids]
+        self.steps_per_poll = max(1, int(steps_per_poll))
+        self.max_prefill_tokens = max_prefill_tokens
+        self._pending: Deque[_Request] = deque()
+        self._running: List[_Request] = []
+        self._cv = threading.Condition()
+        self._stop = False
+        self._thread: Optional[threading.Thread] = None
+        self.free_slots = engine.max_batch
+        # counters for the load tests / metrics
+        self.stats: Dict[str, float] = dict(admitted=0, finished=0, decode_steps=0, row_steps=0, prefill_calls=0)
+
+    # ------------------------------------------------------------------ lifecycle
+    def start(self) -> None:
+        self.engine.cb_begin(self.pad, self.eos)
+        self._thread = threading.Thread(target=self._loop, name="b200-continuous-batcher", daemon=True)
+        self._thread.start()
+
+    def stop(self) -> None:
+        with self._cv:
+            self._stop = True
+            self._cv.notify_all()
+        if self._thread is not None:
+            self._thread.join(timeout=30)
+            self._thread = None
+
+    # ------------------------------------------------------------------ submission
+    def submit_nowait(self, prompts: List[List[int]], padded: torch.Tensor, max_new_tokens: int,
+                      stop_sequences: Sequence[Sequence[int]], done, on_tokens=None) -> None:
+        stops = [list(map(int, s)) for s in stop_sequences if len(s)]
+        if len(prompts) > self.engine.max_batch:
+            raise ValueError(f"request of {len(prompts)} prompts exceeds max_batch {self.engine.max_batch}")
+        if len(stops) > 4 or any(len(s) > 8 for s in stops):
+            raise ValueError("continuous batching supports up to 4 stop sequences of up to 8 tokens each")
+        if any(len(p) < 1 or len(p) + int(max_new_tokens) > self.engine.max_seq_len for p in prompts) or int(max_new_tokens) < 1:
+            raise ValueError("prompt + max_new_tokens exceeds the engine's max_seq_len (or empty prompt / max_new_tokens < 1)")
+        req = _Request(prompts=[list(map(int, p)) for p in prompts], padded=padded, max_new=int(max_new_tokens),
+                       stops=stops, pad=self.pad, done=done, on_tokens=on_tokens)
+        with self._cv:
+            self._pending.append(req)
+            self._cv.notify_all()
+
+    async def submit(self, prompts: List[List[int]], padded: torch.Tensor, max_new_tokens: int,
+                     stop_sequences: Sequence[Sequence[int]] = (), on_tokens=None) -> GenerateResult:
+        loop = asyncio.get_running_loop()
+        fut: asyncio.Future = loop.create_future()
+
+        def done(result, err):
+            def _set():
+                if fut.cancelled():
+                    return
+                if err is not None:
+                    fut.set_exception(err)
+                else:
+                    fut.set_result(result)
+            loop.call_soon_threadsafe(_set)
+        self.submit_nowait(prompts, padded, max_new_tokens, stop_sequences, done, on_tokens)
+        return await fut
+
+    # ------------------------------------------------------------------ scheduler thread
+    def _admit(self) -> None:
+        """Move as many pending requests as fit (slots, prefill token budget) into ONE prefill call."""
+        batch: List[_Request] = []
+        budget = self.max_prefill_tokens
+        free = self.free_slots
+        with self._cv:
+            while self._pending:
+                r = self._pending[0]
+                need = len(r.prompts)
+                toks = sum(len(p) for p in r.prompts)
+                if need > free or (budget is not None and batch and toks > budget):
+                    break
+                self._pending.popleft()
+                batch.append(r)
+                free -= need
+                if budget is not None:
+                    budget -= toks
+        if not batch:
+            return
+        prompts = [p for r in batch for p in r.prompts]
+        max_new = [r.max_new for r in batch for _ in r.prompts]
+        stops = [r.stops for r in batch for _ in r.prompts]
+        try:
+            slots = self.engine.cb_admit(prompts, max_new, stops)
+        except BaseException as e:       # the whole admit call failed: fail these requests, keep serving
+            for r in batch:
+                r.done(None, e)
+            return
+        now = time.perf_counter()
+        i = 0
+        for r in batch:
+            r.slots = slots[i:i + len(r.prompts)]
+            r.t_first = now
+            i += len(r.prompts)
+            self._running.append(r)
+        self.free_slots -= len(prompts)
+        self.stats["admitted"] += len(batch)
+        self.stats["prefill_calls"] += 1
+
+    def _finish(self, r: _Request, n_out: int, stop: bool) -> None:
+        B, S = r.padded.shape
+        out = torch.full((B, S + n_out), r.pad, dtype=torch.int64)
+        out[:, :S] = r.padded
+        for b, sl in enumerate(r.slots):
+            toks = self.engine.cb_read(sl, 0, n_out)
+            out[b, S:S + len(toks)] = torch.tensor(toks, dtype=torch.int64)
+            self.engine.cb_release(sl)
+        self.free_slots += len(r.slots)
+        self.stats["finished"] += 1
+        res = GenerateResult(output_ids=out, stop_triggered=stop, num_generated=n_out, logits=None,
+                             prefill_ms=(r.t_first - r.t_submit) * 1e3, decode_ms=(time.perf_counter() - r.t_first) * 1e3,
+                             decode_steps=max(0, n_out - 1), kernel_launches=0)
+        r.done(res, None)
+
+    def _collect(self) -> None:
+        n_gen, fin, stop = self.engine.cb_poll()
+        still: List[_Request] = []
+        for r in self._running:
+            g = [n_gen[s] for s in r.slots]
+            stopped = [s for s in r.slots if stop[s]]
+            if stopped:
+                n_out = min(n_gen[s] for s in stopped)          # lockstep rows: everything after the match is dropped
+                end = True
+            else:
+                n_out = max(g)
+                end = all(fin[s] for s in r.slots)
+            if r.on_tokens is not None:
+                live = [n_gen[s] for s in r.slots if not fin[s]]      # finished rows read as pad from their end on
+                upto = n_out if end else min(min(live), n_out) if live else n_out
+                if upto > r.streamed:
+                    rows = [self.engine.cb_read(s, r.streamed, upto - r.streamed) for s in r.slots]
+                    for k in range(upto - r.streamed):
+                        r.on_tokens(r.streamed + k, [row[k] if k < len(row) else r.pad for row in rows])
+                    r.streamed = upto
+            if end:
+                self._finish(r, n_out, bool(stopped))
+            else:
+                still.append(r)
+        self._running = still
+
+    def _loop(self) -> None:
+        try:
+            while True:
+                with self._cv:
+                    while not self._stop and not self._pending and not self._running:
+                        self._cv.wait()
+                    if self._stop:
+                        break
+                if self._pending and self.free_slots > 0:
+                    self._admit()
+                if self._running:
+                    rows = sum(len(r.slots) for r in self._running)
+                    self.engine.cb_step(self.steps_per_poll)
+                    self.stats["decode_steps"] += self.steps_per_poll
+                    self.stats["row_steps"] += self.steps_per_poll * rows
+                    self._collect()
+        except BaseException as e:   # engine failure: fail everything that is waiting
+            with self._cv:
+                waiting = list(self._pending) + self._running
+                self._pending.clear()
+                self._running = []
+            for r in waiting:
+                r.done(None, e)
+        finally:
+            try:
+                self.engine.cb_end()
+            except Exception:
+                pass

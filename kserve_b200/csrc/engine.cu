@@ -169,6 +169,16 @@ struct b200_engine {
   P2P p2p{};
   b200_timing_t timing{};
   int launches = 0;
+  // continuous batching (cb.cuh): per-slot sequence state + the compact list of running slots
+  bool cb_on = false;
+  CbState cb{};
+  std::vector<int> cb_active;        // running slots, in row order of the decode step
+  std::vector<char> cb_used;         // slot occupied (running or finished-but-not-released)
+  int32_t* d_cb_row_slot = nullptr;  // [max_batch]
+  int32_t* d_cb_rec = nullptr;       // [max_batch][kCbInitInts]
+  int32_t* h_cb = nullptr;           // pinned: init records / poll results / token reads
+  bool cb_rows_dirty = false;
+  int cb_num_eos = 0;
 };
 
 namespace b200 {
@@ -461,7 +471,7 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
 }
 
 // LM head on `rows` (B x H, already final-normed) -> logits -> per-rank argmax candidates -> step update
-static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int B) {
+static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int B, const int32_t* cb_row_slot = nullptr) {
   cudaStream_t s = e->stream;
   int rc;
   GemmArgs a{e->lm_head, e->Vl, rows_xn, rows_cap, e->Vl, B, e->H, EPI_T_STORE, pick_block_n(B), 1,
@@ -481,6 +491,11 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
     B200_NCCL_OK(n.AllGather(e->cand_val, e->cand_val_all, B, Nccl::kFloat, e->comm, s));
     B200_NCCL_OK(n.AllGather(e->cand_idx, e->cand_idx_all, B, Nccl::kInt32, e->comm, s));
     cv = e->cand_val_all; ci = e->cand_idx_all; ranks = e->cfg.tp_size;
+  }
+  if (cb_row_slot) {   // continuous batching: per-slot bookkeeping
+    B200_CUDA_OK(launch_k(cb_step_kernel, dim3(1), dim3(128), 0, s, cv, ci, ranks, B, cb_row_slot, e->cb, (const int32_t*)e->d_eos, e->cb_num_eos));
+    e->launches++;
+    return 0;
   }
   StepParams sp{};
   sp.cand_val = cv; sp.cand_idx = ci; sp.ranks = ranks; sp.B = B;
@@ -545,6 +560,7 @@ static int decode_step(b200_engine* e, bool use_graph) {
 // (un-padded) sequence lengths; S is the padded prompt width (0 for ragged batcher input).
 static int stage_common(b200_engine* e, int B, int S, const std::vector<int>& lens, const b200_gen_params_t* gp) {
   B200_REQUIRE(e->finalized, "weights not finalized");
+  B200_REQUIRE(!e->cb_on, "engine is in continuous-batching mode (b200_cb_end first)");
   B200_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch size out of range");
   B200_REQUIRE(gp->max_new_tokens >= 1, "max_new_tokens must be >= 1");
   B200_REQUIRE(gp->num_eos <= 16 && gp->num_stop <= 16, "too many eos / stop sequences");
@@ -676,6 +692,150 @@ static int fetch_result(b200_engine* e, int64_t* out_ids, int32_t* out_len, int3
   }
   *out_len = st.S + Tn;
   if (stop_triggered) *stop_triggered = e->h_state->stop_triggered;
+  return 0;
+}
+
+
+// ---- continuous batching ---------------------------------------------------------------------------
+static int cb_alloc(b200_engine* e) {
+  if (e->cb.len) return 0;
+  const size_t nb = (size_t)e->cfg.max_batch;
+  int rc;
+  if ((rc = dmalloc(&e->cb.len, nb))) return rc;
+  if ((rc = dmalloc(&e->cb.n_gen, nb))) return rc;
+  if ((rc = dmalloc(&e->cb.max_new, nb))) return rc;
+  if ((rc = dmalloc(&e->cb.finished, nb))) return rc;
+  if ((rc = dmalloc(&e->cb.stop_hit, nb))) return rc;
+  if ((rc = dmalloc(&e->cb.next_tok, nb))) return rc;
+  if ((rc = dmalloc(&e->cb.stop_len, nb * kCbMaxStop))) return rc;
+  if ((rc = dmalloc(&e->cb.stop_tok, nb * kCbMaxStop * kCbMaxStopLen))) return rc;
+  if ((rc = dmalloc(&e->d_cb_row_slot, nb))) return rc;
+  if ((rc = dmalloc(&e->d_cb_rec, nb * kCbInitInts))) return rc;
+  e->cb.out = e->d_out_tokens; e->cb.out_ld = e->out_ld;
+  const size_t host_ints = std::max(nb * kCbInitInts, std::max((size_t)e->out_ld, 4 * nb));
+  B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_cb), host_ints * 4));
+  return 0;
+}
+
+static int cb_decode_enqueue(b200_engine* e, int R) {
+  int rc;
+  B200_CUDA_OK(launch_k(cb_gather_kernel, dim3(1), dim3(64), 0, e->stream, (const int32_t*)e->d_cb_row_slot, R, e->cb, e->d_next_tok,
+                        e->d_seq_slot, e->d_dec_pos));
+  e->launches++;
+  if ((rc = forward_layers(e, R, R, 0, true))) return rc;
+  return head_and_step(e, e->xn, e->cap_T, R, e->d_cb_row_slot);
+}
+
+// one decode iteration over the running slots through a CUDA graph keyed by the row count
+static int cb_decode_step(b200_engine* e) {
+  const int R = (int)e->cb_active.size();
+  if (R == 0) return 0;
+  if (e->cb_rows_dirty) {
+    for (int r = 0; r < R; ++r) e->h_cb[r] = e->cb_active[r];
+    B200_CUDA_OK(cudaMemcpyAsync(e->d_cb_row_slot, e->h_cb, (size_t)R * 4, cudaMemcpyHostToDevice, e->stream));
+    B200_CUDA_OK(cudaStreamSynchronize(e->stream));   // h_cb is reused; membership changes are rare
+    e->cb_rows_dirty = false;
+  }
+  static const bool eager = getenv("B200_NO_GRAPH") != nullptr;
+  if (eager) return cb_decode_enqueue(e, R);
+  const int key = R | (1 << 20) | (e->cb_num_eos << 9);
+  auto it = e->graphs.find(key);
+  if (it == e->graphs.end()) {
+    const int before = e->launches;
+    int rc = cb_decode_enqueue(e, R);   // eager first: tensor maps / function attributes outside of capture
+    if (rc) return rc;
+    const int per_step = e->launches - before;
+    B200_CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    rc = cb_decode_enqueue(e, R);
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+    e->launches -= per_step;
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    B200_CUDA_OK(ce);
+    cudaGraphExec_t ge = nullptr;
+    B200_CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    e->graphs[key] = ge;
+    e->graph_nodes[key] = per_step;
+    return 0;
+  }
+  B200_CUDA_OK(cudaGraphLaunch(it->second, e->stream));
+  e->launches += e->graph_nodes[key];
+  return 0;
+}
+
+// prefill `n` new sequences into free slots and produce their first token
+static int cb_admit(b200_engine* e, int n, const int64_t* const* rows, const int32_t* lens, const int32_t* max_new,
+                    const int32_t* stop_count, const int32_t* stop_offsets, const int64_t* stop_tokens, int32_t* slots_out) {
+  B200_REQUIRE(e->cb_on, "b200_cb_begin was not called");
+  B200_REQUIRE(n >= 1, "nothing to admit");
+  int free_slots = 0;
+  for (char u : e->cb_used) free_slots += u ? 0 : 1;
+  B200_REQUIRE(n <= free_slots, "not enough free slots");
+  int T = 0, max_len = 0;
+  for (int i = 0; i < n; ++i) {
+    B200_REQUIRE(lens[i] >= 1 && max_new[i] >= 1, "empty sequence / max_new < 1");
+    B200_REQUIRE(lens[i] + max_new[i] <= e->cfg.max_seq_len && lens[i] + max_new[i] <= e->cfg.max_position, "prompt + max_new exceeds max_seq_len");
+    T += lens[i];
+    max_len = std::max(max_len, lens[i]);
+  }
+  B200_REQUIRE(T <= e->cap_T, "packed prompt tokens exceed max_prefill_tokens");
+  cudaStream_t s = e->stream;
+  // slots + init records
+  std::vector<int> slots;
+  for (int sl = 0; sl < (int)e->cb_used.size() && (int)slots.size() < n; ++sl)
+    if (!e->cb_used[sl]) slots.push_back(sl);
+  int so = 0;   // running index into stop_offsets
+  for (int i = 0; i < n; ++i) {
+    int32_t* r = e->h_cb + (size_t)i * kCbInitInts;
+    for (int j = 0; j < kCbInitInts; ++j) r[j] = 0;
+    r[0] = slots[i]; r[1] = lens[i]; r[2] = max_new[i];
+    const int ns = stop_count ? stop_count[i] : 0;
+    B200_REQUIRE(ns <= kCbMaxStop, "too many stop sequences for one sequence");
+    r[3] = ns;
+    for (int j = 0; j < ns; ++j, ++so) {
+      const int o = stop_offsets[so], len = stop_offsets[so + 1] - o;
+      B200_REQUIRE(len >= 0 && len <= kCbMaxStopLen, "stop sequence too long");
+      r[4 + j] = len;
+      for (int k = 0; k < len; ++k) r[4 + kCbMaxStop + j * kCbMaxStopLen + k] = (int32_t)stop_tokens[o + k];
+    }
+  }
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_cb_rec, e->h_cb, (size_t)n * kCbInitInts * 4, cudaMemcpyHostToDevice, s));
+  cb_init_kernel<<<n, 64, 0, s>>>(e->d_cb_rec, n, e->cb);
+  B200_CUDA_OK(cudaGetLastError());
+  B200_CUDA_OK(cudaStreamSynchronize(s));   // h_cb is reused below
+  // packed prompt layout, built on the host (3 ints per prompt token)
+  int32_t* flat = e->h_stage;   // tok | tok_seq | tok_pos | cu | seq_slot | last_rows
+  int32_t *h_tok = flat, *h_seq = flat + T, *h_pos = flat + 2 * T, *h_cu = flat + 3 * T, *h_slot = h_cu + n + 1, *h_last = h_slot + n;
+  B200_REQUIRE((size_t)(3 * T + 3 * n + 1) <= e->h_stage_elems, "prompt staging buffer too small");
+  int t = 0;
+  for (int i = 0; i < n; ++i) {
+    h_cu[i] = t;
+    for (int k = 0; k < lens[i]; ++k, ++t) { h_tok[t] = (int32_t)rows[i][k]; h_seq[t] = slots[i]; h_pos[t] = k; }
+    h_slot[i] = slots[i];
+    h_last[i] = t - 1;
+  }
+  h_cu[n] = t;
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_tok, h_tok, (size_t)T * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_tok_seq, h_seq, (size_t)T * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_tok_pos, h_pos, (size_t)T * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_cu, h_cu, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_seq_slot, h_slot, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_last_rows, h_last, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_cb_rec, h_slot, (size_t)n * 4, cudaMemcpyHostToDevice, s));   // row -> slot of this prefill
+  int rc;
+  e->st.lens.assign(lens, lens + n);
+  if ((rc = forward_layers(e, T, n, max_len, false))) return rc;
+  B200_CUDA_OK(launch_k(gather_rows_kernel, dim3(n), dim3(128), 0, s, (const bf16*)e->xn, (const int32_t*)e->d_last_rows, e->xl, e->H));
+  e->launches++;
+  if ((rc = head_and_step(e, e->xl, e->cfg.max_batch, n, e->d_cb_rec))) return rc;
+  B200_CUDA_OK(cudaStreamSynchronize(s));   // h_stage is reused by the next admit
+  for (int i = 0; i < n; ++i) {
+    e->cb_used[slots[i]] = 1;
+    e->cb_active.push_back(slots[i]);
+    slots_out[i] = slots[i];
+  }
+  e->cb_rows_dirty = true;
   return 0;
 }
 
@@ -1283,6 +1443,101 @@ static int kv_swap(b200_engine_t* e, int32_t slot, bool out, int scrub) {
 }
 int b200_kv_swap_out(b200_engine_t* e, int32_t slot, int32_t scrub) { B200_REQUIRE(e, "null engine"); return kv_swap(e, slot, true, scrub); }
 int b200_kv_swap_in(b200_engine_t* e, int32_t slot) { B200_REQUIRE(e, "null engine"); return kv_swap(e, slot, false, 0); }
+
+
+// ---- continuous batching (include/kserve_b200.h) ---------------------------------------------------
+int b200_cb_begin(b200_engine_t* e, int64_t pad_token_id, const int64_t* eos_token_ids, int32_t num_eos) {
+  B200_REQUIRE(e, "null engine");
+  B200_REQUIRE(e->finalized, "weights not finalized");
+  B200_REQUIRE(e->cfg.tp_size == 1, "continuous batching runs on one GPU per engine (tensor-parallel ranks would need a command broadcast)");
+  B200_REQUIRE(num_eos >= 0 && num_eos <= 16, "too many eos tokens");
+  B200_REQUIRE((long long)e->cfg.max_batch * e->max_pages <= e->num_pages, "KV page pool smaller than max_batch * pages per sequence");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  int rc = cb_alloc(e);
+  if (rc) return rc;
+  (void)pad_token_id;
+  std::vector<int32_t> tmp(std::max(1, num_eos));
+  for (int i = 0; i < num_eos; ++i) tmp[i] = (int32_t)eos_token_ids[i];
+  if (num_eos) B200_CUDA_OK(cudaMemcpy(e->d_eos, tmp.data(), (size_t)num_eos * 4, cudaMemcpyHostToDevice));
+  e->cb_num_eos = num_eos;
+  for (int sl = 0; sl < e->cfg.max_batch; ++sl)
+    for (int i = 0; i < e->max_pages; ++i) e->h_page_table[(size_t)sl * e->max_pages + i] = sl * e->max_pages + i;
+  B200_CUDA_OK(cudaMemcpy(e->d_page_table, e->h_page_table.data(), e->h_page_table.size() * 4, cudaMemcpyHostToDevice));
+  e->cb_used.assign(e->cfg.max_batch, 0);
+  e->cb_active.clear();
+  e->cb_rows_dirty = true;
+  e->cb_on = true;
+  return 0;
+}
+
+int b200_cb_end(b200_engine_t* e) {
+  B200_REQUIRE(e, "null engine");
+  e->cb_on = false;
+  e->cb_active.clear();
+  return 0;
+}
+
+int b200_cb_admit(b200_engine_t* e, int32_t n, const int64_t* const* rows, const int32_t* lens, const int32_t* max_new,
+                  const int32_t* stop_count, const int32_t* stop_offsets, const int64_t* stop_tokens, int32_t* slots_out) {
+  B200_REQUIRE(e && rows && lens && max_new && slots_out, "null argument");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  return cb_admit(e, n, rows, lens, max_new, stop_count, stop_offsets, stop_tokens, slots_out);
+}
+
+int b200_cb_step(b200_engine_t* e, int32_t n_steps) {
+  B200_REQUIRE(e && e->cb_on, "b200_cb_begin was not called");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  for (int i = 0; i < n_steps; ++i) {
+    int rc = cb_decode_step(e);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int b200_cb_poll(b200_engine_t* e, int32_t* n_gen, int32_t* finished, int32_t* stop_hit) {
+  B200_REQUIRE(e && e->cb_on && n_gen && finished, "null argument / not in continuous-batching mode");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  const size_t nb = (size_t)e->cfg.max_batch;
+  cudaStream_t s = e->stream;
+  B200_CUDA_OK(cudaMemcpyAsync(e->h_cb, e->cb.n_gen, nb * 4, cudaMemcpyDeviceToHost, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->h_cb + nb, e->cb.finished, nb * 4, cudaMemcpyDeviceToHost, s));
+  B200_CUDA_OK(cudaMemcpyAsync(e->h_cb + 2 * nb, e->cb.stop_hit, nb * 4, cudaMemcpyDeviceToHost, s));
+  B200_CUDA_OK(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < nb; ++i) {
+    const bool used = e->cb_used[i] != 0;
+    n_gen[i] = used ? e->h_cb[i] : 0;
+    finished[i] = used ? e->h_cb[nb + i] : 0;
+    if (stop_hit) stop_hit[i] = used ? e->h_cb[2 * nb + i] : 0;
+  }
+  return 0;
+}
+
+int b200_cb_read(b200_engine_t* e, int32_t slot, int32_t first, int64_t* out, int32_t cap, int32_t* n_out) {
+  B200_REQUIRE(e && e->cb_on && out && n_out, "null argument / not in continuous-batching mode");
+  B200_REQUIRE(slot >= 0 && slot < e->cfg.max_batch && e->cb_used[slot], "slot is not in use");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = e->stream;
+  int32_t ng = 0;
+  B200_CUDA_OK(cudaMemcpyAsync(&ng, e->cb.n_gen + slot, 4, cudaMemcpyDeviceToHost, s));
+  B200_CUDA_OK(cudaStreamSynchronize(s));
+  const int n = std::max(0, std::min(ng - first, cap));
+  if (n > 0) {
+    B200_CUDA_OK(cudaMemcpyAsync(e->h_cb, e->cb.out + (size_t)slot * e->out_ld + first, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i) out[i] = e->h_cb[i];
+  }
+  *n_out = n;
+  return 0;
+}
+
+int b200_cb_release(b200_engine_t* e, int32_t slot) {
+  B200_REQUIRE(e && e->cb_on, "not in continuous-batching mode");
+  B200_REQUIRE(slot >= 0 && slot < e->cfg.max_batch && e->cb_used[slot], "slot is not in use");
+  e->cb_used[slot] = 0;
+  auto it = std::find(e->cb_active.begin(), e->cb_active.end(), (int)slot);
+  if (it != e->cb_active.end()) { e->cb_active.erase(it); e->cb_rows_dirty = true; }
+  return 0;
+}
 
 // ---- peer-memory exchange setup (tensor parallel) --------------------------------------------------
 int b200_engine_ipc_export(b200_engine_t* e, void* handle64) {

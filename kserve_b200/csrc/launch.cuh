@@ -13,6 +13,7 @@
 #include "ops.cuh"
 #include "p2p.cuh"
 #include "moe.cuh"
+#include "cb.cuh"
 
 namespace b200 {
 

@@ -221,6 +221,56 @@ class B200Engine:
     def kv_swap_in(self, slot: int) -> None:
         _lib.check(self.lib.b200_kv_swap_in(self.h, slot), "b200_kv_swap_in")
 
+    # ------------------------------------------------------------------ continuous batching (b200_cb_*)
+    def cb_begin(self, pad_token_id: int = 0, eos_token_ids: Sequence[int] = ()) -> None:
+        eos = [int(x) for x in eos_token_ids]
+        arr = (C.c_int64 * max(1, len(eos)))(*eos)
+        _lib.check(self.lib.b200_cb_begin(self.h, int(pad_token_id or 0), arr, len(eos)), "b200_cb_begin")
+        self._cb_slots = self.max_batch
+
+    def cb_admit(self, prompts: Sequence[Sequence[int]], max_new_tokens: Sequence[int],
+                 stop_sequences: Optional[Sequence[Sequence[Sequence[int]]]] = None) -> List[int]:
+        """Prefill `prompts` into free slots; returns the slot of each prompt."""
+        n = len(prompts)
+        rows = [(C.c_int64 * len(p))(*[int(t) for t in p]) for p in prompts]
+        ptrs = (C.POINTER(C.c_int64) * n)(*[C.cast(r, C.POINTER(C.c_int64)) for r in rows])
+        lens = (C.c_int32 * n)(*[len(p) for p in prompts])
+        mx = (C.c_int32 * n)(*[int(m) for m in max_new_tokens])
+        stops = [[list(map(int, q)) for q in (ss or []) if len(q)] for ss in (stop_sequences or [[]] * n)]
+        cnt = (C.c_int32 * n)(*[len(ss) for ss in stops])
+        flat, offs = [], [0]
+        for ss in stops:
+            for q in ss:
+                flat += q
+                offs.append(len(flat))
+        offs_a = (C.c_int32 * len(offs))(*offs)
+        flat_a = (C.c_int64 * max(1, len(flat)))(*flat)
+        slots = (C.c_int32 * n)()
+        _lib.check(self.lib.b200_cb_admit(self.h, n, ptrs, lens, mx, cnt, offs_a, flat_a, slots), "b200_cb_admit")
+        return list(slots)
+
+    def cb_step(self, n_steps: int = 1) -> None:
+        _lib.check(self.lib.b200_cb_step(self.h, n_steps), "b200_cb_step")
+
+    def cb_poll(self):
+        """-> (n_gen, finished, stop_hit), each a list over the slots."""
+        nb = self.max_batch
+        a, b, c = (C.c_int32 * nb)(), (C.c_int32 * nb)(), (C.c_int32 * nb)()
+        _lib.check(self.lib.b200_cb_poll(self.h, a, b, c), "b200_cb_poll")
+        return list(a), list(b), list(c)
+
+    def cb_read(self, slot: int, first: int = 0, cap: int = 4096) -> List[int]:
+        out = (C.c_int64 * cap)()
+        n = C.c_int32(0)
+        _lib.check(self.lib.b200_cb_read(self.h, slot, first, out, cap, C.byref(n)), "b200_cb_read")
+        return list(out[: n.value])
+
+    def cb_release(self, slot: int) -> None:
+        _lib.check(self.lib.b200_cb_release(self.h, slot), "b200_cb_release")
+
+    def cb_end(self) -> None:
+        _lib.check(self.lib.b200_cb_end(self.h), "b200_cb_end")
+
     def fetch_staged(self) -> torch.Tensor:
         B, S, T = self._staged_shape
         out = torch.empty((B, S + T), dtype=torch.int64)

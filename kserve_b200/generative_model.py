@@ -116,7 +116,7 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                  tokenizer=None, pad_token_id: Optional[int] = None, max_model_len: Optional[int] = None,
                  max_batch: int = 32, device: int = 0, tensor_parallel_size: int = 1, tp_rank: int = 0,
                  nccl_id: Optional[bytes] = None, system_fingerprint: Optional[str] = None,
-                 request_logger=None):
+                 request_logger=None, continuous_batching: bool = False):
         Model.__init__(self, model_name)
         self.ready = False
         self.model_id_or_path = model_id_or_path
@@ -135,6 +135,9 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         self._request_queue: "queue.Queue" = queue.Queue()
         self._thread: Optional[Thread] = None
         self.eos_token_ids: List[int] = []
+        # iteration-level batching instead of the reference's one-request-at-a-time loop (continuous.py)
+        self.continuous_batching = bool(continuous_batching) and tensor_parallel_size == 1
+        self._cb = None
 
     # ------------------------------------------------------------------ load / stop (generative_model.py:203-285)
     def load(self) -> bool:
@@ -182,6 +185,10 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         self.vocab_rows = vocab_rows
         self._thread = Thread(target=self._process_requests, daemon=True)   # :267-269
         self._thread.start()
+        if self.continuous_batching:
+            from .continuous import ContinuousBatcher
+            self._cb = ContinuousBatcher(self._engine, self._pad_token_id or 0, self.eos_token_ids)
+            self._cb.start()
         self.ready = True
         return self.ready
 
@@ -189,6 +196,9 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         if self.tp_size > 1 and self.tp_rank == 0 and self._engine is not None:
             from .tp import leader_call
             leader_call("stop", (), {})
+        if self._cb is not None:
+            self._cb.stop()
+            self._cb = None
         self._request_queue.put(None)    # :273-277
         if self._thread is not None:
             self._thread.join(timeout=5)
@@ -233,6 +243,28 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
             from .tp import leader_call
             leader_call("generate", (ids, mask), kw)
         return self._engine.generate(ids, mask, streamer=streamer, **kw)
+
+    @staticmethod
+    def _unpadded_rows(ids: torch.Tensor, mask: Optional[torch.Tensor]) -> List[List[int]]:
+        """left-padded [B, S] (+ mask) -> the real token rows (what the packed engine layout holds)"""
+        if mask is None:
+            return [row.tolist() for row in ids]
+        rows = []
+        for b in range(ids.shape[0]):
+            nz = mask[b].nonzero()
+            first = int(nz[0]) if len(nz) else ids.shape[1] - 1
+            rows.append(ids[b, first:].tolist())
+        return rows
+
+    async def _agenerate(self, ids, mask, *, max_new_tokens, pad_token_id, eos_token_ids, stop_sequences=()) -> GenerateResult:
+        """One request through the engine: the continuous batcher when enabled, else the serial generation thread."""
+        if self._cb is not None:
+            try:
+                return await self._cb.submit(self._unpadded_rows(ids, mask), ids, max_new_tokens, stop_sequences)
+            except ValueError as e:
+                raise OpenAIError(str(e))
+        return await self._submit(lambda: self._generate(ids, mask, max_new_tokens=max_new_tokens, pad_token_id=pad_token_id,
+                                                         eos_token_ids=eos_token_ids, stop_sequences=stop_sequences))
 
     # ------------------------------------------------------------------ request validation (:376-402)
     def validate_supported_completion_params(self, request: CompletionRequest):
@@ -333,7 +365,34 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                     put(e)
                 put(None)
                 return None
-            self._request_queue.put((run_stream, lambda r, e: None))
+            if self._cb is not None:
+                detok = IncrementalDetokenizer(self._tokenizer)
+                if echo:
+                    piece = detok.put(self._unpadded_rows(ids, mask)[0])
+                    if piece != "":
+                        put(piece)
+
+                def on_tokens(step, toks):
+                    piece = detok.put([int(toks[0])])
+                    if piece != "":
+                        put(piece)
+
+                def cb_done(res, err):
+                    if err is not None:
+                        put(err)
+                    else:
+                        stop_state["triggered"] = res.stop_triggered
+                        self._observe(res, B)
+                        piece = detok.end()
+                        if piece != "":
+                            put(piece)
+                    put(None)
+                try:
+                    self._cb.submit_nowait(self._unpadded_rows(ids, mask), ids, request.max_tokens, stop_sequences, cb_done, on_tokens)
+                except ValueError as e:
+                    raise OpenAIError(str(e))
+            else:
+                self._request_queue.put((run_stream, lambda r, e: None))
             completion = CompletionStreamer(request=request, generate_queue=out_q, stop_state=stop_state,
                                             system_fingerprint=self.system_fingerprint)
 
@@ -343,7 +402,7 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                 yield "data: [DONE]\n\n"
             return stream_results()
 
-        r: GenerateResult = await self._submit(lambda: self._generate(ids, mask, **common))
+        r: GenerateResult = await self._agenerate(ids, mask, **common)
         self._observe(r, B)
         output_start = 0 if echo else S                        # :324-327
         stats.num_generation_tokens = r.num_generated * B      # :329-335 (every row counts the same length)
@@ -450,8 +509,8 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
             raise InvalidInput(f"batch of {B} exceeds this engine's max batch {self.max_batch}")
         if S + max_tokens > self.max_length:
             raise InvalidInput(f"prompt ({S}) + max_tokens ({max_tokens}) exceeds the model's maximum context length {self.max_length}")
-        r: GenerateResult = await self._submit(lambda: self._generate(
-            ids, mask, max_new_tokens=max_tokens, pad_token_id=self._pad_token_id, eos_token_ids=self.eos_token_ids))
+        r: GenerateResult = await self._agenerate(ids, mask, max_new_tokens=max_tokens, pad_token_id=self._pad_token_id,
+                                                  eos_token_ids=self.eos_token_ids)
         self._observe(r, B)
         gen = r.output_ids[:, S:]
         texts = self._tokenizer.batch_decode(gen, skip_special_tokens=True) if self._tokenizer is not None else None

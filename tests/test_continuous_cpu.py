@@ -1,0 +1,120 @@
+"""Host logic of the continuous batcher against a scripted engine (no GPU): admission under slot pressure,
+lockstep rows, batch-wide stop truncation, EOS padding, streaming order, slot accounting."""
+import asyncio
+
+import torch
+
+from kserve_b200.continuous import ContinuousBatcher
+
+
+class ScriptedEngine:
+    """cb_* surface of B200Engine; sequence i emits script[i][k] as its k-th token."""
+    def __init__(self, max_batch, scripts, eos=()):
+        self.max_batch, self.max_seq_len = max_batch, 4096
+        self.scripts = scripts            # prompt tuple -> token list
+        self.eos = set(eos)
+        self.slots = {}
+        self.calls = []
+
+    def cb_begin(self, pad, eos):
+        self.eos = set(eos)
+
+    def cb_end(self):
+        pass
+
+    def _emit(self, st):
+        if st["fin"]:
+            return
+        tok = st["script"][len(st["out"])]
+        st["out"].append(tok)
+        if tok in self.eos or len(st["out"]) >= st["max_new"]:
+            st["fin"] = True
+        for q in st["stops"]:
+            if len(q) <= len(st["out"]) and st["out"][-len(q):] == q:
+                st["fin"] = st["stop"] = True
+
+    def cb_admit(self, prompts, max_new, stops):
+        free = [s for s in range(self.max_batch) if s not in self.slots]
+        assert len(prompts) <= len(free)
+        out = []
+        for p, m, ss in zip(prompts, max_new, stops):
+            s = free.pop(0)
+            self.slots[s] = dict(script=self.scripts[tuple(p)], out=[], max_new=m, stops=[list(q) for q in ss], fin=False, stop=False)
+            self._emit(self.slots[s])
+            out.append(s)
+        self.calls.append(("admit", len(prompts)))
+        return out
+
+    def cb_step(self, n):
+        for _ in range(n):
+            for st in self.slots.values():
+                self._emit(st)
+        self.calls.append(("step", n, len(self.slots)))
+
+    def cb_poll(self):
+        g = [len(self.slots[s]["out"]) if s in self.slots else 0 for s in range(self.max_batch)]
+        f = [int(self.slots[s]["fin"]) if s in self.slots else 0 for s in range(self.max_batch)]
+        h = [int(self.slots[s]["stop"]) if s in self.slots else 0 for s in range(self.max_batch)]
+        return g, f, h
+
+    def cb_read(self, slot, first=0, cap=4096):
+        return self.slots[slot]["out"][first:first + cap]
+
+    def cb_release(self, slot):
+        del self.slots[slot]
+
+
+def _run(cb, coro):
+    cb.start()
+    try:
+        return asyncio.run(coro)
+    finally:
+        cb.stop()
+
+
+def test_requests_queue_for_slots_and_all_complete():
+    scripts = {(i,): [100 * i + k for k in range(40)] for i in range(6)}
+    eng = ScriptedEngine(2, scripts)
+    cb = ContinuousBatcher(eng, pad_token_id=0, steps_per_poll=3)
+
+    async def main():
+        return await asyncio.gather(*[cb.submit([[i]], torch.tensor([[i]]), 5 + i) for i in range(6)])
+    res = _run(cb, main())
+    for i, r in enumerate(res):
+        assert r.num_generated == 5 + i and not r.stop_triggered
+        assert r.output_ids.tolist() == [[i] + scripts[(i,)][:5 + i]]
+    assert cb.free_slots == 2 and not eng.slots and cb.stats["finished"] == 6
+    assert max(c[2] for c in eng.calls if c[0] == "step") <= 2          # never more rows than slots
+
+
+def test_batchwide_stop_truncates_every_row_and_eos_pads():
+    scripts = {(1,): [5, 6, 7, 8, 9, 10, 11, 12], (2,): [20, 21, 22, 23, 24, 25, 26, 27], (3,): [30, 99, 31, 32, 33, 34, 35, 36],
+               (4,): [40, 41, 42, 43, 44, 45, 46, 47]}
+    eng = ScriptedEngine(8, scripts)
+    cb = ContinuousBatcher(eng, pad_token_id=0, eos_token_ids=[99], steps_per_poll=4)
+    seen = []
+
+    async def main():
+        a = cb.submit([[1], [2]], torch.tensor([[1], [2]]), 8, [[7, 8]])             # stop matches in row 0 at step 4
+        b = cb.submit([[3], [4]], torch.tensor([[3], [4]]), 6, on_tokens=lambda s, t: seen.append((s, list(t))))   # row 0 hits EOS at step 2
+        return await asyncio.gather(a, b)
+    ra, rb = _run(cb, main())
+    assert ra.stop_triggered and ra.num_generated == 4
+    assert ra.output_ids.tolist() == [[1, 5, 6, 7, 8], [2, 20, 21, 22, 23]]
+    assert not rb.stop_triggered and rb.num_generated == 6
+    assert rb.output_ids.tolist() == [[3, 30, 99, 0, 0, 0, 0], [4, 40, 41, 42, 43, 44, 45]]
+    assert [s for s, _ in seen] == list(range(6))
+    assert [t for _, t in seen] == [[30, 40], [99, 41], [0, 42], [0, 43], [0, 44], [0, 45]]
+
+
+def test_invalid_requests_are_rejected_up_front():
+    eng = ScriptedEngine(2, {})
+    cb = ContinuousBatcher(eng)
+    for bad in (dict(prompts=[[1]] * 3, padded=torch.zeros(3, 1), max_new_tokens=4, stop_sequences=[]),
+                dict(prompts=[[1]], padded=torch.zeros(1, 1), max_new_tokens=5000, stop_sequences=[]),
+                dict(prompts=[[1]], padded=torch.zeros(1, 1), max_new_tokens=4, stop_sequences=[[1] * 9])):
+        try:
+            cb.submit_nowait(done=lambda r, e: None, **bad)
+            raise AssertionError("accepted an invalid request")
+        except ValueError:
+            pass
