@@ -102,13 +102,55 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's own CPU implementation of the path
 # ---------------------------------------------------------------------------------------------------
+def usable_cores() -> int:
+    """CPUs this process may actually run on: affinity mask, capped by the cgroup CPU quota (a container that reports
+    128 logical CPUs but is throttled to a few of them makes a 128-thread bf16 matmul ~60x slower, seen on a GPU box)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p_ = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // p_))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
+def pick_cpu_threads() -> int:
+    """Thread count for the CPU arm: the fastest of a few candidates on a decode-shaped bf16 GEMV (2 s probe)."""
+    import torch
+    cap = usable_cores()
+    cands = sorted({min(cap, c) for c in (64, 32, 16, 8)}, reverse=True)
+    w = torch.randn(14336, 4096).to(torch.bfloat16)
+    x = torch.randn(1, 4096).to(torch.bfloat16)
+    best, best_t = cands[-1], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.nn.functional.linear(x, w)
+        t0 = time.perf_counter()
+        for _ in range(8):
+            torch.nn.functional.linear(x, w)
+        dt = time.perf_counter() - t0
+        if dt < best_t * 0.9:       # the larger count stays unless a smaller one is clearly faster
+            best, best_t = c, dt
+        if dt > 2.0:                # badly oversubscribed: do not try anything larger again
+            continue
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_reference(cfg, sample_B, sample_S, sample_T, steps, warmup):
     """HF-transformers CPU backend (what huggingfaceserver runs with --backend huggingface on CPU), through the
     oracle's restated create_completion; random weights of the architecture (values do not affect timing)."""
     import torch
     from oracle.hf_oracle import OracleGenerativeModel
     from transformers import LlamaConfig, LlamaForCausalLM
-    torch.set_num_threads(os.cpu_count())
+    pick_cpu_threads()
     hf_cfg = LlamaConfig(**cfg, tie_word_embeddings=False, eos_token_id=None, bos_token_id=None, pad_token_id=None)
     with torch.device("meta"):
         model = LlamaForCausalLM(hf_cfg)
@@ -131,6 +173,11 @@ def cpu_reference(cfg, sample_B, sample_S, sample_T, steps, warmup):
     model.eval()
     orc = OracleGenerativeModel(model, pad_token_id=cfg["vocab_size"] - 1, max_length=cfg["max_position_embeddings"])
     ids = torch.randint(3, 128000, (sample_B, sample_S), generator=g).tolist()
+    # calibration pass (prompt + 1 token; also the warm-up): the sample is bounded to ~30 s of CPU work per step
+    t0 = time.perf_counter()
+    orc.create_completion(ids, max_tokens=1, temperature=0)
+    t_cal = time.perf_counter() - t0
+    sample_T = max(2, min(sample_T, int(30.0 / max(t_cal, 1e-3))))
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()

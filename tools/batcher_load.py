@@ -54,6 +54,49 @@ def main():
     lat, ttft = [], []
     done_tokens = 0
     stop_at = None
+    mode = os.environ.get("MODE", "batcher")
+    if mode == "continuous":
+        # the same 512 closed-loop clients, served by the iteration-level scheduler
+        from kserve_b200.continuous import ContinuousBatcher
+        cb = ContinuousBatcher(eng, pad_token_id=cfg["vocab_size"] - 1, eos_token_ids=[], steps_per_poll=int(os.environ.get("STEPS_PER_POLL", "4")))
+        cb.start()
+
+        async def cclient(i):
+            nonlocal done_tokens
+            rng = random.Random(i)
+            while time.perf_counter() < stop_at:
+                n = rng.randint(512, 1024)
+                row = [rng.randint(3, 127999) for _ in range(n)]
+                first = []
+                t0 = time.perf_counter()
+                r = await cb.submit([row], torch.tensor([row]), max_new, on_tokens=lambda s, t: first.append(time.perf_counter()) if s == 0 else None)
+                t1 = time.perf_counter()
+                assert r.num_generated == max_new
+                lat.append(t1 - t0)
+                ttft.append(first[0] - t0)
+                done_tokens += max_new
+
+        async def cmain():
+            nonlocal stop_at
+            await cb.submit([[5] * 600] * 64, torch.full((64, 600), 5), 8)      # warm-up (graphs for 64 rows)
+            t0 = time.perf_counter()
+            stop_at = t0 + duration
+            await asyncio.gather(*[cclient(i) for i in range(clients)])
+            return time.perf_counter() - t0
+        elapsed = asyncio.run(cmain())
+        cb.stop()
+        q = lambda xs, p: sorted(xs)[min(len(xs) - 1, int(p * len(xs)))]
+        st = cb.stats
+        res = dict(config="continuous batching, 64 slots, %d closed-loop clients, 1 prompt U[512,1024] tokens, %d new tokens" % (clients, max_new),
+                   seconds=round(elapsed, 2), requests=len(lat), output_tokens_per_s=round(done_tokens / elapsed, 1),
+                   request_latency_s=dict(p50=round(q(lat, .5), 3), p99=round(q(lat, .99), 3)),
+                   ttft_s=dict(p50=round(q(ttft, .5), 3), p99=round(q(ttft, .99), 3)),
+                   prefill_calls=int(st["prefill_calls"]), decode_steps=int(st["decode_steps"]),
+                   mean_rows_per_step=round(st["row_steps"] / max(1, st["decode_steps"]), 2))
+        print(json.dumps(res))
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(res, open("gpurun_out/continuous_load.json", "w"), indent=1)
+        return
 
     async def client(i, handler):
         nonlocal done_tokens
