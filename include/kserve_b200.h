@@ -85,6 +85,14 @@ typedef struct b200_gen_params {
   const int32_t* stop_offsets;   /* [num_stop + 1] offsets into stop_tokens */
   int32_t num_stop;
   const int64_t* forced_tokens;  /* testing: [B][max_new_tokens] tokens to append instead of argmax, or NULL */
+  /* Logits processors / sampling — what build_generation_config (generative_model.py:388-402) passes to transformers.
+   * All-zero == greedy without processors.  tp_size must be 1 when any of them is active. */
+  float repetition_penalty;      /* 0 or 1 = off; presence_penalty > 0 is mapped here by the reference (q8) */
+  int32_t do_sample;             /* 0 = greedy (the reference default, q9); 1 = temperature / top-k / top-p sampling */
+  float temperature;             /* 0 = 1.0 */
+  float top_p;                   /* 0 = 1.0 (off) */
+  int32_t top_k;                 /* 0 = 50, transformers' GenerationConfig default; at most 1024 */
+  uint64_t seed;                 /* Philox key; the same seed reproduces the same tokens (not torch's stream) */
 } b200_gen_params_t;
 
 /* Per-step callback for streaming (TextIteratorStreamer in the reference, generative_model.py:307-322):

@@ -21,7 +21,9 @@ class GenParams(C.Structure):
     _fields_ = [("max_new_tokens", C.c_int32), ("pad_token_id", C.c_int64),
                 ("eos_token_ids", C.POINTER(C.c_int64)), ("num_eos", C.c_int32),
                 ("stop_tokens", C.POINTER(C.c_int64)), ("stop_offsets", C.POINTER(C.c_int32)),
-                ("num_stop", C.c_int32), ("forced_tokens", C.POINTER(C.c_int64))]
+                ("num_stop", C.c_int32), ("forced_tokens", C.POINTER(C.c_int64)),
+                ("repetition_penalty", C.c_float), ("do_sample", C.c_int32), ("temperature", C.c_float),
+                ("top_p", C.c_float), ("top_k", C.c_int32), ("seed", C.c_uint64)]
 
 
 class Timing(C.Structure):

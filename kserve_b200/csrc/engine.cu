@@ -148,6 +148,7 @@ struct b200_engine {
     int num_eos = 0, num_stop = 0;
     bool forced = false;
     bool prefilled = false;
+    bool sample_on = false, rep_on = false;   // processed-score path (sampling.cuh) / repetition-penalty bitmap in use
     int per_seq_pages = 0;
   } st;
   // host-DRAM KV tier: pinned copies of the pages of swapped-out sequences (slot -> buffer)
@@ -170,6 +171,9 @@ struct b200_engine {
   b200_timing_t timing{};
   int launches = 0;
   // continuous batching (cb.cuh): per-slot sequence state + the compact list of running slots
+  SampleCfg* d_sample_cfg = nullptr;
+  uint32_t* d_seen = nullptr;        // [max_batch][seen_words] token-presence bitmap (allocated on first use)
+  int seen_words = 0;
   bool cb_on = false;
   CbState cb{};
   std::vector<int> cb_active;        // running slots, in row order of the decode step
@@ -481,11 +485,19 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
   const int use_p2p = (e->cfg.tp_size > 1 && e->p2p_ready) ? 1 : 0;
   // one GPU: 16 CTAs per row scan slices of the 128k-entry row (a single CTA per row took 65 us of the 4.3 ms step)
   const int chunks = (e->cfg.tp_size == 1 && e->Vl >= 16384) ? 16 : 1;
-  B200_CUDA_OK(launch_k(argmax_kernel, dim3(B, chunks), dim3(1024), 0, s, (const bf16*)e->logits, (long long)e->Vl, e->Vl, e->v0, e->cand_val, e->cand_idx, e->p2p, use_p2p));
+  const bool processed = e->st.sample_on && !cb_row_slot;   // repetition penalty / sampling: sampling.cuh
+  if (processed) {
+    SampleParams sp{};
+    sp.logits = e->logits; sp.ld = e->Vl; sp.V = e->Vl; sp.seen = e->st.rep_on ? e->d_seen : nullptr; sp.words = e->seen_words;
+    sp.cfg = e->d_sample_cfg; sp.st = e->d_state; sp.out_val = e->cand_val; sp.out_idx = e->cand_idx;
+    B200_CUDA_OK(launch_k(sample_kernel, dim3(B), dim3(1024), 0, s, sp));
+  } else {
+    B200_CUDA_OK(launch_k(argmax_kernel, dim3(B, chunks), dim3(1024), 0, s, (const bf16*)e->logits, (long long)e->Vl, e->Vl, e->v0, e->cand_val, e->cand_idx, e->p2p, use_p2p));
+  }
   e->launches += 2;
   const float* cv = e->cand_val;
   const int32_t* ci = e->cand_idx;
-  int ranks = chunks;
+  int ranks = processed ? 1 : chunks;
   if (e->cfg.tp_size > 1 && !use_p2p) {
     Nccl& n = Nccl::get();
     B200_NCCL_OK(n.AllGather(e->cand_val, e->cand_val_all, B, Nccl::kFloat, e->comm, s));
@@ -506,6 +518,7 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
   sp.stop_tok = e->d_stop_tok; sp.stop_off = e->d_stop_off; sp.num_stop = e->st.num_stop;
   sp.st = e->d_state;
   sp.pp = e->p2p; sp.use_p2p = use_p2p;
+  sp.seen = e->st.rep_on ? e->d_seen : nullptr; sp.seen_words = e->seen_words; sp.V = e->Vl;
   B200_CUDA_OK(launch_k(step_update_kernel, dim3(1), dim3(128), 0, s, sp));
   e->launches++;
   return 0;
@@ -514,6 +527,12 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
 static int prefill(b200_engine* e) {
   auto& st = e->st;
   int rc;
+  if (st.rep_on) {   // input_ids of the reference = the prompt (pads included): the tokens the penalty applies to
+    B200_CUDA_OK(cudaMemsetAsync(e->d_seen, 0, (size_t)st.B * e->seen_words * 4, e->stream));
+    seen_set_kernel<<<32, 256, 0, e->stream>>>(e->d_seen, e->seen_words, e->d_tok, e->d_tok_seq, st.T, e->d_cur_len, st.B, st.S, st.pad, e->Vl);
+    B200_CUDA_OK(cudaGetLastError());
+    e->launches++;
+  }
   if ((rc = forward_layers(e, st.T, st.B, st.max_len, false))) return rc;
   B200_CUDA_OK(launch_k(gather_rows_kernel, dim3(st.B), dim3(128), 0, e->stream, (const bf16*)e->xn, (const int32_t*)e->d_last_rows, e->xl, e->H));
   e->launches++;
@@ -529,7 +548,8 @@ static int decode_step_enqueue(b200_engine* e) {
 // Decode step through a CUDA graph captured once per (batch size, forced, stop/eos counts).
 static int decode_step(b200_engine* e, bool use_graph) {
   if (!use_graph) return decode_step_enqueue(e);
-  const int key = e->st.B | (e->st.forced ? 1 << 8 : 0) | (e->st.num_eos << 9) | (e->st.num_stop << 14);
+  const int key = e->st.B | (e->st.forced ? 1 << 8 : 0) | (e->st.num_eos << 9) | (e->st.num_stop << 14) |
+                  (e->st.sample_on ? 1 << 21 : 0) | (e->st.rep_on ? 1 << 22 : 0);
   auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
     // one eager step first: creates tensor maps / sets function attributes outside of capture
@@ -612,6 +632,25 @@ static int stage_common(b200_engine* e, int B, int S, const std::vector<int>& le
   StepState init{0, 0, 0, gp->max_new_tokens};
   *e->h_state = init;
   B200_CUDA_OK(cudaMemcpyAsync(e->d_state, e->h_state, sizeof(StepState), cudaMemcpyHostToDevice, s));
+  // logits processors / sampling (build_generation_config, generative_model.py:388-402)
+  SampleCfg sc{};
+  sc.rep_penalty = (gp->repetition_penalty > 0.f) ? gp->repetition_penalty : 1.0f;
+  sc.temperature = (gp->temperature > 0.f) ? gp->temperature : 1.0f;
+  sc.do_sample = gp->do_sample ? 1 : 0;
+  sc.top_p = (gp->top_p > 0.f && gp->top_p < 1.f) ? gp->top_p : 1.0f;
+  sc.top_k = gp->top_k > 0 ? std::min(gp->top_k, kSampleMaxCand) : 50;
+  sc.seed = gp->seed;
+  st.rep_on = sc.rep_penalty != 1.0f;
+  st.sample_on = st.rep_on || sc.do_sample;
+  if (st.sample_on) {
+    B200_REQUIRE(e->cfg.tp_size == 1, "logits processors / sampling run on one GPU per engine (tp_size == 1)");
+    if (!e->d_sample_cfg) B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->d_sample_cfg), sizeof(SampleCfg)));
+    B200_CUDA_OK(cudaMemcpy(e->d_sample_cfg, &sc, sizeof(sc), cudaMemcpyHostToDevice));
+    if (st.rep_on && !e->d_seen) {
+      e->seen_words = (e->Vl + 31) / 32;
+      B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->d_seen), (size_t)e->cfg.max_batch * e->seen_words * 4));
+    }
+  }
   return 0;
 }
 
@@ -1081,6 +1120,8 @@ int b200_engine_destroy(b200_engine_t* e) {
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->ev2) cudaEventDestroy(e->ev2);
+  if (e->d_sample_cfg) cudaFree(e->d_sample_cfg);
+  if (e->d_seen) cudaFree(e->d_seen);
   if (e->stream2) cudaStreamDestroy(e->stream2);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);

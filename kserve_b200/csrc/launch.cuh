@@ -14,6 +14,7 @@
 #include "p2p.cuh"
 #include "moe.cuh"
 #include "cb.cuh"
+#include "sampling.cuh"
 
 namespace b200 {
 

@@ -383,6 +383,7 @@ struct StepParams {
   const int32_t* stop_tok; const int32_t* stop_off; int num_stop;  // flattened stop sequences
   StepState* st;
   P2P pp; int use_p2p;                    // vocab-parallel candidates arrive through peer memory
+  uint32_t* seen; int seen_words; int V;  // repetition-penalty bitmap [B][seen_words] (null when the penalty is off)
 };
 
 __global__ void __launch_bounds__(128) step_update_kernel(const StepParams p) {
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(128) step_update_kernel(const StepParams p) {
     int fin = p.finished[b];
     if (fin) tok = p.pad_token;
     p.out_tokens[b * p.out_ld + step] = tok;
+    if (p.seen && tok >= 0 && tok < p.V) atomicOr(p.seen + (long long)b * p.seen_words + (tok >> 5), 1u << (tok & 31));
     for (int e = 0; e < p.num_eos; ++e)
       if (!fin && tok == p.eos[e]) fin = 1;
     p.finished[b] = fin;

@@ -110,8 +110,15 @@ class B200Engine:
         _lib.check(self.lib.b200_engine_finalize_weights(self.h), "finalize_weights")
 
     # ------------------------------------------------------------------ generate
-    def _params(self, max_new_tokens, pad_token_id, eos_token_ids, stop_sequences, forced_tokens):
+    def _params(self, max_new_tokens, pad_token_id, eos_token_ids, stop_sequences, forced_tokens, sampling=None):
         gp = _lib.GenParams()
+        sp = sampling or {}
+        gp.repetition_penalty = float(sp.get("repetition_penalty") or 0.0)
+        gp.do_sample = 1 if sp.get("do_sample") else 0
+        gp.temperature = float(sp.get("temperature") or 0.0)
+        gp.top_p = float(sp.get("top_p") or 0.0)
+        gp.top_k = int(sp.get("top_k") or 0)
+        gp.seed = int(sp.get("seed") or 0) & 0xFFFFFFFFFFFFFFFF
         keep = []
         gp.max_new_tokens = int(max_new_tokens)
         gp.pad_token_id = int(pad_token_id if pad_token_id is not None else 0)
@@ -142,7 +149,12 @@ class B200Engine:
     def generate(self, input_ids, attention_mask=None, *, max_new_tokens: int, pad_token_id: Optional[int] = 0,
                  eos_token_ids: Sequence[int] = (), stop_sequences: Sequence[Sequence[int]] = (),
                  forced_tokens=None, want_logits: bool = False,
-                 streamer: Optional[Callable[[int, List[int]], bool]] = None) -> GenerateResult:
+                 streamer: Optional[Callable[[int, List[int]], bool]] = None,
+                 repetition_penalty: Optional[float] = None, do_sample: bool = False, temperature: Optional[float] = None,
+                 top_p: Optional[float] = None, top_k: Optional[int] = None, seed: Optional[int] = None) -> GenerateResult:
+        """`repetition_penalty` / `do_sample` / `temperature` / `top_p` / `top_k` / `seed`: the GenerationConfig fields the
+        reference sets (generative_model.py:388-402) plus the checkpoint defaults transformers merges in; greedy when
+        do_sample is false (the penalty still applies, as a logits processor does under greedy decoding)."""
         ids = torch.as_tensor(input_ids, dtype=torch.int64).contiguous()
         assert ids.dim() == 2 and not ids.is_cuda
         B, S = ids.shape
@@ -150,7 +162,9 @@ class B200Engine:
         if attention_mask is not None:
             mask = torch.as_tensor(attention_mask, dtype=torch.int64).contiguous()
             assert mask.shape == ids.shape
-        gp, keep = self._params(max_new_tokens, pad_token_id, eos_token_ids, stop_sequences, forced_tokens)
+        gp, keep = self._params(max_new_tokens, pad_token_id, eos_token_ids, stop_sequences, forced_tokens,
+                                dict(repetition_penalty=repetition_penalty, do_sample=do_sample, temperature=temperature,
+                                     top_p=top_p, top_k=top_k, seed=seed))
         out = torch.empty((B, S + max_new_tokens), dtype=torch.int64).pin_memory()
         out_len, stop = C.c_int32(0), C.c_int32(0)
         logits = None

@@ -116,7 +116,7 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                  tokenizer=None, pad_token_id: Optional[int] = None, max_model_len: Optional[int] = None,
                  max_batch: int = 32, device: int = 0, tensor_parallel_size: int = 1, tp_rank: int = 0,
                  nccl_id: Optional[bytes] = None, system_fingerprint: Optional[str] = None,
-                 request_logger=None, continuous_batching: bool = False):
+                 request_logger=None, continuous_batching: bool = False, generation_defaults: Optional[dict] = None):
         Model.__init__(self, model_name)
         self.ready = False
         self.model_id_or_path = model_id_or_path
@@ -136,6 +136,8 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         self._thread: Optional[Thread] = None
         self.eos_token_ids: List[int] = []
         # iteration-level batching instead of the reference's one-request-at-a-time loop (continuous.py)
+        self._generation_defaults = generation_defaults
+        self._seed_counter = 0
         self.continuous_batching = bool(continuous_batching) and tensor_parallel_size == 1
         self._cb = None
 
@@ -161,6 +163,13 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
             self._pad_token_id = self._tokenizer.pad_token_id
         if self.max_length is None:
             self.max_length = cfg.get("max_position_embeddings", 2048)   # utils.py:28-159 (derived max len)
+        # checkpoint generation defaults: transformers merges the None fields of the request's GenerationConfig from
+        # model.generation_config (generation/utils.py:1693-1701) — this is how instruct checkpoints turn sampling on (q9)
+        self.generation_defaults = dict(self._generation_defaults or {})
+        gpath = os.path.join(self.model_id_or_path, "generation_config.json") if self.model_id_or_path else None
+        if gpath and os.path.exists(gpath):
+            with open(gpath) as f:
+                self.generation_defaults = {**json.load(f), **self.generation_defaults}
         eos = cfg.get("eos_token_id")
         self.eos_token_ids = [] if eos is None else ([int(e) for e in eos] if isinstance(eos, list) else [int(eos)])
         self._engine = B200Engine(cfg, max_batch=self.max_batch, max_seq_len=self.max_length, device=self.device_index,
@@ -256,15 +265,42 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
             rows.append(ids[b, first:].tolist())
         return rows
 
-    async def _agenerate(self, ids, mask, *, max_new_tokens, pad_token_id, eos_token_ids, stop_sequences=()) -> GenerateResult:
+    def build_generation_config(self, request: CompletionRequest) -> Dict[str, Any]:
+        """generative_model.py:388-402: `top_p`, `temperature` pass through; `presence_penalty > 0` becomes
+        `repetition_penalty` (q8); nothing sets do_sample, so sampling is on only if the checkpoint's own
+        generation_config.json says so (q9), whose temperature / top_p / top_k then fill the request's None fields.
+        `seed` (:302-303 calls set_seed) keys this runtime's Philox stream instead."""
+        d = self.generation_defaults
+        out: Dict[str, Any] = {}
+        rp = request.presence_penalty if (request.presence_penalty and request.presence_penalty > 0) else d.get("repetition_penalty")
+        if rp and float(rp) != 1.0:
+            out["repetition_penalty"] = float(rp)
+        if d.get("do_sample"):
+            temperature = request.temperature if request.temperature is not None else d.get("temperature", 1.0)
+            if temperature is not None and float(temperature) > 0:      # temperature == 0: greedy, as vLLM's type documents it
+                out["do_sample"] = True
+                out["temperature"] = float(temperature)
+                top_p = request.top_p if request.top_p is not None else d.get("top_p", 1.0)
+                out["top_p"] = float(top_p if top_p is not None else 1.0)
+                out["top_k"] = int(d.get("top_k", 50) or 0) or 1024      # GenerationConfig default 50; 0 / None = "off" -> widest supported
+                seed = getattr(request, "seed", None)
+                if seed is None:
+                    self._seed_counter += 1
+                    seed = (int(time.time_ns()) ^ (self._seed_counter * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
+                out["seed"] = int(seed)
+        return out
+
+    async def _agenerate(self, ids, mask, *, max_new_tokens, pad_token_id, eos_token_ids, stop_sequences=(), **sampling) -> GenerateResult:
         """One request through the engine: the continuous batcher when enabled, else the serial generation thread."""
         if self._cb is not None:
+            if sampling:
+                raise OpenAIError("repetition penalty / sampling are not available with --continuous_batching (greedy only)")
             try:
                 return await self._cb.submit(self._unpadded_rows(ids, mask), ids, max_new_tokens, stop_sequences)
             except ValueError as e:
                 raise OpenAIError(str(e))
         return await self._submit(lambda: self._generate(ids, mask, max_new_tokens=max_new_tokens, pad_token_id=pad_token_id,
-                                                         eos_token_ids=eos_token_ids, stop_sequences=stop_sequences))
+                                                         eos_token_ids=eos_token_ids, stop_sequences=stop_sequences, **sampling))
 
     # ------------------------------------------------------------------ request validation (:376-402)
     def validate_supported_completion_params(self, request: CompletionRequest):
@@ -274,10 +310,8 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
             raise OpenAIError("'n' > 1 is not supported")
         if request.echo and self.is_encoder_decoder:
             raise OpenAIError("'echo' is not supported by encoder-decoder models")
-        # The reference maps these onto HF sampling processors; with do_sample never set they only matter when
-        # the checkpoint's generation_config enables sampling (q9).  This round is greedy-only: reject loudly.
-        if request.presence_penalty and request.presence_penalty > 0:
-            raise OpenAIError("'presence_penalty' is not supported by the B200 runtime yet")
+        # presence_penalty / temperature / top_p are handled by build_generation_config (device-side processors).
+        # logit_bias -> sequence_bias keyed by tuple(str) is unusable in the reference itself (q8): reject loudly.
         if request.logit_bias:
             raise OpenAIError("'logit_bias' is not supported by the B200 runtime yet")
 
@@ -331,7 +365,7 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         echo = bool(request.echo)
         stop_state: Dict[str, bool] = {"triggered": False}
         common = dict(max_new_tokens=request.max_tokens, pad_token_id=self._pad_token_id,
-                      eos_token_ids=self.eos_token_ids, stop_sequences=stop_sequences)
+                      eos_token_ids=self.eos_token_ids, stop_sequences=stop_sequences, **self.build_generation_config(request))
 
         if request.stream:
             if B != 1:
@@ -366,6 +400,8 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                 put(None)
                 return None
             if self._cb is not None:
+                if self.build_generation_config(request):
+                    raise OpenAIError("repetition penalty / sampling are not available with --continuous_batching (greedy only)")
                 detok = IncrementalDetokenizer(self._tokenizer)
                 if echo:
                     piece = detok.put(self._unpadded_rows(ids, mask)[0])

@@ -193,6 +193,7 @@ class OracleGenerativeModel:
         if want_logits:
             generation_config.return_dict_in_generate = True
             generation_config.output_logits = True
+            generation_config.output_scores = True      # processed scores (== logits unless a processor is active)
         out = self._model.generate(**inputs, stopping_criteria=stopping, generation_config=generation_config)  # :328
         dt = time.perf_counter() - t0
         seqs_out = out.sequences if want_logits else out
@@ -204,7 +205,8 @@ class OracleGenerativeModel:
         return OracleResult(output_ids=seqs_out, texts=texts, finish_reason=finish_reason,
                             prompt_tokens=num_prompt_tokens, completion_tokens=completion_tokens,
                             step_logits=[l.float() for l in out.logits] if want_logits else None,
-                            seconds=dt)
+                            seconds=dt,
+                            extra={"step_scores": [x.float() for x in out.scores]} if want_logits else {})
 
     @torch.no_grad()
     def forward_logits(self, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -67,7 +67,7 @@ def topk_pack(step_logits, k=16):
 
 
 def gen_case(name, cfg_name, seed, prompt, max_tokens, stop=(), tokenizer=None, pad_token_id=None,
-             full_logits=True, echo=False, stop_from=None):
+             full_logits=True, echo=False, stop_from=None, presence_penalty=None):
     cfg = W.CONFIGS[cfg_name]
     sd = W.synth_state_dict(cfg, seed)
     model = build_model(cfg, sd)
@@ -78,8 +78,9 @@ def gen_case(name, cfg_name, seed, prompt, max_tokens, stop=(), tokenizer=None, 
         S = free.output_ids.shape[1] - max_tokens
         stop = [free.output_ids[row, S + i:S + j].tolist()]
     res = orc.create_completion(prompt, max_tokens=max_tokens, stop=stop, echo=echo, temperature=0,
-                                want_logits=True)
-    tv, ti = topk_pack(res.step_logits)
+                                want_logits=True, presence_penalty=presence_penalty)
+    # top-k of the PROCESSED scores: what argmax saw (identical to the raw logits unless a logits processor ran)
+    tv, ti = topk_pack(res.extra["step_scores"] if presence_penalty else res.step_logits)
     out = dict(
         output_ids=res.output_ids.numpy(),
         topk_vals=tv, topk_idx=ti,
@@ -90,7 +91,7 @@ def gen_case(name, cfg_name, seed, prompt, max_tokens, stop=(), tokenizer=None, 
             pad_token_id=orc.pad_token_id, vocab_rows=int(model.get_input_embeddings().weight.shape[0]),
             weights_checksum=W.checksum(sd), stop=[list(s) if not isinstance(s, str) else s for s in stop],
             prompt=prompt if isinstance(prompt, (str, list)) and (isinstance(prompt, str) or isinstance(prompt[0], str)) else None,
-            echo=echo,
+            echo=echo, presence_penalty=presence_penalty,
             transformers=transformers.__version__, torch=torch.__version__,
             threads=torch.get_num_threads())),
     )
@@ -183,6 +184,9 @@ def main():
              12, tokenizer=tok)
     # (c) stop sequence as token ids: take case (a)'s 5th+6th generated token of row 2 -> must stop the batch
     gen_case("tiny_g2_stop", "tiny_g2", 0, ids_prompt(4, 48, 1000, 1234), 16, stop_from=(2, 4, 6), pad_token_id=1030)
+    # presence_penalty > 0 -> repetition_penalty (generative_model.py:388-402): a logits processor under GREEDY decoding;
+    # prompts drawn from 40 token ids so that repeats (and therefore penalised logits) occur
+    gen_case("tiny_g2_reppen", "tiny_g2", 0, ids_prompt(4, 48, 40, 77), 24, pad_token_id=1030, presence_penalty=1.8)
     # (d) group size 4, 3 layers, odd batch, longer prompt (crosses KV page boundary of 64)
     gen_case("tiny_g4_ids", "tiny_g4", 1, ids_prompt(3, 100, 2048, 99), 40, pad_token_id=0)
     # (e) single sequence, batch 1, long decode crossing pages
