@@ -89,3 +89,38 @@ def test_first_token_distribution_matches_the_warper_chain(eng, temperature, top
     bound = 2.5 * (len(support) / (2 * 3.14159 * N)) ** 0.5 + 0.01
     assert tv < bound, f"total variation {tv:.3f} over {len(support)} tokens exceeds {bound:.3f}"
     assert len(set(counts.nonzero().flatten().tolist())) >= min(3, len(support))
+
+
+def test_openai_route_presence_penalty_and_checkpoint_sampling_defaults():
+    """presence_penalty through /openai/v1/completions equals the oracle's strings-as-ids; a checkpoint whose
+    generation_config turns sampling on (q9) samples reproducibly per `seed` and falls back to greedy at temperature 0."""
+    from fastapi.testclient import TestClient
+    from kserve_b200.generative_model import B200GenerativeModel
+    from kserve_b200.kserve_api import ModelServer
+    from oracle import weights as W
+    c = load_case("tiny_g2_reppen")
+    m = c["meta"]
+    cfg = dict(W.CONFIGS["tiny_g2"], architectures=["LlamaForCausalLM"], model_type="llama")
+    model = B200GenerativeModel("tiny", model_config=cfg, state_dict=W.iter_state_dict(W.CONFIGS["tiny_g2"], 0), pad_token_id=m["pad_token_id"],
+                                max_model_len=512, max_batch=8, generation_defaults={"do_sample": True, "temperature": 0.8, "top_p": 0.9})
+    assert model.load()
+    try:
+        with TestClient(ModelServer().create_application([model])) as client:
+            prompt = c["input_ids"][0].tolist()
+            post = lambda **kw: client.post("/openai/v1/completions", json={"model": "tiny", "prompt": prompt, "max_tokens": 12, **kw})
+            g = post(temperature=0, presence_penalty=m["presence_penalty"])
+            assert g.status_code == 200, g.text
+            toks = [int(x) for x in g.json()["choices"][0]["text"].split()]
+            ref = c["gen"][0].tolist()[:12]
+            tol = logits_tol(c["step_logits"])
+            for t, (a, b) in enumerate(zip(toks, ref)):
+                if a != b:
+                    assert float(c["margin"][0, t]) <= 2 * tol * m["presence_penalty"]
+                    break
+            s1 = post(seed=7).json()["choices"][0]["text"]
+            s2 = post(seed=7).json()["choices"][0]["text"]
+            s3 = post(seed=8).json()["choices"][0]["text"]
+            assert s1 == s2 and s1 != s3
+            assert post(logit_bias={"5": 1.0}).status_code == 500
+    finally:
+        model.stop()
