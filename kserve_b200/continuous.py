@@ -41,6 +41,7 @@ class _Request:
     streamed: int = 0
     t_submit: float = field(default_factory=time.perf_counter)
     t_first: float = 0.0
+    cancelled: bool = False                  # set from the event loop when the awaiting task went away (client disconnect)
 
 
 class ContinuousBatcher:
@@ -58,7 +59,7 @@ class ContinuousBatcher:
         self._thread: Optional[threading.Thread] = None
         self.free_slots = engine.max_batch
         # counters for the load tests / metrics
-        self.stats: Dict[str, float] = dict(admitted=0, finished=0, decode_steps=0, row_steps=0, prefill_calls=0)
+        self.stats: Dict[str, float] = dict(admitted=0, finished=0, cancelled=0, decode_steps=0, row_steps=0, prefill_calls=0)
 
     # ------------------------------------------------------------------ lifecycle
     def start(self) -> None:
@@ -76,7 +77,7 @@ class ContinuousBatcher:
 
     # ------------------------------------------------------------------ submission
     def submit_nowait(self, prompts: List[List[int]], padded: torch.Tensor, max_new_tokens: int,
-                      stop_sequences: Sequence[Sequence[int]], done, on_tokens=None) -> None:
+                      stop_sequences: Sequence[Sequence[int]], done, on_tokens=None) -> "_Request":
         stops = [list(map(int, s)) for s in stop_sequences if len(s)]
         if len(prompts) > self.engine.max_batch:
             raise ValueError(f"request of {len(prompts)} prompts exceeds max_batch {self.engine.max_batch}")
@@ -88,6 +89,12 @@ class ContinuousBatcher:
                        stops=stops, pad=self.pad, done=done, on_tokens=on_tokens)
         with self._cv:
             self._pending.append(req)
+            self._cv.notify_all()
+        return req
+
+    def cancel(self, req: "_Request") -> None:
+        with self._cv:
+            req.cancelled = True
             self._cv.notify_all()
 
     async def submit(self, prompts: List[List[int]], padded: torch.Tensor, max_new_tokens: int,
@@ -104,8 +111,14 @@ class ContinuousBatcher:
                 else:
                     fut.set_result(result)
             loop.call_soon_threadsafe(_set)
-        self.submit_nowait(prompts, padded, max_new_tokens, stop_sequences, done, on_tokens)
-        return await fut
+        req = self.submit_nowait(prompts, padded, max_new_tokens, stop_sequences, done, on_tokens)
+        try:
+            return await fut
+        except asyncio.CancelledError:
+            # the reference wraps its endpoints in `with_cancellation` but cannot abort a running `generate`; here the
+            # sequence leaves the batch at the next poll and its slots are reused
+            self.cancel(req)
+            raise
 
     # ------------------------------------------------------------------ scheduler thread
     def _admit(self) -> None:
@@ -116,6 +129,10 @@ class ContinuousBatcher:
         with self._cv:
             while self._pending:
                 r = self._pending[0]
+                if r.cancelled:
+                    self._pending.popleft()
+                    self.stats["cancelled"] += 1
+                    continue
                 need = len(r.prompts)
                 toks = sum(len(p) for p in r.prompts)
                 if need > free or (budget is not None and batch and toks > budget):
@@ -166,6 +183,12 @@ class ContinuousBatcher:
         n_gen, fin, stop = self.engine.cb_poll()
         still: List[_Request] = []
         for r in self._running:
+            if r.cancelled:
+                for sl in r.slots:
+                    self.engine.cb_release(sl)
+                self.free_slots += len(r.slots)
+                self.stats["cancelled"] += 1
+                continue
             g = [n_gen[s] for s in r.slots]
             stopped = [s for s in r.slots if stop[s]]
             if stopped:

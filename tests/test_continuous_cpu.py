@@ -9,7 +9,8 @@ from kserve_b200.continuous import ContinuousBatcher
 
 class ScriptedEngine:
     """cb_* surface of B200Engine; sequence i emits script[i][k] as its k-th token."""
-    def __init__(self, max_batch, scripts, eos=()):
+    def __init__(self, max_batch, scripts, eos=(), step_delay=0.0):
+        self.step_delay = step_delay
         self.max_batch, self.max_seq_len = max_batch, 4096
         self.scripts = scripts            # prompt tuple -> token list
         self.eos = set(eos)
@@ -46,6 +47,9 @@ class ScriptedEngine:
         return out
 
     def cb_step(self, n):
+        if self.step_delay:
+            import time
+            time.sleep(self.step_delay * n)
         for _ in range(n):
             for st in self.slots.values():
                 self._emit(st)
@@ -118,3 +122,28 @@ def test_invalid_requests_are_rejected_up_front():
             raise AssertionError("accepted an invalid request")
         except ValueError:
             pass
+
+
+def test_cancelled_requests_leave_the_batch_and_free_their_slots():
+    scripts = {(i,): list(range(1000 * i, 1000 * i + 400)) for i in range(3)}
+    eng = ScriptedEngine(2, scripts, step_delay=0.002)
+    cb = ContinuousBatcher(eng, pad_token_id=0, steps_per_poll=2)
+
+    async def main():
+        long_a = asyncio.create_task(cb.submit([[0]], torch.tensor([[0]]), 300))
+        long_b = asyncio.create_task(cb.submit([[1]], torch.tensor([[1]]), 300))
+        await asyncio.sleep(0.05)                         # both are running, the third request has to queue
+        waiting = asyncio.create_task(cb.submit([[2]], torch.tensor([[2]]), 4))
+        await asyncio.sleep(0.02)
+        long_a.cancel()                                   # client went away mid-generation
+        r = await waiting                                 # ... which frees a slot for the queued request
+        long_b.cancel()
+        for t in (long_a, long_b):
+            try:
+                await t
+            except asyncio.CancelledError:
+                pass
+        return r
+    r = _run(cb, main())
+    assert r.output_ids.tolist() == [[2, 2000, 2001, 2002, 2003]]
+    assert cb.stats["cancelled"] >= 1
