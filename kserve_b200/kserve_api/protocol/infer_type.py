@@ -41,13 +41,18 @@ def from_np_dtype(dt) -> str:
     return _NP2DT[dt]
 
 
-def serialize_byte_tensor(arr: np.ndarray) -> bytes:
-    """BYTES elements are <uint32 little-endian length><bytes> back to back (OIP binary extension)."""
+def _serialize_bytes(arr: np.ndarray) -> bytes:
     out = bytearray()
     for item in arr.reshape(-1):
         b = item if isinstance(item, (bytes, bytearray)) else str(item).encode("utf-8")
         out += struct.pack("<I", len(b)) + b
     return bytes(out)
+
+
+def serialize_byte_tensor(arr: np.ndarray) -> np.ndarray:
+    """BYTES elements are <uint32 little-endian length><bytes> back to back (OIP binary extension).  Returned the way the
+    reference (and tritonclient) return it: a 0-d object array whose `.item()` is the byte string."""
+    return np.asarray(_serialize_bytes(arr), dtype=np.object_)
 
 
 def deserialize_bytes_tensor(raw: bytes) -> np.ndarray:
@@ -102,6 +107,15 @@ class _Tensor:
                             dtype=np.object_).reshape(self._shape)
         return np.asarray(self._data, dtype=dtype).reshape(self._shape)
 
+    def __eq__(self, other):
+        if not isinstance(other, _Tensor):
+            return False
+        return (self._name == other._name and self._shape == other._shape and self._datatype == other._datatype
+                and self._parameters == other._parameters and _same(self._data, other._data)
+                and _same(self._raw_data, other._raw_data))
+
+    __hash__ = None
+
     def as_string(self) -> List[str]:
         return [x.decode("utf-8") if isinstance(x, (bytes, bytearray)) else str(x) for x in self.as_numpy().reshape(-1)]
 
@@ -114,11 +128,9 @@ class _Tensor:
         self._shape = list(arr.shape)
         if binary_data:
             self._data = None
-            self._raw_data = serialize_byte_tensor(arr) if dt == "BYTES" else np.ascontiguousarray(arr).tobytes()
+            self._raw_data = _serialize_bytes(arr) if dt == "BYTES" else np.ascontiguousarray(arr).tobytes()
             self._parameters["binary_data_size"] = len(self._raw_data)
         else:
-            if dt == "FP16":
-                raise InvalidInput("FP16 tensors must use the binary data format")
             self._raw_data = None
             self._parameters.pop("binary_data_size", None)
             if dt == "BYTES":
@@ -129,11 +141,13 @@ class _Tensor:
     def _to_dict(self, binary: bool, raw_out: List[bytes]) -> Dict[str, Any]:
         d: Dict[str, Any] = {"name": self._name, "shape": self._shape, "datatype": self._datatype}
         params = dict(self._parameters)
+        if params or binary:
+            d["parameters"] = params          # key order of the reference's REST body: ..., parameters, data
         if binary:
             raw = self._raw_data
             if raw is None:
                 arr = self.as_numpy()
-                raw = serialize_byte_tensor(arr) if self._datatype == "BYTES" else np.ascontiguousarray(arr).tobytes()
+                raw = _serialize_bytes(arr) if self._datatype == "BYTES" else np.ascontiguousarray(arr).tobytes()
             params["binary_data_size"] = len(raw)
             raw_out.append(raw)
         else:
@@ -148,9 +162,19 @@ class _Tensor:
                 if self._data is None:
                     raise InvalidInput(f"'data' field is missing for tensor '{self._name}'")
                 d["data"] = self._data
-        if params:
-            d["parameters"] = params
+        if not params:
+            d.pop("parameters", None)
         return d
+
+
+def _same(a, b) -> bool:
+    if a is None or b is None:
+        return a is None and b is None
+    if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        return np.array_equal(np.asarray(a), np.asarray(b))
+    if isinstance(a, (bytes, bytearray, memoryview)) or isinstance(b, (bytes, bytearray, memoryview)):
+        return bytes(a) == bytes(b)
+    return a == b
 
 
 def _flatten(x):
@@ -173,6 +197,11 @@ class RequestedOutput:
     def __init__(self, name: str, parameters: Optional[Dict] = None):
         self.name, self.parameters = name, parameters or {}
 
+    def __eq__(self, other):
+        return isinstance(other, RequestedOutput) and self.name == other.name and self.parameters == other.parameters
+
+    __hash__ = None
+
     @property
     def binary_data(self) -> Optional[bool]:
         return self.parameters.get("binary_data")
@@ -188,6 +217,15 @@ class InferRequest:
         self.inputs = infer_inputs
         self.parameters = parameters or {}
         self.request_outputs = request_outputs
+
+    def __eq__(self, other):
+        if not isinstance(other, InferRequest):
+            return False
+        return (self.id == other.id and self.model_name == other.model_name and self.model_version == other.model_version
+                and self.parameters == other.parameters and self.inputs == other.inputs
+                and (self.request_outputs or None) == (other.request_outputs or None))
+
+    __hash__ = None
 
     @classmethod
     def from_bytes(cls, req_bytes: bytes, json_length: int, model_name: str) -> "InferRequest":
@@ -222,7 +260,7 @@ class InferRequest:
 
     @classmethod
     def from_dict(cls, d: Dict, model_name: str) -> "InferRequest":
-        raw = json.dumps(d).encode()
+        raw = json.dumps(d, separators=(",", ":")).encode()
         return cls.from_bytes(raw, len(raw), model_name)
 
     def get_input_by_name(self, name: str) -> Optional[InferInput]:
@@ -246,7 +284,7 @@ class InferRequest:
         if self.request_outputs:
             res["outputs"] = [{"name": o.name, **({"parameters": o.parameters} if o.parameters else {})} for o in self.request_outputs]
         if raws:
-            j = json.dumps(res).encode()
+            j = json.dumps(res, separators=(",", ":")).encode()
             return j + b"".join(bytes(r) for r in raws), len(j)
         return res, None
 
@@ -269,6 +307,42 @@ class InferResponse:
                 return o
         return None
 
+    def __eq__(self, other):
+        if not isinstance(other, InferResponse):
+            return False
+        return (self.id == other.id and self.model_name == other.model_name and self.model_version == other.model_version
+                and self.parameters == other.parameters and self.outputs == other.outputs)
+
+    __hash__ = None
+
+    @classmethod
+    def from_bytes(cls, res_bytes: bytes, json_length: int) -> "InferResponse":
+        """The client-side inverse of to_rest (infer_type.py `InferResponse.from_bytes`): JSON header + raw tensors in
+        output order.  BYTES tensors come back as a list of str in `.data`, numeric ones as a numpy array."""
+        try:
+            d = json.loads(res_bytes[:json_length])
+        except json.JSONDecodeError as e:
+            raise InvalidInput(f"Unrecognized request format: {e}")
+        outs, start = [], json_length
+        for o in d.get("outputs", []):
+            params = o.get("parameters") or {}
+            t = InferOutput(o["name"], o["shape"], o["datatype"], parameters=dict(params))
+            if o.get("data") is not None:
+                t.data = o["data"]
+            elif params.get("binary_data_size") is not None:
+                n = params["binary_data_size"]
+                raw = bytes(res_bytes[start:start + n])
+                start += n
+                if t.datatype == "BYTES":
+                    t.data = [x.decode("utf-8") for x in deserialize_bytes_tensor(raw)]
+                else:
+                    t.data = np.frombuffer(raw, dtype=to_np_dtype(t.datatype)).reshape(t.shape)
+            else:
+                raise InvalidInput(f"'data' field is missing for output '{t.name}' for model '{d.get('model_name')}'")
+            outs.append(t)
+        return cls(response_id=d.get("id"), model_name=d.get("model_name"), infer_outputs=outs,
+                   model_version=d.get("model_version"), parameters=d.get("parameters"))
+
     def to_rest(self) -> Tuple[Union[bytes, Dict], Optional[int]]:
         """infer_type.py:1328-1404: dict, or JSON header + raw tensors when binary outputs were requested."""
         want = {o.name: o for o in (self._requested_outputs or [])}
@@ -285,9 +359,14 @@ class InferResponse:
         if self.parameters:
             res["parameters"] = self.parameters
         if raws:
-            j = json.dumps(res).encode()
+            j = json.dumps(res, separators=(",", ":")).encode()
             return j + b"".join(bytes(r) for r in raws), len(j)
         return res, None
+
+
+def _contains_fp16_datatype(infer_response: InferResponse) -> bool:
+    """FP16 outputs force the binary response format (JSON cannot carry them)."""
+    return any(o.datatype == "FP16" for o in infer_response.outputs)
 
 
 def get_predict_input(payload: Union[Dict, InferRequest]):
