@@ -8,9 +8,10 @@ from fastapi import Request
 
 from ....errors import InvalidInput
 from .openai_model import AsyncMappingIterator, ChatPrompt, OpenAIGenerativeModel
-from .types import (ChatCompletion, ChatCompletionChoice, ChatCompletionChunk, ChatCompletionRequest, ChatMessage,
+from .types import (ChatCompletion, ChatCompletionChoice, ChatCompletionChunk, ChatCompletionLogProb,
+                    ChatCompletionLogProbs, ChatCompletionLogProbsContent, ChatCompletionRequest, ChatMessage,
                     ChoiceDelta, ChunkChoice, Completion, CompletionChoice, CompletionChunk, CompletionChunkChoice,
-                    CompletionRequest, ErrorResponse)
+                    CompletionLogProbs, CompletionRequest, ErrorResponse)
 
 
 class OpenAIChatAdapterModel(OpenAIGenerativeModel):
@@ -29,14 +30,28 @@ class OpenAIChatAdapterModel(OpenAIGenerativeModel):
             request_id=request.request_id)
 
     @classmethod
+    def to_choice_logprobs(cls, lp: CompletionLogProbs) -> ChatCompletionLogProbs:
+        """:88-113 — completions-style parallel lists (tokens / token_logprobs / top_logprobs dicts) become the chat
+        API's per-token records with the UTF-8 bytes of each token (pinned by fixtures/openai/chat_completion*.json)."""
+        def rec(token: str, logprob) -> dict:
+            return dict(token=token, bytes=list(token.encode("utf8")), logprob=logprob)
+        content = []
+        for i, token in enumerate(lp.tokens):
+            tops = [ChatCompletionLogProb(**rec(t, v)) for t, v in (lp.top_logprobs[i] or {}).items()]
+            content.append(ChatCompletionLogProbsContent(**rec(token, lp.token_logprobs[i]), top_logprobs=tops))
+        return ChatCompletionLogProbs(content=content)
+
+    @classmethod
     def to_chat_completion_choice(cls, choice: CompletionChoice, role: str) -> ChatCompletionChoice:
-        return ChatCompletionChoice(index=0, finish_reason=choice.finish_reason, logprobs=None,
+        lp = cls.to_choice_logprobs(choice.logprobs) if choice.logprobs is not None else None
+        return ChatCompletionChoice(index=0, finish_reason=choice.finish_reason, logprobs=lp,
                                     message=ChatMessage(content=choice.text, role=role))
 
     @classmethod
     def to_chat_completion_chunk_choice(cls, choice: CompletionChunkChoice, role: str) -> ChunkChoice:
+        lp = cls.to_choice_logprobs(choice.logprobs) if choice.logprobs is not None else None
         return ChunkChoice(delta=ChoiceDelta(content=choice.text, role=role), index=0,
-                           finish_reason=choice.finish_reason, logprobs=None)
+                           finish_reason=choice.finish_reason, logprobs=lp)
 
     @classmethod
     def completion_to_chat_completion(cls, completion: Completion, role: str) -> ChatCompletion:

@@ -98,9 +98,20 @@ class CompletionChunk(OpenAIBaseModel):
 
 
 class ChatCompletionMessageParam(OpenAIBaseModel):
+    """vLLM declares chat messages as TypedDicts: callers index them (`messages[0]["content"]`,
+    test_openai_completion.py:324), so the model answers to both attribute and key access."""
     role: str
     content: Optional[Union[str, List[Dict[str, Any]]]] = None
     name: Optional[str] = None
+
+    def __getitem__(self, key: str):
+        try:
+            return getattr(self, key)
+        except AttributeError:
+            raise KeyError(key)
+
+    def get(self, key: str, default=None):
+        return getattr(self, key, default)
 
 
 class ChatCompletionRequest(OpenAIBaseModel):
@@ -131,12 +142,27 @@ class ChatCompletionRequest(OpenAIBaseModel):
 class ChatMessage(OpenAIBaseModel):
     role: str
     content: Optional[str] = None
+    tool_calls: List[Any] = Field(default_factory=list)     # vLLM's ChatMessage carries an (empty) list: fixtures/openai/chat_completion.json
+
+
+class ChatCompletionLogProb(OpenAIBaseModel):
+    token: str
+    logprob: float = -9999.0
+    bytes: Optional[List[int]] = None
+
+
+class ChatCompletionLogProbsContent(ChatCompletionLogProb):
+    top_logprobs: List[ChatCompletionLogProb] = Field(default_factory=list)
+
+
+class ChatCompletionLogProbs(OpenAIBaseModel):
+    content: Optional[List[ChatCompletionLogProbsContent]] = None
 
 
 class ChatCompletionChoice(OpenAIBaseModel):
     index: int
     message: ChatMessage
-    logprobs: Optional[Any] = None
+    logprobs: Optional[ChatCompletionLogProbs] = None
     finish_reason: Optional[str] = "stop"
 
 
@@ -158,7 +184,7 @@ class ChoiceDelta(OpenAIBaseModel):
 class ChunkChoice(OpenAIBaseModel):
     index: int
     delta: ChoiceDelta
-    logprobs: Optional[Any] = None
+    logprobs: Optional[ChatCompletionLogProbs] = None
     finish_reason: Optional[str] = None
 
 

@@ -148,7 +148,7 @@ def test_openai_streaming_sse_and_chat_mapping(client):
     assert len({c["id"] for c in chunks}) == 1 and all(c["choices"][0]["finish_reason"] == "length" for c in chunks)
     chat = {"model": "gpt", "messages": [{"role": "user", "content": "yo"}]}
     j = client.post("/openai/v1/chat/completions", json=chat).json()
-    assert j["object"] == "chat.completion" and j["choices"][0]["message"] == {"role": "assistant", "content": "echo:<|user|>yo\n"}
+    assert j["object"] == "chat.completion" and j["choices"][0]["message"] == {"role": "assistant", "content": "echo:<|user|>yo\n", "tool_calls": []}
     with client.stream("POST", "/openai/v1/chat/completions", json={**chat, "stream": True}) as r:
         lines = [l for l in r.iter_lines() if l]
     assert lines[-1] == "data: [DONE]"
