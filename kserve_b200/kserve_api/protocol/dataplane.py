@@ -93,6 +93,18 @@ class DataPlane:
                 response_headers["content-type"] = "application/octet-stream"
         return response, response_headers
 
+    async def explain(self, model_name: str, request: Union[Dict, InferRequest],
+                      headers: Optional[Dict[str, str]] = None):
+        """dataplane.py:477-506: same call as infer() with the EXPLAIN verb"""
+        from ..model import InferenceVerb
+        response_headers: Dict[str, str] = {}
+        model = await self.get_model(model_name)
+        if not isinstance(model, InferenceModel):
+            raise ValueError(f"Model of type {type(model).__name__} does not support inference")
+        response, res_headers = await model(request, headers=headers, verb=InferenceVerb.EXPLAIN)
+        response_headers.update(res_headers)
+        return response, response_headers
+
     async def infer(self, model_name: str, request: Union[Dict, InferRequest],
                     headers: Optional[Dict[str, str]] = None):
         """dataplane.py:439-475"""

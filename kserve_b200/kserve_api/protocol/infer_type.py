@@ -74,7 +74,14 @@ class _Tensor:
 
     name = property(lambda s: s._name)
     datatype = property(lambda s: s._datatype)
-    parameters = property(lambda s: s._parameters)
+
+    @property
+    def parameters(self):
+        return self._parameters
+
+    @parameters.setter
+    def parameters(self, v):
+        self._parameters = v if v is not None else {}
 
     @property
     def shape(self):

@@ -79,6 +79,26 @@ def create_application(dataplane: OpenAIDataPlane) -> FastAPI:
             return StreamingResponse(content=response)
         return JSONResponse(content=response, headers=response_headers)
 
+    # ---- V1 explain (v1_endpoints.py:102-140): the predict route with the EXPLAIN verb
+    @app.post("/v1/models/{model_name}:explain")
+    async def v1_explain(model_name: str, request: Request):
+        if not await dp.model_ready(model_name, True):
+            raise E.ModelNotReady(model_name)
+        body = await request.body()
+        headers = dict(request.headers.items())
+        infer_request, attrs = dp.decode(body=body, headers=headers)
+        response, response_headers = await dp.explain(model_name=model_name, request=infer_request, headers=headers)
+        response, res_headers = dp.encode(model_name=model_name, response=response, headers=headers, req_attributes=attrs)
+        response_headers.update(res_headers)
+        response_headers.pop("content-length", None)
+        if isinstance(response, (bytes, str)):
+            return Response(content=response, headers=response_headers)
+        return JSONResponse(content=response, headers=response_headers)
+
+    @app.get("/v2/models")
+    async def v2_models():
+        return {"models": list(dp.model_registry.get_models().keys())}
+
     # ---- V2 infer (v2_endpoints.py:132-194)
     @app.post("/v2/models/{model_name}/infer")
     async def v2_infer(model_name: str, request: Request):
@@ -94,6 +114,14 @@ def create_application(dataplane: OpenAIDataPlane) -> FastAPI:
         if isinstance(response, bytes):
             return Response(content=response, headers=response_headers, media_type="application/octet-stream")
         response_headers.pop("content-type", None)
+        # JSON-only responses go through the reference's pydantic `InferenceResponse` (v2_datamodels.py): fixed key order
+        # model_name, model_version, id, parameters, outputs[name, shape, datatype, parameters, data], absent values as
+        # null (byte strings pinned by test_server.py:591-632, :744-778)
+        if isinstance(response, dict) and "outputs" in response:
+            response = {"model_name": response.get("model_name"), "model_version": response.get("model_version"),
+                        "id": response.get("id"), "parameters": response.get("parameters"),
+                        "outputs": [{"name": o.get("name"), "shape": o.get("shape"), "datatype": o.get("datatype"),
+                                     "parameters": o.get("parameters"), "data": o.get("data")} for o in response["outputs"]]}
         return JSONResponse(content=response, headers=response_headers)
 
     # ---- error handlers (rest/server.py:134-145)
