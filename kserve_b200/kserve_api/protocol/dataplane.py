@@ -11,7 +11,7 @@ from ..model import BaseKServeModel, InferenceModel
 from ..model_repository import ModelRepository
 from .infer_type import InferRequest, InferResponse
 
-SERVER_NAME = "kserve-b200"
+SERVER_NAME = "kserve"   # what GET /v2 reports in the reference (dataplane.py metadata(), test_dataplane.py:124-135)
 SERVER_VERSION = "0.1.0"
 
 
@@ -44,10 +44,8 @@ class DataPlane:
         return {"status": "alive"}
 
     async def ready(self) -> bool:
-        models = self._model_registry.get_models().values()
-        for m in models:
-            if not await m.healthy():
-                return False
+        """dataplane.py:247-279: the server readiness probe answers True whatever the readiness of the registered models
+        (those have their own probes); only a transformer in front of a remote predictor forwards the question."""
         return True
 
     def metadata(self) -> Dict:

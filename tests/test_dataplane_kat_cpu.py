@@ -1,0 +1,83 @@
+"""DataPlane behaviour, restating the non-CloudEvent scenarios of the reference's
+python/kserve/test/test_dataplane.py:83-165 and :425-455: registry lookups and their error text, liveness / readiness
+semantics, metadata shapes, decode -> infer / explain -> encode, and the type gate that keeps OpenAI-only models off
+the V1/V2 inference routes."""
+import asyncio
+
+import pytest
+
+from kserve_b200.kserve_api import Model
+from kserve_b200.kserve_api.errors import ModelNotFound
+from kserve_b200.kserve_api.model_repository import ModelRepository
+from kserve_b200.kserve_api.protocol.dataplane import DataPlane
+from kserve_b200.kserve_api.protocol.rest.openai.openai_model import OpenAIGenerativeModel
+
+
+class Dummy(Model):
+    def __init__(self, name):
+        super().__init__(name)
+        self.ready = False
+
+    def load(self):
+        self.ready = True
+
+    async def predict(self, request, headers=None):
+        return {"predictions": request["inputs"] if "inputs" in request else request["instances"]}
+
+    async def explain(self, request, headers=None):
+        return {"predictions": request["inputs"] if "inputs" in request else request["instances"]}
+
+
+def _dp_with_model(name="TestModel"):
+    dp = DataPlane(model_registry=ModelRepository())
+    m = Dummy(name)
+    m.load()
+    dp._model_registry.update(m)
+    return dp
+
+
+def test_registry_lookup_and_error_text():
+    dp = DataPlane(model_registry=ModelRepository())
+    with pytest.raises(ModelNotFound) as e:
+        dp.get_model_from_registry("FakeModel")
+    assert e.value.reason == "Model with name FakeModel does not exist."
+    dp = _dp_with_model("Model")
+    assert dp.get_model_from_registry("Model").name == "Model"
+
+
+def test_liveness_and_readiness_semantics():
+    assert asyncio.run(DataPlane.live()) == {"status": "alive"}
+    dp = _dp_with_model()
+    dp._model_registry.update(Dummy("NotReadyModel"))          # registered but never loaded
+    assert asyncio.run(dp.ready()) is True                     # server readiness ignores the models' readiness
+    assert asyncio.run(dp.model_ready("TestModel")) is True
+    assert asyncio.run(dp.model_ready("NotReadyModel")) is False
+
+
+def test_metadata_shapes():
+    dp = _dp_with_model()
+    md = dp.metadata()
+    assert md["name"] == "kserve" and md["extensions"] == ["model_repository_extension"] and isinstance(md["version"], str)
+    assert asyncio.run(dp.model_metadata("TestModel")) == {"name": "TestModel", "platform": "", "inputs": [], "outputs": []}
+
+
+def test_decode_infer_explain_encode():
+    dp = _dp_with_model()
+    for call in (dp.infer, dp.explain):
+        req, attrs = dp.decode(b'{"instances":[[1,2]]}', None)
+        resp, headers = asyncio.run(call("TestModel", req))
+        assert dp.encode("TestModel", resp, headers, attrs) == ({"predictions": [[1, 2]]}, {})
+
+
+def test_openai_only_models_are_not_inference_models():
+    class OnlyOpenAI(OpenAIGenerativeModel):
+        async def create_completion(self, params):
+            pass
+
+        async def create_chat_completion(self, params):
+            pass
+    repo = ModelRepository()
+    repo.update(OnlyOpenAI("TestModel"))
+    with pytest.raises(ValueError) as e:
+        asyncio.run(DataPlane(model_registry=repo).infer(model_name="TestModel", request={}))
+    assert e.value.args[0] == "Model of type OnlyOpenAI does not support inference"
