@@ -81,3 +81,29 @@ def test_openai_only_models_are_not_inference_models():
     with pytest.raises(ValueError) as e:
         asyncio.run(DataPlane(model_registry=repo).infer(model_name="TestModel", request={}))
     assert e.value.args[0] == "Model of type OnlyOpenAI does not support inference"
+
+
+def test_model_repository_scenarios():
+    """python/kserve/test/test_model_repository.py:55-135: aliases, OpenAI-only models, readiness of unknown / unloaded
+    models (an OpenAI model without a load step counts as ready)."""
+    repo = ModelRepository()
+    m = Model(name="kserve-model")
+    repo.update(m)
+    assert repo.get_model("kserve-model") is m and m.name == "kserve-model"
+    repo.update(m, name="additional-model-name")
+    assert repo.get_model("additional-model-name") is m
+    assert asyncio.run(repo.is_model_ready("none-model")) is False
+    assert asyncio.run(repo.is_model_ready("kserve-model")) is False
+    m.load()
+    assert asyncio.run(repo.is_model_ready("kserve-model")) is True
+
+    class OnlyOpenAI(OpenAIGenerativeModel):
+        async def create_completion(self, params):
+            pass
+
+        async def create_chat_completion(self, params):
+            pass
+    o = OnlyOpenAI(name="openai-model")
+    repo.update(o)
+    assert isinstance(repo.get_model("openai-model"), OpenAIGenerativeModel)
+    assert asyncio.run(repo.is_model_ready("openai-model")) is True
