@@ -28,7 +28,9 @@ class OpenAIEndpoints:
             return JSONResponse(content=result.model_dump(), status_code=int(result.error.code))
         if isinstance(result, AsyncGenerator):
             return StreamingResponse(result, media_type="text/event-stream")
-        return JSONResponse(content=result.model_dump(exclude_none=True))
+        # the routes are registered with response_model_exclude_none / response_model_exclude_unset (endpoints.py:262-275):
+        # only fields the model set explicitly (and that are not None) reach the client
+        return JSONResponse(content=result.model_dump(exclude_none=True, exclude_unset=True))
 
     async def create_completion(self, request_body: CompletionRequest, raw_request: Request, response: Response):
         model_name = request_body.model
@@ -49,10 +51,18 @@ class OpenAIEndpoints:
         return await self._respond(completion)
 
     async def models(self):
-        return (await self.dataplane.models()).model_dump()
+        """endpoints.py:227-244: {"object": "list", "data": [{"object": "model", "id", "created" (server start), "owned_by": ""}]}"""
+        cards = (await self.dataplane.models()).data
+        return {"object": "list", "data": [{"id": c.id, "object": "model", "created": self.start_time, "owned_by": ""} for c in cards]}
 
-    async def health(self):
-        return Response(status_code=200)
+    async def health(self, model_name: str):
+        """GET {prefix}/v1/models/{model_name} (endpoints.py:246-253): 200 when the model is ready, ModelNotReady (503) otherwise"""
+        try:
+            ready = await self.dataplane.model_ready(model_name)
+        except Exception as e:
+            raise ModelNotReady(model_name) from e
+        if not ready:
+            raise ModelNotReady(model_name)
 
 
 def register_openai_endpoints(app: FastAPI, dataplane: OpenAIDataPlane):
@@ -61,6 +71,6 @@ def register_openai_endpoints(app: FastAPI, dataplane: OpenAIDataPlane):
     router.add_api_route("/v1/completions", ep.create_completion, methods=["POST"], response_model_exclude_none=True)
     router.add_api_route("/v1/chat/completions", ep.create_chat_completion, methods=["POST"], response_model_exclude_none=True)
     router.add_api_route("/v1/models", ep.models, methods=["GET"])
-    router.add_api_route("/health", ep.health, methods=["GET"])
+    router.add_api_route("/v1/models/{model_name}", ep.health, methods=["GET"])
     app.include_router(router)
     app.add_exception_handler(OpenAIError, openai_error_handler)

@@ -57,13 +57,13 @@ class OpenAIChatAdapterModel(OpenAIGenerativeModel):
     def completion_to_chat_completion(cls, completion: Completion, role: str) -> ChatCompletion:
         choices = [cls.to_chat_completion_choice(completion.choices[0], role)] if completion.choices else []
         return ChatCompletion(id=completion.id, choices=choices, created=completion.created, model=completion.model,
-                              system_fingerprint=completion.system_fingerprint, usage=completion.usage)
+                              object="chat.completion", system_fingerprint=completion.system_fingerprint, usage=completion.usage)
 
     @classmethod
     def completion_to_chat_completion_chunk(cls, completion: CompletionChunk, role: str) -> ChatCompletionChunk:
         choices = [cls.to_chat_completion_chunk_choice(completion.choices[0], role)] if completion.choices else []
-        return ChatCompletionChunk(id=completion.id, choices=choices, created=completion.created,
-                                   model=completion.model, system_fingerprint=completion.system_fingerprint)
+        return ChatCompletionChunk(id=completion.id, choices=choices, created=completion.created, model=completion.model,
+                                   object="chat.completion.chunk", system_fingerprint=completion.system_fingerprint)
 
     async def create_chat_completion(self, request: ChatCompletionRequest, raw_request: Optional[Request] = None,
                                      context: Optional[Dict[str, Any]] = None

@@ -51,7 +51,7 @@ class DummyOpenAI(OpenAIChatAdapterModel):
                         CompletionChunkChoice(index=0, text=piece, finish_reason="length")]).model_dump_json() + "\n\n"
                 yield "data: [DONE]\n\n"
             return gen()
-        return Completion(id="cmpl-1", model=request.model, choices=[CompletionChoice(index=0, text=text, finish_reason="length")],
+        return Completion(id="cmpl-1", model=request.model, object="text_completion", created=1, choices=[CompletionChoice(index=0, text=text, finish_reason="length")],
                           usage=UsageInfo(prompt_tokens=4, completion_tokens=7, total_tokens=11))
 
 
@@ -148,7 +148,7 @@ def test_openai_streaming_sse_and_chat_mapping(client):
     assert len({c["id"] for c in chunks}) == 1 and all(c["choices"][0]["finish_reason"] == "length" for c in chunks)
     chat = {"model": "gpt", "messages": [{"role": "user", "content": "yo"}]}
     j = client.post("/openai/v1/chat/completions", json=chat).json()
-    assert j["object"] == "chat.completion" and j["choices"][0]["message"] == {"role": "assistant", "content": "echo:<|user|>yo\n", "tool_calls": []}
+    assert j["object"] == "chat.completion" and j["choices"][0]["message"] == {"role": "assistant", "content": "echo:<|user|>yo\n"}   # unset fields are excluded on the wire
     with client.stream("POST", "/openai/v1/chat/completions", json={**chat, "stream": True}) as r:
         lines = [l for l in r.iter_lines() if l]
     assert lines[-1] == "data: [DONE]"
