@@ -25,7 +25,7 @@ from .engine import B200Engine, GenerateResult
 from .kserve_api.errors import InvalidInput
 from .kserve_api.metrics import DECODE_TOKENS_PER_S, LLM_STATS_KEY, TTFT_HIST, LLMStats, get_labels
 from .kserve_api.model import Model
-from .kserve_api.protocol.infer_type import InferInput, InferOutput, InferRequest, InferResponse
+from .kserve_api.protocol.infer_type import InferOutput, InferRequest, InferResponse
 from .kserve_api.protocol.rest.openai.errors import OpenAIError
 from .kserve_api.protocol.rest.openai.openai_chat_adapter_model import OpenAIChatAdapterModel
 from .kserve_api.protocol.rest.openai.openai_model import ChatPrompt

@@ -7,11 +7,11 @@ import logging
 import time
 from abc import ABC, abstractmethod
 from enum import Enum
-from typing import Awaitable, Dict, List, Optional, Union
+from typing import Dict, List, Optional
 
 from .errors import InvalidInput
 from .metrics import EXPLAIN_HIST_TIME, POST_HIST_TIME, PRE_HIST_TIME, PREDICT_HIST_TIME, get_labels
-from .protocol.infer_type import InferRequest, InferResponse
+from .protocol.infer_type import InferRequest
 
 trace_logger = logging.getLogger("kserve.trace")
 

@@ -6,8 +6,7 @@ from __future__ import annotations
 import argparse
 import asyncio
 import logging
-import signal
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 from .model import BaseKServeModel
 from .model_repository import ModelRepository

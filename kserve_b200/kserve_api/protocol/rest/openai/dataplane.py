@@ -1,5 +1,5 @@
 """OpenAIDataPlane (mirrors python/kserve/kserve/protocol/rest/openai/dataplane.py:41-177)."""
-from typing import AsyncGenerator, Optional, Union
+from typing import AsyncGenerator, Union
 
 from fastapi import Request, Response
 

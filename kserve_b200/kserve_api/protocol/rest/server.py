@@ -2,7 +2,7 @@
 python/kserve/kserve/protocol/rest/server.py:56-189, v1_endpoints.py:33-174, v2_endpoints.py:35-305)."""
 from __future__ import annotations
 
-from typing import AsyncIterator, Optional
+from typing import AsyncIterator
 
 from fastapi import FastAPI, Request, Response
 from fastapi.responses import JSONResponse, StreamingResponse
@@ -10,7 +10,6 @@ from prometheus_client import CONTENT_TYPE_LATEST, generate_latest
 
 from ... import errors as E
 from ..dataplane import DataPlane
-from ..infer_type import InferResponse
 from .openai.dataplane import OpenAIDataPlane
 from .openai.endpoints import register_openai_endpoints
 from .openai.openai_model import OpenAIModel

@@ -8,8 +8,8 @@ New(32, 50), defaults 32/5000 for New(-1,-1)) is replayed against this restateme
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import Any, Callable, Dict, List, Optional, Tuple
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple
 
 SLEEP_US = 100               # handler.go:34
 MAX_BATCH_SIZE = 32          # :35

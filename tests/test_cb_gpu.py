@@ -8,7 +8,6 @@ import asyncio
 import os
 
 import pytest
-import torch
 
 from helpers import GOLDEN, load_case, logits_tol, make_engine
 

@@ -3,7 +3,6 @@ transformers' TextIteratorStreamer piece by piece, and BASELINE.json configs[0] 
 batch 1, 32-token generate through /openai/v1/completions — runs through this repo's server plumbing with the
 oracle as the (test-only) backend."""
 import asyncio
-import json
 import os
 from threading import Thread
 

@@ -7,9 +7,9 @@ import numpy as np
 import pytest
 from fastapi.testclient import TestClient
 
-from kserve_b200.kserve_api import InferInput, InferRequest, InferResponse, Model, ModelServer
+from kserve_b200.kserve_api import InferInput, InferRequest, Model, ModelServer
 from kserve_b200.kserve_api.errors import InvalidInput
-from kserve_b200.kserve_api.protocol.infer_type import InferOutput, get_predict_input, get_predict_response
+from kserve_b200.kserve_api.protocol.infer_type import get_predict_input, get_predict_response
 from kserve_b200.kserve_api.protocol.rest.openai.errors import OpenAIError
 from kserve_b200.kserve_api.protocol.rest.openai.openai_chat_adapter_model import OpenAIChatAdapterModel
 from kserve_b200.kserve_api.protocol.rest.openai.openai_model import ChatPrompt

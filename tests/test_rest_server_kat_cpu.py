@@ -10,8 +10,7 @@ import pytest
 from fastapi.testclient import TestClient
 
 from kserve_b200.kserve_api import Model, ModelServer
-from kserve_b200.kserve_api.protocol.infer_type import (InferInput, InferOutput, InferRequest, InferResponse, RequestedOutput,
-                                                        get_predict_input, get_predict_response)
+from kserve_b200.kserve_api.protocol.infer_type import (InferInput, InferRequest, RequestedOutput, get_predict_input, get_predict_response)
 
 HDR = "inference-header-content-length"
 
