@@ -147,3 +147,73 @@ def test_cancelled_requests_leave_the_batch_and_free_their_slots():
     r = _run(cb, main())
     assert r.output_ids.tolist() == [[2, 2000, 2001, 2002, 2003]]
     assert cb.stats["cancelled"] >= 1
+
+
+def test_randomised_arrivals_keep_every_invariant():
+    """200 requests with random sizes, lengths, EOS positions, stop sequences and a few cancellations: every finished
+    request returns exactly the prefix of its script that the reference semantics dictate, no slot leaks."""
+    import random
+    rng = random.Random(7)
+    EOS = 9999
+    scripts, specs = {}, []
+    for i in range(200):
+        rows = rng.choice([1, 1, 1, 2, 3])
+        max_new = rng.randint(1, 40)
+        prompts = []
+        for r in range(rows):
+            key = (i, r)
+            sc = [rng.randint(10, 500) for _ in range(64)]
+            if rng.random() < 0.3:
+                sc[rng.randint(0, 45)] = EOS
+            scripts[key] = sc
+            prompts.append(list(key))
+        stop = []
+        if rng.random() < 0.25:
+            k = rng.randint(0, 30)
+            stop = [scripts[(i, 0)][k:k + 2]]
+        specs.append((prompts, max_new, stop, rng.random() < 0.05))
+    eng = ScriptedEngine(8, scripts, step_delay=0.0002)
+    cb = ContinuousBatcher(eng, pad_token_id=0, eos_token_ids=[EOS], steps_per_poll=3)
+
+    def expected(prompts, max_new, stop):
+        outs, stop_at = [], None
+        for p in prompts:
+            sc, o = scripts[tuple(p)], []
+            for t in sc[:max_new]:
+                o.append(t)
+                if t == EOS:
+                    break
+                if stop and len(o) >= 2 and o[-2:] == stop[0]:
+                    stop_at = len(o) if stop_at is None else min(stop_at, len(o))
+                    break
+            outs.append(o)
+        if stop_at is not None:
+            n = stop_at
+            outs = [o[:n] for o in outs]
+        else:
+            n = max(len(o) for o in outs)
+        return [o + [0] * (n - len(o)) for o in outs], stop_at is not None
+
+    async def one(spec):
+        prompts, max_new, stop, cancel = spec
+        t = asyncio.create_task(cb.submit(prompts, torch.tensor(prompts), max_new, stop))
+        if cancel:
+            await asyncio.sleep(0.001)
+            t.cancel()
+        try:
+            return await t
+        except asyncio.CancelledError:
+            return None
+
+    async def main():
+        return await asyncio.gather(*[one(s) for s in specs])
+    results = _run(cb, main())
+    done = 0
+    for spec, r in zip(specs, results):
+        if r is None:
+            continue
+        want, stopped = expected(*spec[:3])
+        assert r.output_ids[:, 2:].tolist() == want and r.stop_triggered == stopped and r.num_generated == len(want[0])
+        done += 1
+    assert done >= 180 and cb.free_slots == 8 and not eng.slots
+    assert cb.stats["finished"] + cb.stats["cancelled"] >= done
