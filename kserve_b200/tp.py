@@ -37,4 +37,8 @@ def follower_loop(model) -> int:
         if method == "stop":
             model.stop()
             return 0
-        getattr(model._engine, method)(*args, **kwargs)
+        try:
+            getattr(model._engine, method)(*args, **kwargs)
+        except Exception as e:   # request-level errors (validation inside the engine) are raised on every rank alike:
+            # the leader reports them to the client, the followers must stay in the loop for the next request
+            print(f"[kserve_b200 rank {dist.get_rank()}] {method} failed: {e}", flush=True)

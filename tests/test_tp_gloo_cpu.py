@@ -109,3 +109,47 @@ def test_tp2_sharding_matches_unsharded_oracle():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, 29611, ret), nprocs=2, join=True)
     assert ret["tp"] == ret["ref"]
+
+
+class _FakeEngine:
+    """records the calls replayed on a follower; `generate` with max_new_tokens < 1 fails like the C ABI does"""
+    def __init__(self):
+        self.calls = []
+
+    def generate(self, ids, mask, **kw):
+        if kw.get("max_new_tokens", 1) < 1:
+            raise RuntimeError("max_new_tokens must be >= 1")
+        self.calls.append(("generate", ids.tolist(), kw))
+
+
+class _FakeModel:
+    def __init__(self):
+        self._engine, self.stopped = _FakeEngine(), False
+
+    def stop(self):
+        self.stopped = True
+
+
+def _cmd_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kserve_b200.tp import follower_loop, leader_call
+    if rank == 0:
+        leader_call("generate", (torch.tensor([[1, 2, 3]]), None), dict(max_new_tokens=4, pad_token_id=0))
+        leader_call("generate", (torch.tensor([[7]]), None), dict(max_new_tokens=0))       # fails on every rank alike
+        leader_call("generate", (torch.tensor([[9, 9]]), None), dict(max_new_tokens=2))
+        leader_call("stop", (), {})
+    else:
+        m = _FakeModel()
+        rc = follower_loop(m)
+        ret["calls"] = [(c[0], c[1], c[2]["max_new_tokens"]) for c in m._engine.calls]
+        ret["rc"], ret["stopped"] = rc, m.stopped
+    dist.destroy_process_group()
+
+
+def test_follower_replays_leader_calls_and_survives_request_errors():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cmd_worker, args=(2, 29612, ret), nprocs=2, join=True)
+    assert ret["calls"] == [("generate", [[1, 2, 3]], 4), ("generate", [[9, 9]], 2)]
+    assert ret["rc"] == 0 and ret["stopped"] is True
