@@ -42,7 +42,8 @@ def main(argv=None):
     if rank != 0:
         from .tp import follower_loop
         return follower_loop(model)
-    ModelServer(http_port=args.http_port, enable_latency_logging=args.enable_latency_logging).start([model])
+    ModelServer(http_port=args.http_port, enable_latency_logging=args.enable_latency_logging, grpc_port=args.grpc_port,
+                enable_grpc=args.enable_grpc).start([model])
 
 
 if __name__ == "__main__":

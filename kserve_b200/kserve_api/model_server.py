@@ -1,6 +1,6 @@
 """ModelServer (mirrors python/kserve/kserve/model_server.py:48-461): argparse flags, model registration,
-uvicorn REST server on --http_port.  gRPC and multi-process workers are outside this runtime's scope
-(one engine per GPU)."""
+uvicorn REST server on --http_port and, with --enable_grpc, the Open Inference Protocol gRPC service on --grpc_port
+(protocol/grpc/).  Multi-process workers are outside this runtime's scope (one engine per GPU)."""
 from __future__ import annotations
 
 import argparse
@@ -14,9 +14,12 @@ from .protocol.rest.openai.dataplane import OpenAIDataPlane
 from .protocol.rest.server import create_application
 
 DEFAULT_HTTP_PORT = 8080
+DEFAULT_GRPC_PORT = 8081
 
 parser = argparse.ArgumentParser(add_help=False)
 parser.add_argument("--http_port", default=DEFAULT_HTTP_PORT, type=int, help="The HTTP Port listened to by the model server.")
+parser.add_argument("--grpc_port", default=DEFAULT_GRPC_PORT, type=int, help="The gRPC Port listened to by the model server.")
+parser.add_argument("--enable_grpc", default=False, type=lambda x: str(x).lower() == "true", help="Enable the gRPC server.")
 parser.add_argument("--workers", default=1, type=int, help="Only 1 is supported: one CUDA engine per GPU.")
 parser.add_argument("--enable_latency_logging", default=True, type=lambda x: str(x).lower() == "true")
 parser.add_argument("--log_config_file", default=None, type=str)
@@ -31,10 +34,12 @@ logger = logging.getLogger("kserve")
 class ModelServer:
     def __init__(self, http_port: int = DEFAULT_HTTP_PORT, workers: int = 1,
                  registered_models: Optional[ModelRepository] = None, enable_latency_logging: bool = True,
-                 access_log_format: Optional[str] = None):
+                 access_log_format: Optional[str] = None, grpc_port: int = DEFAULT_GRPC_PORT, enable_grpc: bool = False):
         if workers != 1:
             raise ValueError("kserve_b200 runs one engine per GPU: --workers must be 1")
         self.http_port = http_port
+        self.grpc_port, self.enable_grpc = grpc_port, enable_grpc
+        self._grpc_server = None
         self.registered_models = registered_models or ModelRepository()
         self.enable_latency_logging = enable_latency_logging
         self.access_log_format = access_log_format
@@ -71,9 +76,16 @@ class ModelServer:
         for m in models:
             if m.engine:
                 await m.start_engine()
+        if self.enable_grpc:
+            from .protocol.grpc import GRPCServer
+            self._grpc_server = await GRPCServer(self.grpc_port, self.dataplane).start()
         cfg = uvicorn.Config(app, host="0.0.0.0", port=self.http_port, log_level="info", access_log=True)
         self._server = uvicorn.Server(cfg)
-        await self._server.serve()
+        try:
+            await self._server.serve()
+        finally:
+            if self._grpc_server is not None:
+                await self._grpc_server.stop()
 
     def start(self, models: List[BaseKServeModel]):
         """model_server.py:332-377"""
