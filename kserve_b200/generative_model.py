@@ -477,6 +477,9 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
             raise OpenAIError("chat completions need a tokenizer with a chat template")
         conversation = [{"role": m.role, "content": m.content if isinstance(m.content, str) else
                          "".join(p.get("text", "") for p in (m.content or []))} for m in request.messages]
+        if request.chat_template is None and getattr(self._tokenizer, "chat_template", None) is None:    # :495-500
+            raise OpenAIError("As of transformers v4.44, default chat template is no longer allowed, so you must provide a chat "
+                              "template if the tokenizer does not define one.")
         kwargs = dict(request.chat_template_kwargs or {})
         prompt = self._tokenizer.apply_chat_template(
             conversation=conversation, chat_template=request.chat_template, tokenize=False,

@@ -39,3 +39,20 @@ def test_checkpoint_defaults_fill_the_none_fields():
     m2 = _model({"do_sample": True, "top_k": 0, "repetition_penalty": 1.1})
     g = m2.build_generation_config(_req(seed=1))
     assert g["top_k"] == 1024 and g["repetition_penalty"] == 1.1 and g["temperature"] == 1.0 and g["top_p"] == 1.0
+
+
+def test_chat_template_is_required_like_the_reference():
+    """generative_model.py:495-500: no template on the request and none in the tokenizer -> OpenAIError with this text"""
+    import pytest
+    from kserve_b200.kserve_api.protocol.rest.openai.errors import OpenAIError
+    from kserve_b200.kserve_api.protocol.rest.openai.types import ChatCompletionRequest
+    m = _model()
+    m._tokenizer = SimpleNamespace(chat_template=None)
+    req = ChatCompletionRequest.model_validate({"model": "m", "messages": [{"role": "user", "content": "hi"}]})
+    with pytest.raises(OpenAIError) as e:
+        m.apply_chat_template(req)
+    assert "default chat template is no longer allowed" in str(e.value)
+    calls = {}
+    m._tokenizer = SimpleNamespace(chat_template="{{x}}", apply_chat_template=lambda **kw: calls.update(kw) or "PROMPT")
+    assert m.apply_chat_template(req).prompt == "PROMPT"
+    assert calls["tokenize"] is False and calls["conversation"] == [{"role": "user", "content": "hi"}]
