@@ -270,6 +270,17 @@ class InferRequest:
         raw = json.dumps(d, separators=(",", ":")).encode()
         return cls.from_bytes(raw, len(raw), model_name)
 
+    def as_dataframe(self):
+        """one column per input tensor, named after it (infer_type.py:849-864)"""
+        import pandas as pd
+        dfs = []
+        for t in self.inputs:
+            data = t.data if t._raw_data is None and t.data is not None else t.as_numpy().reshape(-1).tolist()
+            if t.datatype == "BYTES":
+                data = [str(v, "utf-8") if isinstance(v, (bytes, bytearray)) else v for v in data]
+            dfs.append(pd.DataFrame(data, columns=[t.name]))
+        return pd.concat(dfs, axis=1)
+
     def get_input_by_name(self, name: str) -> Optional[InferInput]:
         for i in self.inputs:
             if i.name == name:
@@ -376,24 +387,58 @@ def _contains_fp16_datatype(infer_response: InferResponse) -> bool:
     return any(o.datatype == "FP16" for o in infer_response.outputs)
 
 
-def get_predict_input(payload: Union[Dict, InferRequest]):
-    """kserve/utils/utils.py:149-192 — V1 dict ``instances`` or V2 InferRequest -> numpy."""
+def get_predict_input(payload: Union[Dict, InferRequest], columns: Optional[List] = None):
+    """kserve/utils/utils.py:149-192 — V1 dict (`instances` / `inputs`) or V2 InferRequest -> what the model code consumes:
+    a numpy array, a list of str (string instances / a BYTES tensor sent as JSON strings), or a pandas DataFrame (V1
+    instances that are dicts; V2 requests with parameters.content_type == "pd")."""
     if isinstance(payload, dict):
         inst = payload["inputs"] if "inputs" in payload else payload["instances"]
+        if len(inst) == 0:
+            return np.array(inst)
+        first = inst[0]
+        if isinstance(first, dict) or (isinstance(first, list) and len(first) != 0 and isinstance(first[0], dict)):
+            import pandas as pd
+            return pd.concat([pd.DataFrame(i, columns=columns) for i in inst], axis=0)
+        if isinstance(first, str):
+            return inst
         return np.array(inst)
     if isinstance(payload, InferRequest):
-        if len(payload.inputs) == 1:
-            return payload.inputs[0].as_numpy()
-        return {i.name: i.as_numpy() for i in payload.inputs}
+        ct = (payload.parameters or {}).get("content_type")
+        if ct is not None and not isinstance(ct, str):          # gRPC hands over an InferParameter
+            ct = getattr(ct, "string_param", None)
+        if ct == "pd":
+            return payload.as_dataframe()
+        t = payload.inputs[0]
+        if t.datatype == "BYTES" and t._raw_data is None and isinstance(t.data, list) and len(t.data) > 0 and isinstance(t.data[0], str):
+            return t.data
+        return t.as_numpy()
     raise InvalidInput(f"unsupported payload type {type(payload)}")
 
 
-def get_predict_response(payload, result: Union[np.ndarray, Dict[str, np.ndarray]], model_name: str):
-    """kserve/utils/utils.py:194-254 — numpy -> V1 dict or V2 InferResponse mirroring the request's encoding."""
+def get_predict_response(payload, result, model_name: str):
+    """kserve/utils/utils.py:194-254 — model result -> V1 dict or V2 InferResponse mirroring the request's encoding.  `result`:
+    numpy array, list, list of str (-> one BYTES tensor), pandas DataFrame (one output per column), or — an extension the
+    runtime model uses — a dict name -> array."""
+    try:
+        import pandas as pd
+        is_df = isinstance(result, pd.DataFrame)
+    except ImportError:                                          # pragma: no cover
+        is_df = False
     if isinstance(payload, dict):
+        if is_df:
+            return {"predictions": [row.to_dict() for _, row in result.iterrows()]}
         return {"predictions": result.tolist() if isinstance(result, np.ndarray) else result}
+    if not isinstance(payload, InferRequest):
+        raise InvalidInput(f"unsupported payload type {type(payload)}")
+    if is_df:
+        items = [(col, result[col].to_numpy()) for col in result.columns]
+    elif isinstance(result, dict):
+        items = list(result.items())
+    elif isinstance(result, list) and len(result) > 0 and isinstance(result[0], str):
+        items = [("output-0", np.array(result, dtype=np.object_))]
+    else:
+        items = [("output-0", np.array(result) if isinstance(result, list) else result)]
     outs = []
-    items = result.items() if isinstance(result, dict) else [("output-0", result)]
     for name, arr in items:
         o = InferOutput(name, list(arr.shape), from_np_dtype(arr.dtype))
         o.data = arr

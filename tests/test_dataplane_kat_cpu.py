@@ -107,3 +107,32 @@ def test_model_repository_scenarios():
     repo.update(o)
     assert isinstance(repo.get_model("openai-model"), OpenAIGenerativeModel)
     assert asyncio.run(repo.is_model_ready("openai-model")) is True
+
+
+def test_predict_input_and_response_helpers():
+    """kserve/utils/utils.py:149-254: the payload forms custom models consume / return"""
+    import numpy as np
+    import pandas as pd
+    from kserve_b200.kserve_api.protocol.infer_type import (InferInput, InferRequest, get_predict_input, get_predict_response)
+    assert get_predict_input({"instances": [[1, 2], [3, 4]]}).tolist() == [[1, 2], [3, 4]]
+    assert get_predict_input({"inputs": ["a", "b"]}) == ["a", "b"]
+    assert get_predict_input({"instances": []}).shape == (0,)
+    df = get_predict_input({"instances": [{"a": [1], "b": [2]}, {"a": [3], "b": [4]}]})
+    assert isinstance(df, pd.DataFrame) and df["a"].tolist() == [1, 3] and df["b"].tolist() == [2, 4]
+    req = InferRequest(model_name="m", request_id="1", infer_inputs=[InferInput("x", [2], "INT32", data=[5, 6]),
+                                                                     InferInput("s", [2], "BYTES", data=["u", "v"])])
+    assert get_predict_input(req).tolist() == [5, 6]
+    req.parameters = {"content_type": "pd"}
+    df = get_predict_input(req)
+    assert list(df.columns) == ["x", "s"] and df["s"].tolist() == ["u", "v"]
+    assert get_predict_input(InferRequest(model_name="m", infer_inputs=[InferInput("s", [2], "BYTES", data=["u", "v"])])) == ["u", "v"]
+    # responses
+    assert get_predict_response({"instances": []}, np.array([[1, 2]]), "m") == {"predictions": [[1, 2]]}
+    assert get_predict_response({"instances": []}, pd.DataFrame({"a": [1, 2]}), "m") == {"predictions": [{"a": 1}, {"a": 2}]}
+    r = get_predict_response(req, pd.DataFrame({"p": np.array([1.5, 2.5], dtype=np.float32), "q": np.array([1, 2], dtype=np.int64)}), "m")
+    assert [(o.name, o.datatype, o.shape) for o in r.outputs] == [("p", "FP32", [2]), ("q", "INT64", [2])] and r.id == "1"
+    r = get_predict_response(req, ["cat", "dog"], "m")
+    assert (r.outputs[0].name, r.outputs[0].datatype, r.outputs[0].shape) == ("output-0", "BYTES", [2])
+    assert r.to_rest()[0]["outputs"][0]["data"] == ["cat", "dog"]
+    r = get_predict_response(req, [[1, 2], [3, 4]], "m")
+    assert r.outputs[0].shape == [2, 2] and r.outputs[0].datatype == "INT64"
