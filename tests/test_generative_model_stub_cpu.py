@@ -1,0 +1,155 @@
+"""The whole host path of the runtime model without a GPU: B200GenerativeModel wired to a scripted engine
+(`generate()` returns prompt + a deterministic continuation), driven through the REST routes, the V2 binary leg and gRPC.
+What the CUDA engine computes is covered by the `-m gpu` tests; this pins everything around it: tokenisation and left
+padding, usage accounting (q3), echo, stop -> finish_reason, SSE framing, chat re-wrap, V1 / V2 / gRPC envelopes."""
+import asyncio
+import json
+import os
+from threading import Thread
+
+import numpy as np
+import pytest
+import torch
+from fastapi.testclient import TestClient
+
+from helpers import GOLDEN
+from kserve_b200.engine import GenerateResult
+from kserve_b200.generative_model import B200GenerativeModel
+from kserve_b200.kserve_api import ModelServer
+
+
+class ScriptedEngine:
+    """continuation token k of a row = (last prompt token + 1 + k) mod 250 + 3: printable-ish bytes for the byte tokenizer"""
+    max_batch, max_seq_len = 8, 512
+
+    def __init__(self):
+        self.calls = []
+
+    def generate(self, ids, mask=None, *, max_new_tokens, pad_token_id=0, eos_token_ids=(), stop_sequences=(), streamer=None, **kw):
+        self.calls.append(dict(shape=tuple(ids.shape), mask=None if mask is None else mask.sum(1).tolist(), max_new=max_new_tokens,
+                               stops=[list(s) for s in stop_sequences], extra=kw))
+        last = ids[:, -1]
+        gen = torch.stack([(last + 1 + k) % 250 + 3 for k in range(max_new_tokens)], 1)
+        n, stopped = max_new_tokens, False
+        for k in range(1, max_new_tokens + 1):            # batch-wide stop sequences, like the device kernel
+            for s in stop_sequences:
+                if len(s) and k >= len(s) and any(gen[b, k - len(s):k].tolist() == list(s) for b in range(gen.shape[0])):
+                    n, stopped = k, True
+            if stopped:
+                break
+        gen = gen[:, :n]
+        if streamer is not None:
+            for k in range(n):
+                streamer(k, gen[:, k].tolist())
+        return GenerateResult(output_ids=torch.cat([ids, gen], 1), stop_triggered=stopped, num_generated=n, logits=None,
+                              prefill_ms=1.0, decode_ms=1.0, decode_steps=max(0, n - 1), kernel_launches=0)
+
+    def close(self):
+        pass
+
+
+@pytest.fixture(scope="module")
+def served():
+    from transformers import AutoTokenizer
+    tok = AutoTokenizer.from_pretrained(os.path.join(GOLDEN, "byte_tokenizer"), padding_side="left")
+    m = B200GenerativeModel("stub", model_config={"vocab_size": 257}, tokenizer=tok, max_model_len=512, max_batch=8)
+    # what load() sets up, minus the CUDA engine
+    if not tok.pad_token:
+        tok.add_special_tokens({"pad_token": "[PAD]"})
+    m._pad_token_id, m.eos_token_ids, m.generation_defaults, m.vocab_rows = tok.pad_token_id, [], {}, len(tok)
+    m._engine = ScriptedEngine()
+    m._thread = Thread(target=m._process_requests, daemon=True)
+    m._thread.start()
+    m.ready = True
+    with TestClient(ModelServer().create_application([m])) as client:
+        yield client, m, tok
+    m._request_queue.put(None)
+
+
+def _continuation(tok, prompt, n):
+    last = tok.encode(prompt)[-1]
+    return [(last + 1 + k) % 250 + 3 for k in range(n)]
+
+
+def test_completion_usage_echo_and_ragged_batch(served):
+    client, m, tok = served
+    prompts = ["Hello world", "a"]
+    r = client.post("/openai/v1/completions", json={"model": "stub", "prompt": prompts, "max_tokens": 5})
+    assert r.status_code == 200, r.text
+    j = r.json()
+    S = max(len(tok.encode(p)) for p in prompts)
+    assert j["usage"] == {"prompt_tokens": S * 2, "completion_tokens": 10, "total_tokens": S * 2 + 10}      # q3: pads are counted
+    assert [c["text"] for c in j["choices"]] == [tok.decode(_continuation(tok, p, 5), skip_special_tokens=True) for p in prompts]
+    assert all(c["finish_reason"] == "length" and "logprobs" not in c for c in j["choices"])
+    call = m._engine.calls[-1]
+    assert call["shape"] == (2, S) and call["mask"] == [len(tok.encode(p)) for p in prompts]              # left padded
+    e = client.post("/openai/v1/completions", json={"model": "stub", "prompt": "Hello", "max_tokens": 3, "echo": True}).json()
+    assert e["choices"][0]["text"].startswith("Hello")
+
+
+def test_stop_string_finish_reason_and_default_max_tokens(served):
+    client, m, tok = served
+    # a prompt whose continuation bytes survive decode -> encode (the byte tokenizer does not round-trip invalid UTF-8)
+    prompt = next(p for p in ("xy" + chr(c) for c in range(33, 100))
+                  if tok.encode(tok.decode(_continuation(tok, p, 16)[3:5]), add_special_tokens=False) == _continuation(tok, p, 16)[3:5])
+    cont = _continuation(tok, prompt, 16)
+    stop = tok.decode(cont[3:5])
+    j = client.post("/openai/v1/completions", json={"model": "stub", "prompt": prompt, "stop": stop}).json()
+    assert j["choices"][0]["finish_reason"] == "stop" and j["usage"]["completion_tokens"] == 5
+    assert m._engine.calls[-1]["stops"] == [tok.encode(stop, add_special_tokens=False)] and m._engine.calls[-1]["max_new"] == 16   # q1
+    j = client.post("/openai/v1/completions", json={"model": "stub", "prompt": "xyz", "max_tokens": None}).json()
+    assert j["usage"]["completion_tokens"] == 512 - 3                                                       # max_length - S (:563-564)
+
+
+def test_sse_stream_and_chat(served):
+    client, m, tok = served
+    whole = client.post("/openai/v1/completions", json={"model": "stub", "prompt": "abc", "max_tokens": 12}).json()["choices"][0]["text"]
+    with client.stream("POST", "/openai/v1/completions", json={"model": "stub", "prompt": "abc", "max_tokens": 12, "stream": True}) as r:
+        assert r.headers["content-type"].startswith("text/event-stream")
+        lines = [l for l in r.iter_lines() if l]
+    assert lines[-1] == "data: [DONE]"
+    chunks = [json.loads(l[6:]) for l in lines[:-1]]
+    assert "".join(c["choices"][0]["text"] for c in chunks) == whole and len({c["id"] for c in chunks}) == 1
+    chat = {"model": "stub", "messages": [{"role": "user", "content": "hi"}], "max_tokens": 4}
+    j = client.post("/openai/v1/chat/completions", json=chat).json()
+    assert j["object"] == "chat.completion" and j["choices"][0]["message"]["role"] == "assistant"
+    direct = client.post("/openai/v1/completions", json={"model": "stub", "prompt": "<|user|>hi\n<|assistant|>", "max_tokens": 4}).json()
+    assert j["choices"][0]["message"]["content"] == direct["choices"][0]["text"]
+
+
+def test_v1_v2_binary_and_grpc_envelopes(served):
+    client, m, tok = served
+    ids = np.array([[5, 6, 7], [8, 9, 10]], dtype=np.int64)
+    want = [[(int(r[-1]) + 1 + k) % 250 + 3 for k in range(4)] for r in ids]
+    r = client.post("/v1/models/stub:predict", json={"instances": ids.tolist(), "parameters": {"max_tokens": 4}})
+    assert r.status_code == 200 and r.json()["predictions"] == want
+    hdr = json.dumps({"inputs": [{"name": "input_ids", "shape": [2, 3], "datatype": "INT64", "parameters": {"binary_data_size": ids.nbytes}}],
+                      "parameters": {"max_tokens": 4, "binary_data_output": True}}).encode()
+    r = client.post("/v2/models/stub/infer", content=hdr + ids.tobytes(), headers={"Inference-Header-Content-Length": str(len(hdr))})
+    assert r.status_code == 200, r.text
+    n = int(r.headers["inference-header-content-length"])
+    out = json.loads(r.content[:n])["outputs"][0]
+    assert np.frombuffer(r.content[n:n + out["parameters"]["binary_data_size"]], dtype=np.int64).reshape(out["shape"]).tolist() == want
+
+    import grpc
+    from kserve_b200.kserve_api.model_repository import ModelRepository
+    from kserve_b200.kserve_api.protocol.grpc import GRPCServer, pb
+    from kserve_b200.kserve_api.protocol.rest.openai.dataplane import OpenAIDataPlane
+
+    async def call():
+        repo = ModelRepository()
+        repo.update(m)
+        srv = await GRPCServer(0, OpenAIDataPlane(model_registry=repo), host="127.0.0.1").start()
+        try:
+            async with grpc.aio.insecure_channel(f"127.0.0.1:{srv.bound_port}") as ch:
+                infer = ch.unary_unary(f"/{pb.SERVICE_NAME}/ModelInfer", request_serializer=pb.ModelInferRequest.SerializeToString,
+                                       response_deserializer=pb.ModelInferResponse.FromString)
+                return await infer(pb.ModelInferRequest(model_name="stub", id="9", parameters={"max_tokens": {"int64_param": 4}},
+                                                        inputs=[{"name": "input_ids", "shape": [2, 3], "datatype": "INT64"}],
+                                                        raw_input_contents=[ids.tobytes()]))
+        finally:
+            await srv.stop(0)
+    res = asyncio.run(call())
+    by = {o.name: i for i, o in enumerate(res.outputs)}
+    assert np.frombuffer(res.raw_output_contents[by["output_ids"]], dtype=np.int64).reshape(2, 4).tolist() == want
+    assert res.id == "9" and "text" in by
