@@ -424,18 +424,25 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                             put(piece)
                     put(None)
                 try:
-                    self._cb.submit_nowait(self._unpadded_rows(ids, mask), ids, request.max_tokens, stop_sequences, cb_done, on_tokens)
+                    cb_req = self._cb.submit_nowait(self._unpadded_rows(ids, mask), ids, request.max_tokens, stop_sequences, cb_done, on_tokens)
                 except ValueError as e:
                     raise OpenAIError(str(e))
             else:
+                cb_req = None
                 self._request_queue.put((run_stream, lambda r, e: None))
             completion = CompletionStreamer(request=request, generate_queue=out_q, stop_state=stop_state,
                                             system_fingerprint=self.system_fingerprint)
 
             async def stream_results() -> AsyncGenerator[str, None]:   # :612-617 SSE framing
-                async for partial in completion:
-                    yield f"data: {partial.model_dump_json()}\n\n"
-                yield "data: [DONE]\n\n"
+                finished = False
+                try:
+                    async for partial in completion:
+                        yield f"data: {partial.model_dump_json()}\n\n"
+                    finished = True
+                    yield "data: [DONE]\n\n"
+                finally:
+                    if not finished and cb_req is not None:     # the client went away mid-stream: free the slot
+                        self._cb.cancel(cb_req)
             return stream_results()
 
         r: GenerateResult = await self._agenerate(ids, mask, **common)

@@ -153,3 +153,78 @@ def test_v1_v2_binary_and_grpc_envelopes(served):
     by = {o.name: i for i, o in enumerate(res.outputs)}
     assert np.frombuffer(res.raw_output_contents[by["output_ids"]], dtype=np.int64).reshape(2, 4).tolist() == want
     assert res.id == "9" and "text" in by
+
+
+class ScriptedCbEngine(ScriptedEngine):
+    """the b200_cb_* surface with the same continuation rule, for the --continuous_batching wiring"""
+    def __init__(self):
+        super().__init__()
+        self.slots, self.released = {}, []
+
+    def cb_begin(self, pad, eos):
+        pass
+
+    def cb_end(self):
+        pass
+
+    def cb_admit(self, prompts, max_new, stops):
+        out = []
+        for p, m_, ss in zip(prompts, max_new, stops):
+            s = next(i for i in range(self.max_batch) if i not in self.slots)
+            self.slots[s] = dict(last=p[-1], out=[], max_new=m_, fin=False)
+            out.append(s)
+        self.cb_step(1)
+        return out
+
+    def cb_step(self, n):
+        import time
+        time.sleep(0.002 * n)
+        for _ in range(n):
+            for st in self.slots.values():
+                if not st["fin"]:
+                    st["out"].append((st["last"] + 1 + len(st["out"])) % 250 + 3)
+                    st["fin"] = len(st["out"]) >= st["max_new"]
+
+    def cb_poll(self):
+        get = lambda k, d: [self.slots[s][k] if s in self.slots else d for s in range(self.max_batch)]
+        return [len(x) if isinstance(x, list) else 0 for x in get("out", [])], [int(x) for x in get("fin", 0)], [0] * self.max_batch
+
+    def cb_read(self, slot, first=0, cap=4096):
+        return self.slots[slot]["out"][first:first + cap]
+
+    def cb_release(self, slot):
+        self.released.append(slot)
+        del self.slots[slot]
+
+
+def test_continuous_batching_wiring_and_stream_disconnect(served):
+    """--continuous_batching: completions and SSE streams go through the scheduler; a client that disconnects mid-stream
+    frees its slot (the reference cannot abort a running generate, q10)."""
+    from kserve_b200.continuous import ContinuousBatcher
+    client, m, tok = served
+    eng = ScriptedCbEngine()
+    cb = ContinuousBatcher(eng, pad_token_id=m._pad_token_id, steps_per_poll=2)
+    cb.start()
+    m._cb = cb
+    try:
+        j = client.post("/openai/v1/completions", json={"model": "stub", "prompt": ["Hello world", "a"], "max_tokens": 5}).json()
+        assert [c["text"] for c in j["choices"]] == [tok.decode(_continuation(tok, p, 5), skip_special_tokens=True) for p in ("Hello world", "a")]
+        assert j["usage"]["completion_tokens"] == 10
+        with client.stream("POST", "/openai/v1/completions", json={"model": "stub", "prompt": "abc", "max_tokens": 9, "stream": True}) as r:
+            lines = [l for l in r.iter_lines() if l]
+        assert lines[-1] == "data: [DONE]"
+        assert "".join(json.loads(l[6:])["choices"][0]["text"] for l in lines[:-1]) == tok.decode(_continuation(tok, "abc", 9), skip_special_tokens=True)
+        assert client.post("/openai/v1/completions", json={"model": "stub", "prompt": "x", "presence_penalty": 1.5}).status_code == 500
+
+        async def abandon():          # start a long stream, read one chunk, close the generator
+            from kserve_b200.kserve_api.protocol.rest.openai.types import CompletionRequest
+            gen = await m.create_completion(CompletionRequest(model="stub", prompt="abc", max_tokens=400, stream=True))
+            first = await gen.__anext__()
+            assert first.startswith("data: ")
+            await gen.aclose()
+            await asyncio.sleep(0.1)
+        asyncio.run(abandon())
+        assert cb.stats["cancelled"] == 1 and cb.free_slots == eng.max_batch and not eng.slots
+    finally:
+        m._cb = None
+        cb.stop()
