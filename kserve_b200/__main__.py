@@ -15,16 +15,25 @@ def main(argv=None):
     parser.add_argument("--model_dir", default="/mnt/models", help="HF checkpoint directory (config.json, *.safetensors, tokenizer)")
     parser.add_argument("--model_id", default=None, help="alias of --model_dir (no Hub access in this runtime)")
     parser.add_argument("--max_model_len", "--max_length", type=int, default=None)
-    parser.add_argument("--dtype", default="auto", choices=["auto", "bfloat16"], help="the B200 engine computes in bf16")
+    parser.add_argument("--dtype", default="auto", choices=["auto", "float16", "float32", "bfloat16", "float", "half"],
+                        help="the reference's choices (__main__.py:195-210); the B200 engine computes in bfloat16, which is what "
+                             "'auto' and 'bfloat16' select — the other values are refused at start-up rather than silently "
+                             "served at a different precision")
     parser.add_argument("--backend", default="b200", choices=["b200"])
     parser.add_argument("--max_batch", type=int, default=32)
     parser.add_argument("--continuous_batching", action="store_true",
                         help="iteration-level batching: requests join / leave the running decode batch between steps")
     parser.add_argument("--tensor_parallel_size", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
-    parser.add_argument("--enable_batcher", action="store_true", help="batch V1 :predict like the Go agent (--max-batchsize/--max-latency)")
-    parser.add_argument("--max-batchsize", dest="max_batchsize", type=int, default=32)
-    parser.add_argument("--max-latency", dest="max_latency", type=int, default=5000)
+    # the agent's flags (cmd/agent/main.go:66-68 --enable-batcher / --max-batchsize / --max-latency), same defaults
+    parser.add_argument("--enable_batcher", "--enable-batcher", dest="enable_batcher", action="store_true",
+                        help="install the request batcher in front of V1 :predict (pkg/batcher), formed batches run as one device-side concat/scatter call")
+    parser.add_argument("--max-batchsize", "--max_batchsize", dest="max_batchsize", type=int, default=32)
+    parser.add_argument("--max-latency", "--max_latency", dest="max_latency", type=int, default=5000)
     args, _ = parser.parse_known_args(argv)
+    if args.dtype not in ("auto", "bfloat16"):
+        parser.error(f"--dtype {args.dtype}: the B200 runtime computes in bfloat16 only (use --dtype auto or bfloat16)")
+    if args.enable_batcher and (args.max_batchsize <= 0 or args.max_latency <= 0):
+        parser.error("Invalid max batch size / max latency")        # cmd/agent/main.go:256-273
     from .generative_model import B200GenerativeModel
     path = args.model_id or args.model_dir
     nccl_id, rank = None, int(os.environ.get("RANK", "0"))
@@ -35,6 +44,8 @@ def main(argv=None):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("gloo")
         nccl_id = broadcast_nccl_id(rank)
+    if args.enable_batcher:
+        args.max_batch = max(args.max_batch, min(args.max_batchsize, 64))     # a formed batch must fit one engine call
     model = B200GenerativeModel(args.model_name, path, max_model_len=args.max_model_len, max_batch=args.max_batch,
                                 device=int(os.environ.get("LOCAL_RANK", "0")), tensor_parallel_size=args.tensor_parallel_size,
                                 tp_rank=rank, nccl_id=nccl_id, continuous_batching=args.continuous_batching)
@@ -43,7 +54,8 @@ def main(argv=None):
         from .tp import follower_loop
         return follower_loop(model)
     ModelServer(http_port=args.http_port, enable_latency_logging=args.enable_latency_logging, grpc_port=args.grpc_port,
-                enable_grpc=args.enable_grpc).start([model])
+                enable_grpc=args.enable_grpc,
+                batcher=(args.max_batchsize, args.max_latency) if args.enable_batcher else None).start([model])
 
 
 if __name__ == "__main__":

@@ -67,37 +67,53 @@ class BatchHandler:
         path = self._path
         await self._batch_predict(path, instances, waiters)
 
+    @staticmethod
+    def _resolve(fut: asyncio.Future, value: Dict[str, Any]) -> None:
+        # a waiter whose client went away is cancelled (its serve() task was): skip it, the others must still be answered
+        if not fut.done():
+            fut.set_result(value)
+
     async def _batch_predict(self, path, instances, waiters):
-        """handler.go:99-155"""
+        """handler.go:99-155.  Every waiter of the batch is resolved on every path out of this function (a waiter popped
+        from the table and never answered would hang its client forever)."""
+        def answer_all(message: str, batch_id: str) -> None:
+            for fut, _, _ in waiters:
+                self._resolve(fut, {"message": message, "batchId": batch_id, "predictions": None})
         try:
-            code, body = await self.next(path, {"instances": instances})
-        except Exception as e:  # a raising predictor is a non-200 downstream
-            code, body = 500, str(e)
-        if code != 200:
-            msg = body if isinstance(body, str) else json.dumps(body)
-            for fut, _, _ in waiters:
-                fut.set_result({"message": msg, "batchId": "", "predictions": None})
-            return
-        batch_id = str(uuid.uuid4())
-        preds = body.get("predictions") if isinstance(body, dict) else None
-        if not isinstance(preds, list):
-            for fut, _, _ in waiters:
-                fut.set_result({"message": "can't Unmarshal predictions", "batchId": batch_id, "predictions": None})
-            return
-        if len(preds) != len(instances):
-            for fut, _, _ in waiters:
-                fut.set_result({"message": "size of prediction is not equal to the size of instances",
-                                "batchId": batch_id, "predictions": None})
-            return
-        for fut, f, c in waiters:
-            fut.set_result({"message": "", "batchId": batch_id, "predictions": preds[f:f + c]})
+            try:
+                code, body = await self.next(path, {"instances": instances})
+            except asyncio.CancelledError:
+                raise
+            except Exception as e:  # a raising predictor is a non-200 downstream
+                code, body = 500, str(e)
+            if code != 200:
+                answer_all(body if isinstance(body, str) else json.dumps(body), "")
+                return
+            batch_id = str(uuid.uuid4())
+            preds = body.get("predictions") if isinstance(body, dict) else None
+            if not isinstance(preds, list):
+                answer_all("can't Unmarshal predictions", batch_id)
+                return
+            if len(preds) != len(instances):
+                answer_all("size of prediction is not equal to the size of instances", batch_id)
+                return
+            for fut, f, c in waiters:
+                self._resolve(fut, {"message": "", "batchId": batch_id, "predictions": preds[f:f + c]})
+        finally:
+            for fut, _, _ in waiters:       # cancellation / unexpected error inside the block above
+                if not fut.done():
+                    fut.set_result({"message": "batch aborted", "batchId": "", "predictions": None})
 
     async def _latency_timer(self):
         # stands in for the `case <-time.After(SleepTime)` arm: re-check until the waiting batch has fired
         while self._waiters:
             await asyncio.sleep(max(SLEEP_TIME_S, min(0.001, self.MaxLatency / 1e3)))
             async with self._lock:
-                await self._tick()
+                try:
+                    await self._tick()
+                except Exception as e:   # the timer must outlive a failing batch: later waiters depend on it
+                    if self.log:
+                        self.log.error("batcher tick failed: %s", e)
 
     async def serve(self, path: str, body: bytes) -> Tuple[int, Any]:
         """handler.go:222-266 -> (status, response).  Non-:predict paths go straight to the next handler."""

@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
 ]
-SOURCES = ["engine.cu", "batcher.cu"]
+SOURCES = ["engine.cu"]
 
 
 def _newest_source_mtime() -> float:

@@ -58,6 +58,8 @@ class ContinuousBatcher:
         self._stop = False
         self._thread: Optional[threading.Thread] = None
         self.free_slots = engine.max_batch
+        self.fatal: Optional[BaseException] = None      # set when the scheduler thread died: submit raises it from then on
+        self.on_fatal: Optional[Callable[[BaseException], None]] = None   # the model flips `ready` to False here
         # counters for the load tests / metrics
         self.stats: Dict[str, float] = dict(admitted=0, finished=0, cancelled=0, decode_steps=0, row_steps=0, prefill_calls=0)
 
@@ -88,6 +90,10 @@ class ContinuousBatcher:
         req = _Request(prompts=[list(map(int, p)) for p in prompts], padded=padded, max_new=int(max_new_tokens),
                        stops=stops, pad=self.pad, done=done, on_tokens=on_tokens)
         with self._cv:
+            if self.fatal is not None:
+                raise RuntimeError(f"continuous batcher is down: {self.fatal}")
+            if self._stop:
+                raise RuntimeError("continuous batcher is stopped")
             self._pending.append(req)
             self._cv.notify_all()
         return req
@@ -181,8 +187,9 @@ class ContinuousBatcher:
 
     def _collect(self) -> None:
         n_gen, fin, stop = self.engine.cb_poll()
-        still: List[_Request] = []
-        for r in self._running:
+        running, self._running = self._running, []
+        ended: List = []
+        for r in running:
             if r.cancelled:
                 for sl in r.slots:
                     self.engine.cb_release(sl)
@@ -206,10 +213,16 @@ class ContinuousBatcher:
                         r.on_tokens(r.streamed + k, [row[k] if k < len(row) else r.pad for row in rows])
                     r.streamed = upto
             if end:
-                self._finish(r, n_out, bool(stopped))
+                ended.append((r, n_out, bool(stopped)))     # off the running list BEFORE done() can be called
             else:
-                still.append(r)
-        self._running = still
+                self._running.append(r)
+        for i, (r, n_out, stopped) in enumerate(ended):
+            try:
+                self._finish(r, n_out, stopped)
+            except BaseException as e:
+                for r2, _, _ in ended[i:]:                  # not finished yet: fail them once, then let the loop die
+                    r2.done(None, e)
+                raise
 
     def _loop(self) -> None:
         try:
@@ -227,14 +240,26 @@ class ContinuousBatcher:
                     self.stats["decode_steps"] += self.steps_per_poll
                     self.stats["row_steps"] += self.steps_per_poll * rows
                     self._collect()
-        except BaseException as e:   # engine failure: fail everything that is waiting
+        except BaseException as e:   # engine failure: fail everything that is waiting and refuse new work
+            with self._cv:
+                self.fatal = e
+            if self.on_fatal is not None:
+                try:
+                    self.on_fatal(e)
+                except Exception:
+                    pass
+        finally:
+            # both exits (stop() and a failure) resolve every request still known to the scheduler
             with self._cv:
                 waiting = list(self._pending) + self._running
                 self._pending.clear()
                 self._running = []
+                err = self.fatal or RuntimeError("continuous batcher stopped")
             for r in waiting:
-                r.done(None, e)
-        finally:
+                try:
+                    r.done(None, err)
+                except Exception:
+                    pass
             try:
                 self.engine.cb_end()
             except Exception:

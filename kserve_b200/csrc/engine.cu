@@ -1331,6 +1331,11 @@ int b200_generate(b200_engine_t* e, const int64_t* ids, const int64_t* mask, int
   };
   int steps = 0;
   int ar = after_step(0);
+  // Tensor parallel: only the leader has a callback, so a `done` seen after the first token (EOS first / a stop sequence
+  // that matches token 0) must not make it skip decode steps the followers still run — their all-reduces would wait for
+  // it forever.  Every rank leaves at the shared i % 8 poll below; a user abort (ar == 1) is honoured there as well.
+  bool aborted = ar == 1;
+  if (e->cfg.tp_size > 1) ar = 0;
   if (ar == 0) {
     for (int i = 1; i < gp->max_new_tokens; ++i) {
       if ((rc = decode_step(e, !eager))) return rc;
@@ -1339,6 +1344,7 @@ int b200_generate(b200_engine_t* e, const int64_t* ids, const int64_t* mask, int
       // under TP every rank must leave the loop at the same step (the next step contains collectives), so the
       // only exit points are the shared polling cadence below; a streaming leader just stops receiving tokens.
       if (ar && e->cfg.tp_size == 1) break;
+      if (ar == 1) aborted = true;
       if (ar && e->cfg.tp_size > 1) ar = 0;
       if ((!cb || e->cfg.tp_size > 1) && (i % 8) == 0) {  // poll the device-side done flag without a per-token sync
         B200_CUDA_OK(cudaMemcpyAsync(e->h_state, e->d_state, sizeof(StepState), cudaMemcpyDeviceToHost, s));
@@ -1353,7 +1359,7 @@ int b200_generate(b200_engine_t* e, const int64_t* ids, const int64_t* mask, int
   B200_CUDA_OK(cudaEventElapsedTime(&e->timing.decode_ms, e->ev1, e->ev2));
   e->timing.decode_steps = steps;
   e->timing.kernel_launches = e->launches;
-  return ar == 1 ? 1 : 0;
+  return (ar == 1 || aborted) ? 1 : 0;
 }
 
 // Replaces the body of BatchHandler.batchPredict (pkg/batcher/handler.go:99-155): the instances of every

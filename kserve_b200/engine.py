@@ -27,13 +27,12 @@ class GenerateResult:
     kernel_launches: int
 
 
-def hf_rope_tables(rope_theta: float, head_dim: int, max_pos: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """cos/sin exactly as LlamaRotaryEmbedding computes them (transformers modeling_llama.py:96-135):
-    fp32 inv_freq, fp32 angle = inv_freq * position, cos/sin in fp32, cast to bf16."""
-    inv_freq = 1.0 / (rope_theta ** (torch.arange(0, head_dim, 2, dtype=torch.int64).to(torch.float) / head_dim))
-    pos = torch.arange(max_pos, dtype=torch.float32)
-    freqs = pos[:, None] * inv_freq[None, :]
-    return freqs.cos().to(torch.bfloat16).contiguous(), freqs.sin().to(torch.bfloat16).contiguous()
+def hf_rope_tables(rope_theta_or_cfg, head_dim: int, max_pos: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """cos/sin exactly as LlamaRotaryEmbedding computes them (see utils.hf_rope_tables); accepts a bare rope_theta
+    (default rope) or a config dict (rope_scaling / rope_parameters: default, linear, llama3)."""
+    from .utils import hf_rope_tables as _tables
+    cfg = rope_theta_or_cfg if isinstance(rope_theta_or_cfg, dict) else {"rope_theta": float(rope_theta_or_cfg)}
+    return _tables(cfg, head_dim, max_pos)
 
 
 class B200Engine:
@@ -57,7 +56,8 @@ class B200Engine:
         mc.head_dim = cfg.get("head_dim") or cfg["hidden_size"] // cfg["num_attention_heads"]
         mc.max_position = max(max_seq_len, 64)
         mc.rms_eps = cfg.get("rms_norm_eps", 1e-5)
-        mc.rope_theta = cfg.get("rope_theta", 10000.0)
+        from .utils import rope_parameters
+        mc.rope_theta = float(rope_parameters(cfg)["rope_theta"])
         mc.max_batch = max_batch
         mc.max_seq_len = max_seq_len
         mc.max_prefill_tokens = max_prefill_tokens or max_batch * max_seq_len
@@ -67,11 +67,12 @@ class B200Engine:
         mc.num_experts_per_tok = int(cfg.get("num_experts_per_tok", 0) or 0) if mc.num_experts else 0
         self.device = device
         self.tp_size = tp_size
+        # rope tables first: an unsupported rope_scaling type must fail before any device memory is taken
+        cos, sin = hf_rope_tables(self.cfg, mc.head_dim, mc.max_position)
         h = C.c_void_p()
         idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
         _lib.check(self.lib.b200_engine_create(C.byref(mc), idbuf, C.byref(h)), "b200_engine_create")
         self.h = h
-        cos, sin = hf_rope_tables(mc.rope_theta, mc.head_dim, mc.max_position)
         _lib.check(self.lib.b200_engine_set_rope_table(self.h, cos.data_ptr(), sin.data_ptr(), mc.max_position),
                    "b200_engine_set_rope_table")
         self._cb_keepalive = None
@@ -141,7 +142,8 @@ class B200Engine:
         gp.num_stop = len(stops)
         if forced_tokens is not None:
             ft = torch.as_tensor(forced_tokens, dtype=torch.int64).contiguous()
-            assert ft.shape[1] == max_new_tokens
+            if ft.dim() != 2 or ft.shape[1] != max_new_tokens:
+                raise ValueError("forced_tokens must be [B, max_new_tokens]")
             keep.append(ft)
             gp.forced_tokens = C.cast(ft.data_ptr(), C.POINTER(C.c_int64))
         return gp, keep
@@ -156,12 +158,16 @@ class B200Engine:
         reference sets (generative_model.py:388-402) plus the checkpoint defaults transformers merges in; greedy when
         do_sample is false (the penalty still applies, as a logits processor does under greedy decoding)."""
         ids = torch.as_tensor(input_ids, dtype=torch.int64).contiguous()
-        assert ids.dim() == 2 and not ids.is_cuda
+        if ids.dim() != 2 or ids.is_cuda:
+            raise ValueError("input_ids must be a host int64 [B, S] tensor")
         B, S = ids.shape
+        if int(max_new_tokens) < 1:
+            raise ValueError("max_new_tokens must be >= 1")
         mask = None
         if attention_mask is not None:
             mask = torch.as_tensor(attention_mask, dtype=torch.int64).contiguous()
-            assert mask.shape == ids.shape
+            if mask.shape != ids.shape:          # the C side reads B*S mask words: never let a short buffer through
+                raise ValueError(f"attention_mask shape {tuple(mask.shape)} differs from input_ids shape {tuple(ids.shape)}")
         gp, keep = self._params(max_new_tokens, pad_token_id, eos_token_ids, stop_sequences, forced_tokens,
                                 dict(repetition_penalty=repetition_penalty, do_sample=do_sample, temperature=temperature,
                                      top_p=top_p, top_k=top_k, seed=seed))
@@ -223,6 +229,11 @@ class B200Engine:
         a, b = C.c_float(0), C.c_float(0)
         _lib.check(self.lib.b200_run_staged_timed(self.h, decode_steps, C.byref(a), C.byref(b)), "b200_run_staged_timed")
         return a.value, b.value
+
+    def last_timing(self) -> "_lib.Timing":
+        tm = _lib.Timing()
+        self.lib.b200_engine_last_timing(self.h, C.byref(tm))
+        return tm
 
     def last_launches(self) -> int:
         tm = _lib.Timing()

@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from .engine import B200Engine, GenerateResult
+from .utils import get_and_verify_max_len, logger, plan_memory, rope_inv_freq
 from .kserve_api.errors import InvalidInput
 from .kserve_api.metrics import DECODE_TOKENS_PER_S, LLM_STATS_KEY, TTFT_HIST, LLMStats, get_labels
 from .kserve_api.model import Model
@@ -125,6 +126,7 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         self._tokenizer = tokenizer
         self._pad_token_id = pad_token_id
         self.max_length = max_model_len
+        self._user_max_len = max_model_len
         self.max_batch = max_batch
         self.device_index = device
         self.tp_size, self.tp_rank, self.nccl_id = tensor_parallel_size, tp_rank, nccl_id
@@ -161,8 +163,29 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                 self._tokenizer.add_special_tokens({"pad_token": "[PAD]"})
                 vocab_rows = len(self._tokenizer)
             self._pad_token_id = self._tokenizer.pad_token_id
-        if self.max_length is None:
-            self.max_length = cfg.get("max_position_embeddings", 2048)   # utils.py:28-159 (derived max len)
+        try:
+            self.max_length = get_and_verify_max_len(cfg, self.max_length)    # :206 -> utils.py:28-159
+        except (ValueError, NotImplementedError) as e:
+            raise OpenAIError(str(e))
+        # What this runtime cannot execute must not load (a silently ignored field generates fluent, wrong tokens):
+        rope_inv_freq(cfg, cfg.get("head_dim") or cfg["hidden_size"] // cfg["num_attention_heads"])   # raises on yarn / dynamic / longrope
+        window = cfg.get("sliding_window")
+        layer_types = cfg.get("layer_types")
+        uses_window = window is not None and cfg.get("use_sliding_window", True) and (
+            layer_types is None or any(t == "sliding_attention" for t in layer_types))
+        if uses_window and window < self.max_length:
+            # inside the window sliding-window attention IS full attention, so serving at most `window` tokens is exact
+            if self._user_max_len is not None:
+                raise OpenAIError(f"max_model_len ({self.max_length}) exceeds the checkpoint's sliding_window ({window}); "
+                                  "the B200 runtime implements full attention only")
+            logger.warning("sliding_window=%d < max length %d: serving at most %d tokens (full attention == sliding "
+                           "window inside the window)", window, self.max_length, window)
+            self.max_length = int(window)
+        for key in ("attention_bias", "mlp_bias"):
+            if cfg.get(key):
+                raise OpenAIError(f"config.{key}=true is not supported by the B200 runtime")
+        if cfg.get("hidden_act", "silu") != "silu":
+            raise OpenAIError(f"hidden_act={cfg.get('hidden_act')} is not supported by the B200 runtime (silu only)")
         # checkpoint generation defaults: transformers merges the None fields of the request's GenerationConfig from
         # model.generation_config (generation/utils.py:1693-1701) — this is how instruct checkpoints turn sampling on (q9)
         self.generation_defaults = dict(self._generation_defaults or {})
@@ -172,10 +195,27 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                 self.generation_defaults = {**json.load(f), **self.generation_defaults}
         eos = cfg.get("eos_token_id")
         self.eos_token_ids = [] if eos is None else ([int(e) for e in eos] if isinstance(eos, list) else [int(eos)])
+        try:
+            if torch.cuda.is_available():
+                cap_t, pages = plan_memory(cfg, vocab_rows, self.max_batch, self.max_length, self.tp_size,
+                                           torch.cuda.mem_get_info(self.device_index)[0])
+            else:       # B200Engine raises below (no CPU fallback); nothing to plan
+                cap_t, pages = None, self.max_batch * -(-self.max_length // 64)
+        except ValueError as e:
+            raise OpenAIError(str(e))
+        if self.continuous_batching and pages < self.max_batch * -(-self.max_length // 64):
+            # slots own fixed page ranges in continuous-batching mode: run fewer slots rather than fail at cb_begin
+            self.max_batch = max(1, pages // -(-self.max_length // 64))
+            logger.warning("KV page pool (%d pages) holds %d full-length sequences: max_batch reduced to that", pages, self.max_batch)
+        self.max_prefill_tokens = cap_t
         self._engine = B200Engine(cfg, max_batch=self.max_batch, max_seq_len=self.max_length, device=self.device_index,
+                                  max_prefill_tokens=cap_t, num_kv_pages=pages,
                                   tp_rank=self.tp_rank, tp_size=self.tp_size, nccl_id=self.nccl_id, vocab_rows=vocab_rows)
         weights = self._state_dict if self._state_dict is not None else load_safetensors_dir(self.model_id_or_path)
         V0 = cfg["vocab_size"]
+
+        tied: List[Optional[torch.Tensor]] = [None]
+        seen_head = [False]
 
         def resized():
             for name, t in weights:
@@ -186,9 +226,16 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                     else:
                         extra = t.float().mean(0, keepdim=True).to(t.dtype).expand(vocab_rows - t.shape[0], -1)
                         t = torch.cat([t, extra], 0)
+                if name == "model.embed_tokens.weight" and cfg.get("tie_word_embeddings"):
+                    tied[0] = t
+                if name == "lm_head.weight":
+                    seen_head[0] = True
                 yield name, t
-            if cfg.get("tie_word_embeddings"):
-                pass
+            # tie_word_embeddings: the checkpoint has no lm_head.weight; the head IS the (resized) embedding matrix
+            if cfg.get("tie_word_embeddings") and not seen_head[0]:
+                if tied[0] is None:
+                    raise OpenAIError("tie_word_embeddings is set but the checkpoint has no model.embed_tokens.weight")
+                yield "lm_head.weight", tied[0]
         self._engine.load_weights(resized())
         self._state_dict = None
         self.vocab_rows = vocab_rows
@@ -197,6 +244,10 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         if self.continuous_batching:
             from .continuous import ContinuousBatcher
             self._cb = ContinuousBatcher(self._engine, self._pad_token_id or 0, self.eos_token_ids)
+
+            def _cb_down(err):           # a dead scheduler thread must not leave the model advertised as ready
+                self.ready = False
+            self._cb.on_fatal = _cb_down
             self._cb.start()
         self.ready = True
         return self.ready
@@ -253,6 +304,20 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
             leader_call("generate", (ids, mask), kw)
         return self._engine.generate(ids, mask, streamer=streamer, **kw)
 
+    def _batch_predict(self, rows, **kw):
+        """engine.batch_predict (b200_batch_predict) with the tensor-parallel call replication of `_generate`"""
+        if self.tp_size > 1:
+            from .tp import leader_call
+            leader_call("batch_predict", (rows,), kw)
+        t0 = time.perf_counter()
+        out = self._engine.batch_predict(rows, **kw)
+        labels = get_labels(self.name)
+        tm = self._engine.last_timing()
+        TTFT_HIST.labels(**labels).observe(tm.prefill_ms / 1e3)
+        if tm.decode_ms > 0 and tm.decode_steps > 0:
+            DECODE_TOKENS_PER_S.labels(**labels).observe(len(rows) * tm.decode_steps / (tm.decode_ms / 1e3))
+        return out
+
     @staticmethod
     def _unpadded_rows(ids: torch.Tensor, mask: Optional[torch.Tensor]) -> List[List[int]]:
         """left-padded [B, S] (+ mask) -> the real token rows (what the packed engine layout holds)"""
@@ -297,7 +362,7 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                 raise OpenAIError("repetition penalty / sampling are not available with --continuous_batching (greedy only)")
             try:
                 return await self._cb.submit(self._unpadded_rows(ids, mask), ids, max_new_tokens, stop_sequences)
-            except ValueError as e:
+            except (ValueError, RuntimeError) as e:
                 raise OpenAIError(str(e))
         return await self._submit(lambda: self._generate(ids, mask, max_new_tokens=max_new_tokens, pad_token_id=pad_token_id,
                                                          eos_token_ids=eos_token_ids, stop_sequences=stop_sequences, **sampling))
@@ -425,7 +490,7 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                     put(None)
                 try:
                     cb_req = self._cb.submit_nowait(self._unpadded_rows(ids, mask), ids, request.max_tokens, stop_sequences, cb_done, on_tokens)
-                except ValueError as e:
+                except (ValueError, RuntimeError) as e:
                     raise OpenAIError(str(e))
             else:
                 cb_req = None
@@ -534,7 +599,12 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
             inp = payload.get_input_by_name("input_ids")
             text_in = payload.get_input_by_name("text")
             if inp is not None:
-                arr = inp.as_numpy()
+                try:
+                    arr = inp.as_numpy()
+                except InvalidInput:
+                    raise
+                except Exception as e:       # byte count / shape mismatch of a binary tensor is the client's error
+                    raise InvalidInput(f"malformed 'input_ids' tensor: {e}")
                 if arr.ndim != 2:
                     raise InvalidInput("input_ids must be [batch, seq]")
                 ids = torch.from_numpy(np.ascontiguousarray(arr.astype(np.int64, copy=False)))
@@ -547,14 +617,35 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
             else:
                 raise InvalidInput("expected an 'input_ids' INT64 [B,S] or a 'text' BYTES [B] input")
         else:
+            if not isinstance(payload, dict):
+                raise InvalidInput("expected a JSON object with 'instances'")
             params = payload.get("parameters") or {}
             ids, mask, as_text = self._batch_from_instances(payload.get("instances", []))
-        max_tokens = int(params.get("max_tokens", params.get("max_new_tokens", 16)))
+        try:
+            max_tokens = int(params.get("max_tokens", params.get("max_new_tokens", 16)))
+        except (TypeError, ValueError):
+            raise InvalidInput("'max_tokens' must be an integer")
+        if max_tokens < 1:
+            raise InvalidInput("'max_tokens' must be >= 1")
         B, S = ids.shape
+        if mask is not None and tuple(mask.shape) != (B, S):
+            raise InvalidInput(f"attention_mask shape {list(mask.shape)} differs from input_ids shape {[B, S]}")
         if B > self.max_batch:
             raise InvalidInput(f"batch of {B} exceeds this engine's max batch {self.max_batch}")
         if S + max_tokens > self.max_length:
             raise InvalidInput(f"prompt ({S}) + max_tokens ({max_tokens}) exceeds the model's maximum context length {self.max_length}")
+        if mask is not None:
+            lead = mask.cumsum(1) > 0                  # left padding only: once a row starts it may not contain zeros
+            if bool(((mask == 0) & lead).any()) or not bool(lead[:, -1].all()):
+                raise InvalidInput("attention_mask must be left padding (zeros, then ones) with at least one token per row")
+        if not isinstance(payload, InferRequest) and not as_text and self._cb is None:
+            # the V1 `:predict` leg the batcher fronts: the instances (ragged token rows, one per instance of every merged
+            # request) are concatenated on the device and the predictions come back as one matrix in instance order —
+            # the body of BatchHandler.batchPredict (pkg/batcher/handler.go:99-155) as one C-ABI call
+            rows = self._unpadded_rows(ids, mask)
+            pred, _ = await self._submit(lambda: self._batch_predict(rows, max_new_tokens=max_tokens, pad_token_id=self._pad_token_id,
+                                                                     eos_token_ids=self.eos_token_ids))
+            return {"predictions": [row.tolist() for row in pred]}
         r: GenerateResult = await self._agenerate(ids, mask, max_new_tokens=max_tokens, pad_token_id=self._pad_token_id,
                                                   eos_token_ids=self.eos_token_ids)
         self._observe(r, B)

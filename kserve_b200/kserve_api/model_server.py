@@ -34,11 +34,13 @@ logger = logging.getLogger("kserve")
 class ModelServer:
     def __init__(self, http_port: int = DEFAULT_HTTP_PORT, workers: int = 1,
                  registered_models: Optional[ModelRepository] = None, enable_latency_logging: bool = True,
-                 access_log_format: Optional[str] = None, grpc_port: int = DEFAULT_GRPC_PORT, enable_grpc: bool = False):
+                 access_log_format: Optional[str] = None, grpc_port: int = DEFAULT_GRPC_PORT, enable_grpc: bool = False,
+                 batcher: Optional[tuple] = None):
         if workers != 1:
             raise ValueError("kserve_b200 runs one engine per GPU: --workers must be 1")
         self.http_port = http_port
         self.grpc_port, self.enable_grpc = grpc_port, enable_grpc
+        self.batcher = batcher          # (max_batchsize, max_latency_ms): the agent's batcher in front of V1 :predict
         self._grpc_server = None
         self.registered_models = registered_models or ModelRepository()
         self.enable_latency_logging = enable_latency_logging
@@ -68,7 +70,7 @@ class ModelServer:
 
     def create_application(self, models: List[BaseKServeModel]):
         self._register_and_check(models)
-        return create_application(self.dataplane)
+        return create_application(self.dataplane, batcher=self.batcher)
 
     async def _serve(self, models: List[BaseKServeModel]):
         import uvicorn

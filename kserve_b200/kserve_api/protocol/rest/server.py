@@ -2,7 +2,7 @@
 python/kserve/kserve/protocol/rest/server.py:56-189, v1_endpoints.py:33-174, v2_endpoints.py:35-305)."""
 from __future__ import annotations
 
-from typing import AsyncIterator
+from typing import Any, AsyncIterator, Dict, Optional, Tuple
 
 from fastapi import FastAPI, Request, Response
 from fastapi.responses import JSONResponse, StreamingResponse
@@ -15,9 +15,34 @@ from .openai.endpoints import register_openai_endpoints
 from .openai.openai_model import OpenAIModel
 
 
-def create_application(dataplane: OpenAIDataPlane) -> FastAPI:
+def create_application(dataplane: OpenAIDataPlane, batcher: Optional[Tuple[int, int]] = None) -> FastAPI:
+    """batcher = (max_batchsize, max_latency_ms) installs the request batcher in front of V1 `:predict`, where the Go
+    agent puts it (cmd/agent/main.go:256-273 startBatcher, :431-433 `batcher.New(...)` wrapping the proxy to the model
+    server; pkg/batcher/handler.go:222-266 ServeHTTP).  Concurrent `:predict` requests are merged into ONE downstream
+    predict whose instances are the concatenation of theirs; every caller gets `{"message", "batchId", "predictions"}`
+    with its own slice."""
     app = FastAPI(title="KServe ModelServer (B200 runtime)", version=dataplane._server_version)
     dp: DataPlane = dataplane
+    batch_handler = None
+    if batcher is not None:
+        from ....batcher import BatchHandler
+
+        async def downstream(path: str, body: Dict[str, Any]) -> Tuple[int, Any]:
+            """the predictor behind the batcher: what the agent's reverse proxy reaches over HTTP, called in-process"""
+            model_name = path.rsplit("/", 1)[-1].rsplit(":", 1)[0]
+            try:
+                response, _ = await dp.infer(model_name=model_name, request=body, headers={})
+            except E.InvalidInput as e:
+                return 400, {"error": str(e)}
+            except E.ModelNotFound as e:
+                return 404, {"error": str(e)}
+            except E.ModelNotReady as e:
+                return 503, {"error": str(e)}
+            except Exception as e:   # InferenceError and anything else: a 500 from the predictor
+                return 500, {"error": f"{type(e).__name__} : {e}"}
+            return 200, response
+        batch_handler = BatchHandler(batcher[0], batcher[1], downstream)
+        app.state.batch_handler = batch_handler
 
     # ---- health / metadata
     @app.get("/")
@@ -66,6 +91,12 @@ def create_application(dataplane: OpenAIDataPlane) -> FastAPI:
         if not await dp.model_ready(model_name, True):
             raise E.ModelNotReady(model_name)
         body = await request.body()
+        if batch_handler is not None:        # handler.go:222-266
+            status, out = await batch_handler.serve(request.url.path, body)
+            if status != 200 or isinstance(out, str):
+                return Response(content=(out if isinstance(out, str) else str(out)) + "\n", status_code=status,
+                                media_type="text/plain; charset=utf-8")     # http.Error(w, msg, code)
+            return JSONResponse(content=out)
         headers = dict(request.headers.items())
         infer_request, attrs = dp.decode(body=body, headers=headers)
         response, response_headers = await dp.infer(model_name=model_name, request=infer_request, headers=headers)

@@ -44,6 +44,16 @@ class ScriptedEngine:
         return GenerateResult(output_ids=torch.cat([ids, gen], 1), stop_triggered=stopped, num_generated=n, logits=None,
                               prefill_ms=1.0, decode_ms=1.0, decode_steps=max(0, n - 1), kernel_launches=0)
 
+    def batch_predict(self, rows, *, max_new_tokens, pad_token_id=0, eos_token_ids=(), stop_sequences=()):
+        """ragged rows in, predictions [n_rows, T] out (b200_batch_predict): same script as generate, no padding involved"""
+        self.calls.append(dict(batch_predict=[len(r) for r in rows], max_new=max_new_tokens))
+        last = torch.tensor([r[-1] for r in rows])
+        return torch.stack([(last + 1 + k) % 250 + 3 for k in range(max_new_tokens)], 1), False
+
+    def last_timing(self):
+        from kserve_b200._lib import Timing
+        return Timing(prefill_ms=1.0, decode_ms=1.0, decode_steps=1, kernel_launches=0)
+
     def close(self):
         pass
 
@@ -228,3 +238,35 @@ def test_continuous_batching_wiring_and_stream_disconnect(served):
     finally:
         m._cb = None
         cb.stop()
+
+
+def test_enable_batcher_installs_batch_handler_in_front_of_predict(served):
+    """--enable_batcher: concurrent V1 :predict requests are merged into ONE engine call (device-side concat of their
+    ragged instances) and each caller gets {"message", "batchId", "predictions"} with its own slice — the wiring of
+    cmd/agent/main.go:431-433 + pkg/batcher/handler.go:222-266; scenario of test/e2e/batcher/test_batcher.py:33-85
+    (same batchId for requests that were batched together)."""
+    import concurrent.futures
+    _, m, tok = served
+    app = ModelServer(batcher=(4, 200)).create_application([m])     # maxBatchSize 4 instances, maxLatency 200 ms
+    with TestClient(app) as client:
+        n0 = len(m._engine.calls)
+        bodies = [{"instances": [[5, 6, 7]]}, {"instances": [[8, 9]]}, {"instances": [[1, 2, 3, 4], [9]]}]
+        with concurrent.futures.ThreadPoolExecutor(3) as ex:
+            rs = list(ex.map(lambda b: client.post("/v1/models/stub:predict", json=b), bodies))
+        assert all(r.status_code == 200 for r in rs), [r.text for r in rs]
+        js = [r.json() for r in rs]
+        assert len({j["batchId"] for j in js}) == 1 and all(j["message"] == "" for j in js)          # one formed batch
+        calls = m._engine.calls[n0:]
+        assert len(calls) == 1 and sorted(calls[0]["batch_predict"]) == [1, 2, 3, 4]                # ONE engine call, ragged rows
+        for b, j in zip(bodies, js):                                                                 # each caller gets its own rows back
+            assert j["predictions"] == [[(row[-1] + 1 + k) % 250 + 3 for k in range(16)] for row in b["instances"]]
+        # below the size trigger the latency trigger fires
+        r = client.post("/v1/models/stub:predict", json={"instances": [[3, 4]]})
+        assert r.status_code == 200 and len(r.json()["predictions"]) == 1 and r.json()["batchId"] != js[0]["batchId"]
+        # handler.go:233-243
+        assert client.post("/v1/models/stub:predict", content=b"{not json").status_code == 400
+        r = client.post("/v1/models/stub:predict", json={"instances": []})
+        assert r.status_code == 400 and "no instances in the request" in r.text
+        # a failing downstream answers 200 with the message set and predictions null (handler.go:108-117)
+        r = client.post("/v1/models/stub:predict", json={"instances": [["not", "ids", 1]]})
+        assert r.status_code == 200 and r.json()["predictions"] is None and r.json()["message"]
