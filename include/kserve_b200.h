@@ -105,7 +105,9 @@ typedef int (*b200_token_callback)(void* user, int32_t step, const int64_t* toke
  *   out_ids        host int64 [B][S + max_new_tokens]; rows are the prompt followed by generated tokens
  *   out_len        S + number of generated tokens (same for every row, as in the reference)
  *   stop_triggered 1 iff a stop sequence ended generation (finish_reason "stop", :621-627)
- *   logits_bf16    NULL, or host uint16 [max_new_tokens][B][vocab_size] receiving each step's bf16 logits */
+ *   logits_bf16    NULL, or host uint16 [max_new_tokens][B][vocab_size] receiving each step's bf16 logits; under tensor
+ *                  parallelism rank r receives its vocabulary shard [max_new_tokens][B][Vl], Vl = min(ceil(V / tp),
+ *                  V - r * ceil(V / tp)) columns starting at column r * ceil(V / tp) */
 int b200_generate(b200_engine_t* e, const int64_t* input_ids, const int64_t* attention_mask, int32_t B,
                   int32_t S, const b200_gen_params_t* params, int64_t* out_ids, int32_t* out_len,
                   int32_t* stop_triggered, uint16_t* logits_bf16, b200_token_callback cb, void* user);

@@ -1312,7 +1312,8 @@ int b200_generate(b200_engine_t* e, const int64_t* ids, const int64_t* mask, int
   const bool record = logits_bf16 != nullptr;
   const bool eager = record;             // per-step logits copies -> no graph
   const size_t lrow = (size_t)e->Vl;     // logits of this rank's vocab shard
-  B200_REQUIRE(!record || e->cfg.tp_size == 1, "logits recording is single-GPU only");
+  // tensor parallel: every rank records the logits of ITS vocabulary shard ([max_new_tokens][B][ceil(V / tp)] rows,
+  // the last rank's rows are shorter); the host concatenates the shards
   std::vector<int64_t> cbuf(B);
   auto after_step = [&](int step) -> int {
     if (record)

@@ -66,7 +66,7 @@ class B200Engine:
         mc.num_experts = int(cfg.get("num_local_experts", 0) or 0)
         mc.num_experts_per_tok = int(cfg.get("num_experts_per_tok", 0) or 0) if mc.num_experts else 0
         self.device = device
-        self.tp_size = tp_size
+        self.tp_size, self.tp_rank = tp_size, tp_rank
         # rope tables first: an unsupported rope_scaling type must fail before any device memory is taken
         cos, sin = hf_rope_tables(self.cfg, mc.head_dim, mc.max_position)
         h = C.c_void_p()
@@ -80,6 +80,12 @@ class B200Engine:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
                 self.setup_p2p()      # collective: every rank constructs its engine at the same point
+
+    def vocab_shard(self) -> Tuple[int, int]:
+        """(first column, columns) of the LM-head shard this rank owns (the whole vocabulary on one GPU)"""
+        per = -(-self.vocab // self.tp_size)
+        v0 = per * self.tp_rank
+        return v0, max(0, min(per, self.vocab - v0))
 
     def setup_p2p(self) -> None:
         """Exchange the IPC handles of the peer-memory blocks (torch.distributed is only the courier)."""
@@ -174,8 +180,8 @@ class B200Engine:
         out = torch.empty((B, S + max_new_tokens), dtype=torch.int64).pin_memory()
         out_len, stop = C.c_int32(0), C.c_int32(0)
         logits = None
-        if want_logits:
-            logits = torch.empty((max_new_tokens, B, self.vocab), dtype=torch.bfloat16).pin_memory()
+        if want_logits:      # tensor parallel: this rank's vocabulary shard (see include/kserve_b200.h)
+            logits = torch.empty((max_new_tokens, B, self.vocab_shard()[1]), dtype=torch.bfloat16).pin_memory()
         if streamer is not None:
             def _cb(user, step, toks, batch):
                 return 1 if streamer(step, [toks[i] for i in range(batch)]) else 0

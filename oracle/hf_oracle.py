@@ -50,6 +50,9 @@ class StopSequenceStoppingCriteria(StoppingCriteria):
 def build_llama(cfg: dict, state_dict: Dict[str, torch.Tensor], dtype=torch.bfloat16,
                 eos_token_id=None) -> LlamaForCausalLM:
     """from_config + load seeded weights (the reference uses from_pretrained, :249-254)."""
+    cfg = {k: v for k, v in cfg.items() if not k.startswith("_")}      # tools/synth_weights.py private markers
+    if cfg.get("rope_scaling"):        # transformers 5.x spelling of the 4.x `rope_scaling` + `rope_theta` pair
+        cfg["rope_parameters"] = {**cfg.pop("rope_scaling"), "rope_theta": cfg.pop("rope_theta")}
     hf_cfg = LlamaConfig(**cfg, tie_word_embeddings=False, eos_token_id=eos_token_id,
                          bos_token_id=None, pad_token_id=None, attention_bias=False, mlp_bias=False)
     with torch.device("meta"):
@@ -62,7 +65,10 @@ def build_llama(cfg: dict, state_dict: Dict[str, torch.Tensor], dtype=torch.bflo
     n_fixed = 0
     for mod in model.modules():
         if hasattr(mod, "inv_freq"):
-            inv_freq, scaling = type(mod).compute_default_rope_parameters(mod.config, "cpu")
+            from transformers.modeling_rope_utils import ROPE_INIT_FUNCTIONS
+            init = (type(mod).compute_default_rope_parameters if mod.rope_type == "default"
+                    else ROPE_INIT_FUNCTIONS[mod.rope_type])      # what LlamaRotaryEmbedding.__init__ selects
+            inv_freq, scaling = init(mod.config, "cpu")
             mod.register_buffer("inv_freq", inv_freq.float(), persistent=False)
             mod.register_buffer("original_inv_freq", inv_freq.float().clone(), persistent=False)
             mod.attention_scaling = scaling

@@ -66,8 +66,20 @@ def topk_pack(step_logits, k=16):
     return np.stack(vals, 1), np.stack(idx, 1)  # [B, T, k]
 
 
+ONLY = None         # --only: the case names to (re)generate
+
+SUB_COLS = 4096     # big-vocabulary cases keep every step's logits on this many fixed pseudo-random columns (+ the top-16)
+
+
+def sub_columns(vocab: int) -> torch.Tensor:
+    g = torch.Generator().manual_seed(99)
+    return torch.randperm(vocab, generator=g)[:SUB_COLS].sort().values
+
+
 def gen_case(name, cfg_name, seed, prompt, max_tokens, stop=(), tokenizer=None, pad_token_id=None,
-             full_logits=True, echo=False, stop_from=None, presence_penalty=None):
+             full_logits=True, echo=False, stop_from=None, presence_penalty=None, sub_logits=False):
+    if ONLY is not None and name not in ONLY:
+        return
     cfg = W.CONFIGS[cfg_name]
     sd = W.synth_state_dict(cfg, seed)
     model = build_model(cfg, sd)
@@ -112,6 +124,10 @@ def gen_case(name, cfg_name, seed, prompt, max_tokens, stop=(), tokenizer=None, 
             # a flip between the 2nd and 3rd expert matters iff the margin is inside bf16 noise AND the expert has weight
             risk.append(torch.where(w2 > 0.01, margin, torch.ones_like(margin)))
         out["router_margin"] = torch.stack(risk, 0).min(0).values.numpy().astype(np.float32)   # [B, S+T]
+    if sub_logits:      # [B, T, SUB_COLS] fp16 (exact for bf16 values in range) + the columns
+        cols = sub_columns(cfg["vocab_size"])
+        out["sub_cols"] = cols.numpy().astype(np.int32)
+        out["sub_logits"] = torch.stack(res.step_logits, 1)[..., cols].numpy().astype(np.float16)
     if full_logits:
         out["step_logits"] = torch.stack(res.step_logits, 1).numpy().astype(np.float32)  # [B, T, V]
     else:
@@ -169,11 +185,15 @@ def ids_prompt(B, S, vocab_hi, seed):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--big", action="store_true")
+    ap.add_argument("--only", default=None, help="comma separated case names: generate just these (new fixtures without touching the old ones)")
     args = ap.parse_args()
+    global ONLY
+    ONLY = set(args.only.split(",")) if args.only else None
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
 
-    build_byte_tokenizer(os.path.join(GOLDEN, "byte_tokenizer"))
+    if ONLY is None:
+        build_byte_tokenizer(os.path.join(GOLDEN, "byte_tokenizer"))
 
     # (a) equal-length token-id prompts (generative_model.py:552-555 path), group size 2
     gen_case("tiny_g2_ids", "tiny_g2", 0, ids_prompt(4, 48, 1000, 1234), 16, pad_token_id=1030)
@@ -201,13 +221,42 @@ def main():
     # which every position of every row is decisive, so the full logits comparison applies to them.
     for name, cfg_name, seed, B, S, T, vhi, pad in (("tiny_moe_ids", "tiny_moe", 3, 3, 14, 6, 1000, 1030),
                                                      ("tiny_moe8_ids", "tiny_moe8", 4, 2, 12, 6, 2048, 0)):
+        if ONLY is not None and name not in ONLY:
+            continue
         prompt = find_decisive_moe_prompt(cfg_name, seed, B, S, T, vhi, pad)
         gen_case(name, cfg_name, seed, prompt, T, pad_token_id=pad)
         z = np.load(os.path.join(GOLDEN, name + ".npz"))
         assert float(z["router_margin"].min()) >= MOE_DECISIVE, "search result is not decisive in the batched run"
+    # (h) 8 KV heads: shards under TP = 2 / 4 / 8 (tests/test_tp_gpu.py, bench.py's in-run parity check); S crosses a KV page
+    gen_case("tiny_kv8_ids", "tiny_kv8", 5, ids_prompt(4, 70, 4000, 4321), 16, pad_token_id=4098)
+    # (i) peaked logits (lm_head = permuted embedding): >= 95 % of the steps are decisive, greedy ids compare exactly
+    gen_case("tiny_g2_peaked", "tiny_g2_peaked", 0, ids_prompt(4, 48, 1000, 1234), 16, pad_token_id=1030)
+    gen_case("tiny_g4_peaked", "tiny_g4_peaked", 1, ids_prompt(3, 100, 2048, 99), 40, pad_token_id=0)
+    gen_case("tiny_kv8_peaked", "tiny_kv8_peaked", 5, ids_prompt(4, 70, 4000, 4321), 16, pad_token_id=4098)
+    # (j) rope_scaling "llama3" (Llama-3.1 checkpoints), prompt longer than original_max_position_embeddings
+    gen_case("tiny_g2_rope3", "tiny_g2_rope3", 0, ids_prompt(2, 300, 1000, 55), 8, pad_token_id=1030)
     if args.big:
         gen_case("llama3_8b_2l_ids", "llama3_8b_2l", 0, ids_prompt(2, 96, 128000, 1234), 8,
                  pad_token_id=128255, full_logits=False)
+        big_cases()
+
+
+def big_cases():
+    """BASELINE.json's headline shapes on the 2-layer Llama-3-8B-dims model: 1024-token prompts (16 KV tiles through the
+    prefill attention, M = 4096 rows through the prefill GEMMs), decode at context 1025..1040, V = 128256."""
+    pad = 128255
+    gen_case("llama3_8b_2l_b4", "llama3_8b_2l", 0, ids_prompt(4, 1024, 128000, 2024), 16, pad_token_id=pad,
+             full_logits=False, sub_logits=True)
+    gen_case("llama3_8b_2l_peaked_b4", "llama3_8b_2l_peaked", 0, ids_prompt(4, 1024, 128000, 2024), 16, pad_token_id=pad,
+             full_logits=False, sub_logits=True)
+    # ragged U[512, 1024] prompts, left padded with the pad id (token-id prompts carry no mask: transformers infers it, q4)
+    g = torch.Generator().manual_seed(31)
+    lens = torch.randint(512, 1025, (4,), generator=g).tolist()
+    lens[1] = 1024
+    rows = ids_prompt(4, 1024, 128000, 2025)
+    rows = [[pad] * (1024 - n) + r[1024 - n:] for r, n in zip(rows, lens)]
+    gen_case("llama3_8b_2l_peaked_ragged", "llama3_8b_2l_peaked", 0, rows, 16, pad_token_id=pad,
+             full_logits=False, sub_logits=True)
 
 
 if __name__ == "__main__":

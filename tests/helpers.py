@@ -18,6 +18,15 @@ def logits_tol(ref_logits: torch.Tensor) -> float:
     return TOL_ULPS * 2.0 ** -8 * float(ref_logits.abs().max())
 
 
+def logits_tol_elementwise(ref: torch.Tensor, row_floor: torch.Tensor = None) -> torch.Tensor:
+    """Per-element tolerance for PEAKED logits: TOL_ULPS bf16 ulps of max(|logit|, the row's 2nd-largest |logit|).
+    One logit towers over the rest there, so a tolerance relative to the row maximum would be vacuous for the bulk; the
+    2nd-largest magnitude is the scale of everything but the peak, and the peak itself is held to its own ulps."""
+    if row_floor is None:
+        row_floor = ref.abs().topk(2, dim=-1).values[..., 1]
+    return TOL_ULPS * 2.0 ** -8 * torch.maximum(ref.abs(), row_floor.abs().unsqueeze(-1))
+
+
 def load_case(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     meta = json.loads(str(z["meta"]))
@@ -30,6 +39,9 @@ def load_case(name):
         case["step_logits"] = torch.from_numpy(z["step_logits"])  # [B, T, V]
     if "step0_logits" in z:
         case["step0_logits"] = torch.from_numpy(z["step0_logits"].astype(np.float32))
+    if "sub_logits" in z:     # big-vocabulary cases: every step's logits on a fixed subset of the columns, [B, T, n]
+        case["sub_logits"] = torch.from_numpy(z["sub_logits"].astype(np.float32))
+        case["sub_cols"] = torch.from_numpy(z["sub_cols"].astype(np.int64))
     pad = meta["pad_token_id"]
     mask = (case["input_ids"] != pad).long() if pad is not None else torch.ones_like(case["input_ids"])
     case["mask"] = mask

@@ -35,3 +35,13 @@ def test_cpu_thread_policy_and_peaks():
     p = bench.load_peaks()
     assert p["hbm_gbs"] > 1000 and p["tf_sustained"] <= p["tf_burst"]
     assert json.dumps(p)
+
+
+def test_both_arms_share_one_config_dict():
+    """the reference arm mislabelled its workload and `same_config` was false.  Both arms now build `config`
+    from one function of (model, batch, prompt, gen, gpus), and it states what one reference step is."""
+    a = bench.workload_config("Llama-3-8B", 32, 1024, 128, 4)
+    assert a == bench.workload_config("Llama-3-8B", 32, 1024, 128, 4)
+    assert a["global_batch"] == 32 and a["parallelism"] == "tp4" and "batch 1 x 1024-in/128-out in full" in a["reference_sample"]
+    src = open(bench.__file__).read()
+    assert src.count('"config": workload_config(') == 2          # the GPU arm and the reference arm, nothing hand-written

@@ -12,7 +12,7 @@ import os
 import pytest
 import torch
 
-from helpers import load_case, logits_tol, make_engine
+from helpers import load_case, logits_tol, logits_tol_elementwise, make_engine
 
 pytestmark = pytest.mark.gpu
 
@@ -28,7 +28,12 @@ def _record(name, **kw):
 
 
 CASES = ["tiny_g2_ids", "tiny_g2_text", "tiny_g2_padinfer", "tiny_g4_ids", "tiny_g4_b1",
-         "tiny_moe_ids", "tiny_moe8_ids"]   # the last two: Mixtral-style sparse MoE (BASELINE configs[3] architecture)
+         "tiny_moe_ids", "tiny_moe8_ids",   # Mixtral-style sparse MoE (BASELINE configs[3] architecture)
+         "tiny_kv8_ids",                    # 8 KV heads (the TP = 4 / 8 test shapes), odd vocabulary
+         "tiny_g2_rope3"]                   # rope_scaling "llama3" (Llama-3.1), prompt past original_max_position_embeddings
+# lm_head = permuted embedding: one logit towers over the rest as in a trained model, so (nearly) every step is decisive
+# and greedy ids are compared EXACTLY; logits are held to a per-element tolerance
+PEAKED = ["tiny_g2_peaked", "tiny_g4_peaked", "tiny_kv8_peaked"]
 
 
 @pytest.fixture(scope="module")
@@ -93,6 +98,102 @@ def test_free_running_ids(engines, name):
     # determinism of the engine itself: same call twice -> identical ids
     r2 = eng.generate(c["input_ids"], c["mask"], max_new_tokens=c["T"], pad_token_id=c["meta"]["pad_token_id"])
     assert torch.equal(r.output_ids, r2.output_ids)
+
+
+@pytest.mark.parametrize("name", PEAKED)
+def test_peaked_logits_greedy_ids_exact(engines, name):
+    c = load_case(name)
+    eng = engines(c)
+    pad = c["meta"]["pad_token_id"]
+    r = eng.generate(c["input_ids"], c["mask"], max_new_tokens=c["T"], pad_token_id=pad, forced_tokens=c["gen"], want_logits=True)
+    got = r.logits.float().permute(1, 0, 2)
+    ref = c["step_logits"]
+    tol = logits_tol_elementwise(ref)
+    err = (got - ref).abs()
+    assert bool((err <= tol).all()), f"worst element: err/tol = {float((err / tol).max()):.2f}"
+    decisive = c["margin"] > 2 * logits_tol(ref)
+    assert float(decisive.float().mean()) >= 0.95
+    assert bool((got.argmax(-1) == c["gen"])[decisive].all())
+    free = eng.generate(c["input_ids"], c["mask"], max_new_tokens=c["T"], pad_token_id=pad)
+    exact = free.output_ids[:, c["S"]:] == c["gen"]
+    _record(name + ":peaked", decisive_frac=float(decisive.float().mean()), free_running_exact_match=float(exact.float().mean()),
+            worst_err_over_tol=float((err / tol).max()), max_err_bulk=float(err.max()), steps=int(exact.numel()))
+    if bool(decisive.all()):
+        assert bool(exact.all()), "every step is decisive: free-running greedy ids must equal the oracle's exactly"
+    else:
+        first_soft = (~decisive).float().argmax(1)          # rows may legitimately diverge from their first soft step on
+        for b in range(exact.shape[0]):
+            upto = int(first_soft[b]) if not bool(decisive[b].all()) else exact.shape[1]
+            assert bool(exact[b, :upto].all())
+
+
+HEADLINE = ["llama3_8b_2l_b4", "llama3_8b_2l_peaked_b4", "llama3_8b_2l_peaked_ragged"]
+
+
+@pytest.fixture(scope="module")
+def headline_engines():
+    """2-layer Llama-3-8B-dims engines for BASELINE.json's headline shapes (4 x 1024-token prompts, V = 128256)."""
+    cache = {}
+
+    def get(case):
+        m = case["meta"]
+        if m["cfg"] not in cache:
+            for e in cache.values():      # one 3.5 GB model at a time
+                e.close()
+            cache.clear()
+            cache[m["cfg"]] = make_engine(m["cfg"], m["seed"], vocab_rows=m["vocab_rows"], max_batch=4, max_seq_len=1152)
+        return cache[m["cfg"]]
+    yield get
+    for e in cache.values():
+        e.close()
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name", HEADLINE)
+def test_headline_shapes_1024_prompt_tokens(headline_engines, name):
+    """the headline configuration's shapes against the oracle — S = 1024 (16 KV tiles through
+    attn_prefill_tc_kernel, 4096 packed rows through the 2-CTA prefill GEMMs), decode at context 1025..1040, a ragged
+    U[512,1024] left-padded batch, V = 128256.  Teacher-forced: every step's logits on 4096 fixed columns + the oracle's
+    top-16; peaked cases additionally require the free-running greedy ids to be the oracle's, token for token."""
+    c = load_case(name)
+    eng = headline_engines(c)
+    pad = c["meta"]["pad_token_id"]
+    peaked = "peaked" in name
+    r = eng.generate(c["input_ids"], c["mask"], max_new_tokens=c["T"], pad_token_id=pad, forced_tokens=c["gen"], want_logits=True)
+    assert torch.equal(r.output_ids, c["output_ids"])
+    got = r.logits.float().permute(1, 0, 2)                  # [B, T, V]
+    assert not torch.isnan(got).any()
+    sub = got[..., c["sub_cols"]]
+    topv = torch.gather(got, 2, c["topk_idx"].long())
+    if peaked:
+        floor = c["topk_vals"][..., 1]
+        ok_sub = (sub - c["sub_logits"]).abs() <= logits_tol_elementwise(c["sub_logits"], floor)
+        ok_top = (topv - c["topk_vals"]).abs() <= logits_tol_elementwise(c["topk_vals"], floor)
+        tol_scalar = float(logits_tol(c["topk_vals"]))
+    else:
+        tol_scalar = float(logits_tol(c["topk_vals"]))      # max |logit| of the case is in the top-k
+        ok_sub = (sub - c["sub_logits"]).abs() <= tol_scalar
+        ok_top = (topv - c["topk_vals"]).abs() <= tol_scalar
+    err_sub, err_top = float((sub - c["sub_logits"]).abs().max()), float((topv - c["topk_vals"]).abs().max())
+    decisive = c["margin"] > 2 * tol_scalar
+    agree = got.argmax(-1) == c["gen"]
+    stats = dict(max_err_sub=err_sub, max_err_topk=err_top, tol=tol_scalar, max_logit=float(c["topk_vals"].abs().max()),
+                 decisive=int(decisive.sum()), steps=int(decisive.numel()), agree_tf=int(agree.sum()))
+    assert bool(ok_sub.all()) and bool(ok_top.all()), stats
+    assert bool(agree[decisive].all()), stats
+    free = eng.generate(c["input_ids"], c["mask"], max_new_tokens=c["T"], pad_token_id=pad)
+    exact = free.output_ids[:, c["S"]:] == c["gen"]
+    stats["free_running_exact_match"] = float(exact.float().mean())
+    _record(name + ":headline", **stats)
+    if peaked:
+        assert float(decisive.float().mean()) >= 0.95, stats
+        if bool(decisive.all()):
+            assert bool(exact.all()), stats
+    else:
+        for b in range(exact.shape[0]):
+            neq = (~exact[b]).nonzero()
+            if len(neq):
+                assert not bool(decisive[b, int(neq[0])]), f"row {b} diverges at a decisive step"
 
 
 def test_stop_sequence_batch_wide(engines):
