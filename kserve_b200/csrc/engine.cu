@@ -183,11 +183,32 @@ struct b200_engine {
   int32_t* h_cb = nullptr;           // pinned: init records / poll results / token reads
   bool cb_rows_dirty = false;
   int cb_num_eos = 0;
+  // weight-stream L2 prefetcher (prefetch.cuh): one table of the step's weight-streaming GEMMs per graph key
+  PfCtx pf;
+  std::unordered_map<int, PfGemm*> pf_tables;   // graph key -> device table
+  std::unordered_map<int, int> pf_counts;
+  cudaEvent_t ev_pf_fork = nullptr, ev_pf_join = nullptr;
+  int pf_lead = 24;
 };
 
 namespace b200 {
 
 static int pick_block_n(int B) { return B <= 16 ? 16 : (B <= 32 ? 32 : 64); }
+
+// peer-memory all-reduce + residual + RMSNorm of the decode step: one-shot LL below 4 ranks, two-shot (reduce-scatter +
+// all-gather, 4x less NVLink traffic at 8 ranks) from 4 ranks on; B200_AR_TWO_SHOT_MIN_TP moves the switch (A/B runs)
+typedef void (*ArKernel)(const P2P, bf16*, const bf16*, bf16*, float, const float*, int, long long, long long, const bf16*, int, int);
+static ArKernel ar_kernel(const b200_engine* e) {
+  static const int min_tp = getenv("B200_AR_TWO_SHOT_MIN_TP") ? atoi(getenv("B200_AR_TWO_SHOT_MIN_TP")) : 4;
+  return (e->cfg.tp_size >= min_tp && (e->H / e->cfg.tp_size) % 8 == 0) ? allreduce2_norm_kernel : allreduce_norm_kernel;
+}
+
+// every GEMM of the engine goes through here so that the decode step's weight-streaming launches join the
+// prefetcher's table (launch.cuh: PfCtx) without threading the context through each call site
+static int launch_gemm(b200_engine* e, GemmArgs& a, int sms, cudaStream_t s) {
+  a.pf = &e->pf;
+  return launch_gemm(e->tmaps, a, sms, s);
+}
 
 static int pick_splits(const b200_engine* e, int n_out, int K) {
   const int m_tiles = (n_out + kGemmBlockM - 1) / kGemmBlockM;
@@ -264,7 +285,7 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
       GemmArgs a{w.wqkv, e->qkv_cols, e->xn, e->cap_T, e->qkv_cols, B, H, sp > 1 ? EPI_T_PARTIAL : EPI_T_STORE, bn, sp,
                  sp > 1 ? (void*)e->ws : (void*)e->qkv, nullptr, e->qkv_cols, (long long)B * e->qkv_cols, 0, true};
       a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
-      if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+      if ((rc = launch_gemm(e, a, e->num_sms, s))) return rc;
       if (sp > 1) { rp.partial = e->ws; rp.splits = sp; rp.split_stride = (long long)B * e->qkv_cols; rp.ld_partial = e->qkv_cols; }
       rp.qkv = e->qkv;
       rp.q_out = e->qdec; rp.ldq = e->nh * kHeadDim;
@@ -272,7 +293,7 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
     } else {
       GemmArgs a{e->xn + r0 * H, e->cap_T - (int)r0, w.wqkv, e->qkv_cols, T, e->qkv_cols, H, EPI_STORE, 256, 1,
                  e->qkv + r0 * e->qkv_cols, nullptr, e->qkv_cols, 0, 0, false};
-      if ((rc = launch_gemm(e->tmaps, a, gsms, s))) return rc;
+      if ((rc = launch_gemm(e, a, gsms, s))) return rc;
       rp.qkv = e->qkv + r0 * e->qkv_cols;
       rp.q_out = e->qkv + r0 * e->qkv_cols; rp.ldq = e->qkv_cols;  // in place
       rp.tok_seq = e->d_tok_seq + r0; rp.tok_pos = e->d_tok_pos + r0;
@@ -323,7 +344,7 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
         const int sp = pick_splits(e, H, K);
         if (sp > 1) {
           GemmArgs a{wmat, H, act, e->cap_T, H, B, K, EPI_T_PARTIAL, bn, sp, e->ws, nullptr, H, (long long)B * H, 0, true};
-          if ((rc2 = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc2;
+          if ((rc2 = launch_gemm(e, a, e->num_sms, s))) return rc2;
           e->launches++;
           if (!tp) {
             if ((rc2 = launch_rmsnorm(1, e->x, next_norm, e->xn, T, H, eps, e->ws, sp, (long long)B * H, H, nullptr, s))) return rc2;
@@ -331,7 +352,7 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
             return 0;
           }
           if (e->p2p_ready) {   // split-K reduce + all-reduce over peer memory + residual + RMSNorm in one kernel
-            B200_CUDA_OK(launch_k(allreduce_norm_kernel, dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, e->p2p,
+            B200_CUDA_OK(launch_k(ar_kernel(e), dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, e->p2p,
                                   e->x, next_norm, e->xn, eps, (const float*)e->ws, sp, (long long)B * H, (long long)H, (const bf16*)nullptr,
                                   e->ar_index++, 2 * e->L));
             e->launches++;
@@ -342,10 +363,10 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
         } else {
           GemmArgs a{wmat, H, act, e->cap_T, H, B, K, EPI_T_STORE, bn, 1, e->ybuf, nullptr, H, 0, 0, true};
           a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
-          if ((rc2 = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc2;
+          if ((rc2 = launch_gemm(e, a, e->num_sms, s))) return rc2;
           e->launches++;
           if (tp && e->p2p_ready) {
-            B200_CUDA_OK(launch_k(allreduce_norm_kernel, dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, e->p2p,
+            B200_CUDA_OK(launch_k(ar_kernel(e), dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, e->p2p,
                                   e->x, next_norm, e->xn, eps, (const float*)nullptr, 0, 0LL, 0LL, (const bf16*)e->ybuf,
                                   e->ar_index++, 2 * e->L));
             e->launches++;
@@ -355,13 +376,13 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
       } else {
         if (!tp) {
           GemmArgs a{act, e->cap_T, wmat, H, T, H, K, EPI_STORE_RES, 256, 1, e->x, e->x, H, 0, 0, false};   // (r0 == 0: one GPU)
-          if ((rc2 = launch_gemm(e->tmaps, a, gsms, s))) return rc2;
+          if ((rc2 = launch_gemm(e, a, gsms, s))) return rc2;
           if ((rc2 = launch_rmsnorm(0, e->x, next_norm, e->xn, T, H, eps, nullptr, 0, 0, 0, nullptr, s))) return rc2;
           e->launches += 2;
           return 0;
         }
         GemmArgs a{act + r0 * K, e->cap_T - (int)r0, wmat, H, T, H, K, EPI_STORE, 256, 1, e->ybuf + r0 * H, nullptr, H, 0, 0, false};
-        if ((rc2 = launch_gemm(e->tmaps, a, gsms, s))) return rc2;
+        if ((rc2 = launch_gemm(e, a, gsms, s))) return rc2;
         e->launches++;
       }
       if ((rc2 = allreduce_bf16(e, e->ybuf + r0 * H, (size_t)T * H, s))) return rc2;
@@ -394,10 +415,10 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
       if (grouped) {
         GemmArgs a{w.wgu_e, e->E * 2 * e->I, e->xg, e->g_rows, 2 * e->I, B, H, EPI_T_SWIGLU, bn, 1, e->hg, nullptr, e->I, 0, e->I, true};
         a.n_rt = e->e_count; a.row_off = e->e_off; a.groups = e->E;
-        if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+        if ((rc = launch_gemm(e, a, e->num_sms, s))) return rc;
         GemmArgs d{w.wdown_e, e->E * H, e->hg, e->g_rows, H, B, e->I, EPI_T_STORE, bn, 1, e->yg, nullptr, H, 0, 0, true};
         d.n_rt = e->e_count; d.row_off = e->e_off; d.groups = e->E;
-        if ((rc = launch_gemm(e->tmaps, d, e->num_sms, s))) return rc;
+        if ((rc = launch_gemm(e, d, e->num_sms, s))) return rc;
         e->launches += 2;
       }
       for (int x = 0; x < e->E && !grouped; ++x) {
@@ -407,18 +428,18 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
           GemmArgs a{wgu, 2 * e->I, e->xg, e->g_rows, 2 * e->I, B, H, EPI_T_SWIGLU, bn, 1, e->hg, nullptr, e->I, 0, e->I, true};
           a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
           a.n_rt = e->e_count + x; a.row_off = e->e_off + x;
-          if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+          if ((rc = launch_gemm(e, a, e->num_sms, s))) return rc;
           GemmArgs d{wdn, H, e->hg, e->g_rows, H, B, e->I, dsp > 1 ? EPI_T_PARTIAL : EPI_T_STORE, bn, dsp,
                      dsp > 1 ? (void*)(e->ws + (size_t)x * dsp * B * H) : (void*)e->yg, nullptr, H, (long long)B * H, 0, true};
           d.n_rt = e->e_count + x; d.row_off = e->e_off + x;
-          if ((rc = launch_gemm(e->tmaps, d, e->num_sms, s))) return rc;
+          if ((rc = launch_gemm(e, d, e->num_sms, s))) return rc;
         } else {
           GemmArgs a{e->xg, e->g_rows, wgu, 2 * e->I, T, 2 * e->I, H, EPI_SWIGLU, 256, 1, e->hg, nullptr, e->I, 0, e->I, false};
           a.m_rt = e->e_count + x; a.row_off = e->e_off + x;
-          if ((rc = launch_gemm(e->tmaps, a, gsms, s))) return rc;
+          if ((rc = launch_gemm(e, a, gsms, s))) return rc;
           GemmArgs d{e->hg, e->g_rows, wdn, H, T, H, e->I, EPI_STORE, 256, 1, e->yg, nullptr, H, 0, 0, false};
           d.m_rt = e->e_count + x; d.row_off = e->e_off + x;
-          if ((rc = launch_gemm(e->tmaps, d, gsms, s))) return rc;
+          if ((rc = launch_gemm(e, d, gsms, s))) return rc;
         }
         e->launches += 2;
       }
@@ -431,7 +452,7 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
       B200_CUDA_OK(launch_k(moe_combine_norm_kernel, dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, cp));
       e->launches++;
       if (tp && decode && e->p2p_ready) {   // all-reduce of the combined expert outputs + residual + next norm, over peer memory
-        B200_CUDA_OK(launch_k(allreduce_norm_kernel, dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, e->p2p,
+        B200_CUDA_OK(launch_k(ar_kernel(e), dim3(T), dim3(kNormThreads), (size_t)(H + 32) * sizeof(float), s, e->p2p,
                               e->x, next_norm, e->xn, eps, (const float*)nullptr, 0, 0LL, 0LL, (const bf16*)e->ybuf,
                               e->ar_index++, 2 * e->L));
         e->launches++;
@@ -450,18 +471,18 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
       if (gsp > 1) {   // few tiles per GPU (tensor parallel): split-K partials + a reducing SwiGLU kernel
         GemmArgs a{w.wgu, 2 * e->I, e->xn, e->cap_T, 2 * e->I, B, H, EPI_T_PARTIAL, bn, gsp, e->ws, nullptr, 2 * e->I,
                    (long long)B * 2 * e->I, 0, true};
-        if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+        if ((rc = launch_gemm(e, a, e->num_sms, s))) return rc;
         B200_CUDA_OK(launch_k(swiglu_reduce_kernel, dim3(B), dim3(512), 0, s, (const float*)e->ws, gsp, (long long)B * 2 * e->I,
                               (long long)2 * e->I, e->hbuf, e->I));
         e->launches++;
       } else {
         GemmArgs a{w.wgu, 2 * e->I, e->xn, e->cap_T, 2 * e->I, B, H, EPI_T_SWIGLU, bn, 1, e->hbuf, nullptr, e->I, 0, e->I, true};
         a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
-        if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+        if ((rc = launch_gemm(e, a, e->num_sms, s))) return rc;
       }
     } else {
       GemmArgs a{e->xn + r0 * H, e->cap_T - (int)r0, w.wgu, 2 * e->I, T, 2 * e->I, H, EPI_SWIGLU, 256, 1, e->hbuf + r0 * e->I, nullptr, e->I, 0, e->I, false};
-      if ((rc = launch_gemm(e->tmaps, a, gsms, s))) return rc;
+      if ((rc = launch_gemm(e, a, gsms, s))) return rc;
     }
     e->launches++;
     if ((rc = row_parallel(e->hbuf, e->I, w.wdown, next_norm))) return rc;
@@ -481,7 +502,7 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
   GemmArgs a{e->lm_head, e->Vl, rows_xn, rows_cap, e->Vl, B, e->H, EPI_T_STORE, pick_block_n(B), 1,
              e->logits, nullptr, e->Vl, 0, 0, true};
   a.sk_ws = e->sk_ws; a.sk_flags = e->sk_flags; a.sk_tiles = e->sk_tiles; a.sk_ws_floats = e->sk_ws_floats;
-  if ((rc = launch_gemm(e->tmaps, a, e->num_sms, s))) return rc;
+  if ((rc = launch_gemm(e, a, e->num_sms, s))) return rc;
   const int use_p2p = (e->cfg.tp_size > 1 && e->p2p_ready) ? 1 : 0;
   // one GPU: 16 CTAs per row scan slices of the 128k-entry row (a single CTA per row took 65 us of the 4.3 ms step)
   const int chunks = (e->cfg.tp_size == 1 && e->Vl >= 16384) ? 16 : 1;
@@ -505,7 +526,8 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
     cv = e->cand_val_all; ci = e->cand_idx_all; ranks = e->cfg.tp_size;
   }
   if (cb_row_slot) {   // continuous batching: per-slot bookkeeping
-    B200_CUDA_OK(launch_k(cb_step_kernel, dim3(1), dim3(128), 0, s, cv, ci, ranks, B, cb_row_slot, e->cb, (const int32_t*)e->d_eos, e->cb_num_eos));
+    B200_CUDA_OK(launch_k(cb_step_kernel, dim3(1), dim3(128), 0, s, cv, ci, ranks, B, cb_row_slot, e->cb, (const int32_t*)e->d_eos, e->cb_num_eos,
+                          e->pf.d_seq));
     e->launches++;
     return 0;
   }
@@ -519,6 +541,7 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
   sp.st = e->d_state;
   sp.pp = e->p2p; sp.use_p2p = use_p2p;
   sp.seen = e->st.rep_on ? e->d_seen : nullptr; sp.seen_words = e->seen_words; sp.V = e->Vl;
+  sp.pf_seq = e->pf.d_seq;
   B200_CUDA_OK(launch_k(step_update_kernel, dim3(1), dim3(128), 0, s, sp));
   e->launches++;
   return 0;
@@ -545,20 +568,49 @@ static int decode_step_enqueue(b200_engine* e) {
   return head_and_step(e, e->xn, e->cap_T, e->st.B);
 }
 
-// Decode step through a CUDA graph captured once per (batch size, forced, stop/eos counts).
-static int decode_step(b200_engine* e, bool use_graph) {
-  if (!use_graph) return decode_step_enqueue(e);
-  const int key = e->st.B | (e->st.forced ? 1 << 8 : 0) | (e->st.num_eos << 9) | (e->st.num_stop << 14) |
-                  (e->st.sample_on ? 1 << 21 : 0) | (e->st.rep_on ? 1 << 22 : 0);
+// One decode step through a CUDA graph captured once per key.  The first call for a key runs the step eagerly (tensor
+// maps / function attributes are created outside of capture, and the weight-stream prefetcher's table is recorded), the
+// second captures it: the main chain (programmatic dependent launches) plus, on a forked branch, the prefetch kernel
+// that walks the step's weight-streaming GEMMs ahead of the chain (prefetch.cuh).
+template <class Enqueue>
+static int graph_step(b200_engine* e, int key, Enqueue&& enqueue) {
+  static const bool pf_off = getenv("B200_NO_PREFETCHER") != nullptr;
+  const bool pf_on = !pf_off && e->pf.d_prog != nullptr;
   auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
-    // one eager step first: creates tensor maps / sets function attributes outside of capture
     const int before = e->launches;
-    int rc = decode_step_enqueue(e);
-    if (rc) return rc;
+    e->pf.active = pf_on; e->pf.recording = pf_on; e->pf.count = 0; e->pf.table.clear();
+    int rc = enqueue();
+    e->pf.recording = false;
+    if (rc) { e->pf.active = false; return rc; }
     const int per_step = e->launches - before;
+    PfGemm* d_tab = nullptr;
+    const int n_pf = (int)e->pf.table.size();
+    if (pf_on && n_pf > 0) {
+      B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_tab), sizeof(PfGemm) * n_pf));
+      B200_CUDA_OK(cudaMemcpy(d_tab, e->pf.table.data(), sizeof(PfGemm) * n_pf, cudaMemcpyHostToDevice));   // synchronous
+      e->pf_tables[key] = d_tab; e->pf_counts[key] = n_pf;
+    }
+    // the prefetcher's CTAs stay resident on every SM for the whole step: they must not pin the SMs to a small
+    // shared-memory carve-out, or no GEMM CTA (165 KB of dynamic shared memory) can become resident next to them
+    // (r02 timeline: with the default carve-out the first GEMM waited 3 ms for the prefetcher's time-out)
+    B200_CUDA_OK(cudaFuncSetAttribute(weight_prefetch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     B200_CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-    rc = decode_step_enqueue(e);
+    if (d_tab) {   // fork: the prefetcher runs beside the whole chain
+
+      B200_CUDA_OK(cudaEventRecord(e->ev_pf_fork, e->stream));
+      B200_CUDA_OK(cudaStreamWaitEvent(e->stream2, e->ev_pf_fork, 0));
+      weight_prefetch_kernel<<<e->num_sms, 32, 0, e->stream2>>>(d_tab, n_pf, e->pf.d_prog, e->pf.d_seq, e->pf_lead, 3000000ull,
+                                                                       getenv("B200_PF_MODE") ? atoi(getenv("B200_PF_MODE")) : 0,
+                                                                       getenv("B200_PF_SKIP") ? atoi(getenv("B200_PF_SKIP")) : 8);
+      B200_CUDA_OK(cudaGetLastError());
+      B200_CUDA_OK(cudaEventRecord(e->ev_pf_join, e->stream2));
+    }
+    e->pf.count = 0;
+    rc = enqueue();
+    if (rc == 0 && d_tab && e->pf.count != n_pf) { set_last_error("prefetcher table does not match the captured step"); rc = -6; }
+    if (d_tab) cudaStreamWaitEvent(e->stream, e->ev_pf_join, 0);
+    e->pf.active = false;
     cudaGraph_t g = nullptr;
     cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
     e->launches -= per_step;  // the captured enqueue did not execute
@@ -568,12 +620,19 @@ static int decode_step(b200_engine* e, bool use_graph) {
     B200_CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
     cudaGraphDestroy(g);
     e->graphs[key] = ge;
-    e->graph_nodes[key] = per_step;
-    return 0;  // the eager step above already advanced the sequence by one token
+    e->graph_nodes[key] = per_step + (d_tab ? 1 : 0);
+    return 0;  // the eager step above already advanced the sequences by one token
   }
   B200_CUDA_OK(cudaGraphLaunch(it->second, e->stream));
   e->launches += e->graph_nodes[key];
   return 0;
+}
+
+static int decode_step(b200_engine* e, bool use_graph) {
+  if (!use_graph) return decode_step_enqueue(e);
+  const int key = e->st.B | (e->st.forced ? 1 << 8 : 0) | (e->st.num_eos << 9) | (e->st.num_stop << 14) |
+                  (e->st.sample_on ? 1 << 21 : 0) | (e->st.rep_on ? 1 << 22 : 0);
+  return graph_step(e, key, [&] { return decode_step_enqueue(e); });
 }
 
 // Validates the request, sizes the KV pages and resets the per-request device state.  `lens` are the real
@@ -778,29 +837,7 @@ static int cb_decode_step(b200_engine* e) {
   static const bool eager = getenv("B200_NO_GRAPH") != nullptr;
   if (eager) return cb_decode_enqueue(e, R);
   const int key = R | (1 << 20) | (e->cb_num_eos << 9);
-  auto it = e->graphs.find(key);
-  if (it == e->graphs.end()) {
-    const int before = e->launches;
-    int rc = cb_decode_enqueue(e, R);   // eager first: tensor maps / function attributes outside of capture
-    if (rc) return rc;
-    const int per_step = e->launches - before;
-    B200_CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-    rc = cb_decode_enqueue(e, R);
-    cudaGraph_t g = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
-    e->launches -= per_step;
-    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-    B200_CUDA_OK(ce);
-    cudaGraphExec_t ge = nullptr;
-    B200_CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
-    cudaGraphDestroy(g);
-    e->graphs[key] = ge;
-    e->graph_nodes[key] = per_step;
-    return 0;
-  }
-  B200_CUDA_OK(cudaGraphLaunch(it->second, e->stream));
-  e->launches += e->graph_nodes[key];
-  return 0;
+  return graph_step(e, key, [&] { return cb_decode_enqueue(e, R); });
 }
 
 // prefill `n` new sequences into free slots and produce their first token
@@ -941,6 +978,16 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   B200_CUDA_OK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
   B200_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   B200_CUDA_OK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  B200_CUDA_OK(cudaEventCreateWithFlags(&e->ev_pf_fork, cudaEventDisableTiming));
+  B200_CUDA_OK(cudaEventCreateWithFlags(&e->ev_pf_join, cudaEventDisableTiming));
+  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->pf.d_prog), sizeof(unsigned long long) * 1024));
+  B200_CUDA_OK(cudaMemset(e->pf.d_prog, 0, sizeof(unsigned long long) * 1024));
+  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->pf.d_seq), sizeof(unsigned int)));
+  {
+    const unsigned int one = 1;     // prog slots start at sequence 0: nothing is "consumed" before the first step publishes
+    B200_CUDA_OK(cudaMemcpy(e->pf.d_seq, &one, sizeof(one), cudaMemcpyHostToDevice));
+  }
+  if (getenv("B200_PF_LEAD")) e->pf_lead = std::max(1, atoi(getenv("B200_PF_LEAD")));
   B200_CUDA_OK(cudaEventCreate(&e->ev0));
   B200_CUDA_OK(cudaEventCreate(&e->ev1));
   B200_CUDA_OK(cudaEventCreate(&e->ev2));
@@ -1097,6 +1144,11 @@ int b200_engine_destroy(b200_engine_t* e) {
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : e->pf_tables) cudaFree(kv.second);
+  if (e->pf.d_prog) cudaFree(e->pf.d_prog);
+  if (e->pf.d_seq) cudaFree(e->pf.d_seq);
+  if (e->ev_pf_fork) cudaEventDestroy(e->ev_pf_fork);
+  if (e->ev_pf_join) cudaEventDestroy(e->ev_pf_join);
   if (e->comm) Nccl::get().CommDestroy(e->comm);
   for (int r = 0; r < kMaxTp; ++r) if (e->ar_peer_map[r]) cudaIpcCloseMemHandle(e->ar_peer_map[r]);
   if (e->ar_local) cudaFree(e->ar_local);

@@ -4,6 +4,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 
 #include "attention.cuh"
 #include "attention_tc.cuh"
@@ -15,6 +16,7 @@
 #include "moe.cuh"
 #include "cb.cuh"
 #include "sampling.cuh"
+#include "prefetch.cuh"
 
 namespace b200 {
 
@@ -139,6 +141,17 @@ int launch_gemm_2cta_inst(const CUtensorMap* ta, const CUtensorMap* tb, const Ge
   return 0;
 }
 
+// Host side of the weight-stream prefetcher (prefetch.cuh): while a decode step is being enqueued, every weight-streaming
+// GEMM takes the next index of the step's table; in `recording` mode its descriptor is appended as well.
+struct PfCtx {
+  bool active = false;      // this enqueue publishes progress / is followed by a prefetch kernel
+  bool recording = false;   // first (eager) enqueue of a graph key: build the table
+  int count = 0;            // GEMMs seen so far in this enqueue
+  std::vector<PfGemm> table;
+  unsigned long long* d_prog = nullptr;   // [num_sms]
+  unsigned int* d_seq = nullptr;
+};
+
 struct GemmArgs {
   const bf16* A; int a_rows;        // rows of the A buffer as declared to TMA (>= M)
   const bf16* B; int b_rows;        // rows of the B buffer as declared to TMA (>= N)
@@ -155,6 +168,7 @@ struct GemmArgs {
   const int* row_off = nullptr;
   int groups = 0;                   // > 0: grouped swap-AB problem (see GemmParams::group_m_tiles); A rows = groups * M,
   long long group_out_stride = 0;   // n_rt / row_off are arrays of `groups` entries
+  PfCtx* pf = nullptr;              // weight-stream prefetcher context of the step being enqueued (decode only)
 };
 
 inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStream_t s) {
@@ -204,6 +218,21 @@ inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStr
     const int slots = (int)((p.kb_total + per_min - 1) / per_min) + 1;    // pieces a tile can be cut into, minus the owner
     if ((size_t)p.m_tiles * slots * a.block_n * kGemmBlockM <= a.sk_ws_floats) {
       p.sched = 1; p.sk_slots = slots; grid = g2;
+    }
+  }
+  p.pf_prog = nullptr; p.pf_seq = nullptr; p.pf_index = 0;
+  {
+    static const int pub = getenv("B200_PF_PUB") ? atoi(getenv("B200_PF_PUB")) : 3;
+    p.pf_pub = pub;
+  }
+  if (a.pf && a.pf->active && p.prefetch_a && a.groups == 0 && p.n_tiles == 1 && a.pf->count < kPfMaxGemms) {
+    p.pf_prog = a.pf->d_prog; p.pf_seq = a.pf->d_seq; p.pf_index = a.pf->count++;
+    if (a.pf->recording) {
+      PfGemm g{};
+      g.tmap_a = *ta;
+      g.sched = GemmSched{p.m_tiles, p.n_tiles, p.splits, p.kb_total, p.kb_per_split, p.sched};
+      g.grid = grid;
+      a.pf->table.push_back(g);
     }
   }
   B200_REQUIRE(p.splits == 1 || a.epi == EPI_T_PARTIAL, "split-K only with the fp32 partial epilogue");

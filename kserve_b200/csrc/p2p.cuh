@@ -141,4 +141,149 @@ allreduce_norm_kernel(const P2P pp, bf16* __restrict__ x, const bf16* __restrict
   }
 }
 
+// Two-shot variant for tp >= 4 (reduce-scatter + all-gather, both as pushed LL packets, in the same single kernel).
+// The one-shot kernel above makes every rank push its whole row to every rank: (tp - 1) * B * H * 4 bytes out per GPU
+// (3.6 MB at tp = 8, B = 32 -> 18 us measured, r01).  Here rank j owns columns [j * H/tp, (j+1) * H/tp) of every row:
+//   1. scatter : each rank pushes slice j of its own contribution to rank j            ((tp-1)/tp * B * H * 4 B out)
+//   2. reduce  : the owner sums the tp contributions of its slice in rank order (fp32, ONE rounding to bf16 — the same
+//                value the one-shot kernel computes, so results are bit-identical to it and across ranks)
+//   3. gather  : the owner pushes the reduced slice to every rank                      ((tp-1)/tp * B * H * 4 B out)
+//   4. every rank polls the complete row, adds the residual and applies the RMSNorm.
+// 4x less NVLink traffic than one-shot at tp = 8 for two store latencies instead of one.  Buffers live in the same
+// IPC block (y region): scatter [2][tp][kArRows][H/tp/2] u64 at offset 0, gather [2][kArRows][H/2] u64 behind it; the
+// epoch-parity double buffering argument of the one-shot kernel carries over (a peer writes epoch e+2 into a slot only
+// after it has seen this rank's gather packets of e+1, which this rank sends after it finished reading epoch e).
+__global__ void __launch_bounds__(kNormThreads)
+allreduce2_norm_kernel(const P2P pp, bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ xn, float eps,
+                       const float* __restrict__ partial, int splits, long long split_stride, long long ld_partial,
+                       const bf16* __restrict__ ysrc, int ar_index, int ar_per_step) {
+  TraceScope _ts(TK_RMSNORM);
+  pdl_launch_dependents();
+  extern __shared__ float row[];  // H floats + 32
+  const int H = pp.lay.H, tp = pp.tp;
+  const int Hs = H / tp;          // columns per owner (multiple of 8: H % 64 == 0, tp <= 8)
+  float* red = row + H;
+  const int r = blockIdx.x;
+  const uint32_t epoch = (uint32_t)ld_sys(pp.row_epoch) * (uint32_t)ar_per_step + (uint32_t)ar_index + 1u;
+  const int slot = epoch & 1;
+  const long long gather_base = (long long)2 * tp * kArRows * (Hs / 2);        // u64 words: scatter region size
+  pdl_wait();
+  _ts.mark();
+  // 1. scatter this rank's contribution: column chunk i goes to its owner
+  for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
+    float f[8];
+    if (partial) {
+      sum_partials8(partial + (long long)r * ld_partial + i, splits, split_stride, f);
+    } else {
+      uint4 u = *reinterpret_cast<const uint4*>(ysrc + (long long)r * H + i);
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 p2 = unpack_bf16x2(uw[t]);
+        f[2 * t] = p2.x;
+        f[2 * t + 1] = p2.y;
+      }
+    }
+    const uint4 pk = pack8(f);
+    const int owner = i / Hs, c = i - owner * Hs;
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(pp.peer[owner] + pp.lay.y_off) +
+                              (((long long)slot * tp + pp.rank) * kArRows + r) * (Hs / 2) + c / 2;
+    st_ll2(dst, pk.x, pk.y, epoch);
+    st_ll2(dst + 2, pk.z, pk.w, epoch);
+  }
+  // 2. owner: poll the tp contributions of this rank's slice of row r; one (source, 8-column chunk) per thread task
+  const unsigned long long* lbase = reinterpret_cast<const unsigned long long*>(pp.peer[pp.rank] + pp.lay.y_off);
+  const int chunks = Hs / 8;
+  for (int task = threadIdx.x; task < tp * chunks; task += blockDim.x) {
+    const int src_rank = task / chunks, c = (task - src_rank * chunks) * 8;
+    const unsigned long long* src = lbase + (((long long)slot * tp + src_rank) * kArRows + r) * (Hs / 2) + c / 2;
+    unsigned long long q[4];
+    ld_ll2(src, q[0], q[1]);
+    ld_ll2(src + 2, q[2], q[3]);
+    uint32_t spins = 0;
+    while ((uint32_t)(q[0] >> 32) != epoch || (uint32_t)(q[1] >> 32) != epoch || (uint32_t)(q[2] >> 32) != epoch ||
+           (uint32_t)(q[3] >> 32) != epoch) {
+      if (++spins > (1u << 26)) {
+        printf("b200: peer scatter packet timeout (row %d thread %d rank %d epoch %u)\n", r, threadIdx.x, src_rank, epoch);
+        __trap();
+      }
+      ld_ll2(src, q[0], q[1]);
+      ld_ll2(src + 2, q[2], q[3]);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 p2 = unpack_bf16x2((uint32_t)q[t]);
+      row[src_rank * Hs + c + 2 * t] = p2.x;
+      row[src_rank * Hs + c + 2 * t + 1] = p2.y;
+    }
+  }
+  __syncthreads();
+  // 3. rank-order fp32 sum, one rounding, pushed to every rank's gather buffer (4 columns = one 16-byte LL pair per task)
+  for (int c = threadIdx.x * 4; c < Hs; c += blockDim.x * 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int sr = 0; sr < tp; ++sr) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) a[t] += row[sr * Hs + c + t];
+    }
+    const uint32_t d0 = pack_bf16x2(a[0], a[1]), d1 = pack_bf16x2(a[2], a[3]);
+    const long long goff = gather_base + ((long long)slot * kArRows + r) * (H / 2) + (pp.rank * Hs + c) / 2;
+#pragma unroll
+    for (int d = 0; d < kMaxTp; ++d) {
+      const int peer = (pp.rank + d) % kMaxTp;
+      if (peer < tp) st_ll2(reinterpret_cast<unsigned long long*>(pp.peer[peer] + pp.lay.y_off) + goff, d0, d1, epoch);
+    }
+  }
+  __syncthreads();   // `row` is reused below
+  // 4. poll the complete reduced row, residual add, RMSNorm
+  bf16* xr = x + (long long)r * H;
+  const unsigned long long* grow = lbase + gather_base + ((long long)slot * kArRows + r) * (H / 2);
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
+    unsigned long long q[4];
+    ld_ll2(grow + i / 2, q[0], q[1]);
+    ld_ll2(grow + i / 2 + 2, q[2], q[3]);
+    uint32_t spins = 0;
+    while ((uint32_t)(q[0] >> 32) != epoch || (uint32_t)(q[1] >> 32) != epoch || (uint32_t)(q[2] >> 32) != epoch ||
+           (uint32_t)(q[3] >> 32) != epoch) {
+      if (++spins > (1u << 26)) {
+        printf("b200: peer gather packet timeout (row %d thread %d epoch %u)\n", r, threadIdx.x, epoch);
+        __trap();
+      }
+      ld_ll2(grow + i / 2, q[0], q[1]);
+      ld_ll2(grow + i / 2 + 2, q[2], q[3]);
+    }
+    const uint4 xu = *reinterpret_cast<const uint4*>(xr + i);
+    const uint32_t xw[4] = {xu.x, xu.y, xu.z, xu.w};
+    float f[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 p2 = unpack_bf16x2(xw[t]);
+      float2 y2 = unpack_bf16x2((uint32_t)q[t]);
+      f[2 * t] = bf16_round(p2.x + y2.x);
+      f[2 * t + 1] = bf16_round(p2.y + y2.y);
+    }
+    *reinterpret_cast<uint4*>(xr + i) = pack8(f);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      row[i + t] = f[t];
+      ss += f[t] * f[t];
+    }
+  }
+  const float tot = block_sum(ss, red);
+  const float rs = 1.0f / sqrtf(tot / (float)H + eps);
+  bf16* o = xn + (long long)r * H;
+  for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
+    const uint4 wu = *reinterpret_cast<const uint4*>(w + i);
+    const uint32_t ww[4] = {wu.x, wu.y, wu.z, wu.w};
+    float g[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 w2 = unpack_bf16x2(ww[t]);
+      g[2 * t] = w2.x * bf16_round(row[i + 2 * t] * rs);
+      g[2 * t + 1] = w2.y * bf16_round(row[i + 2 * t + 1] * rs);
+    }
+    *reinterpret_cast<uint4*>(o + i) = pack8(g);
+  }
+}
+
 }  // namespace b200

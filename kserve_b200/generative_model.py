@@ -376,9 +376,15 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         if request.echo and self.is_encoder_decoder:
             raise OpenAIError("'echo' is not supported by encoder-decoder models")
         # presence_penalty / temperature / top_p are handled by build_generation_config (device-side processors).
-        # logit_bias -> sequence_bias keyed by tuple(str) is unusable in the reference itself (q8): reject loudly.
-        if request.logit_bias:
-            raise OpenAIError("'logit_bias' is not supported by the B200 runtime yet")
+        # logit_bias (q8): the reference maps it to `sequence_bias = {tuple(token): bias}` (:396-401).  The keys of an
+        # OpenAI logit_bias are token-id STRINGS, so tuple("123") is ('1', '2', '3') and transformers'
+        # SequenceBiasLogitsProcessor._validate_arguments rejects every such request inside generate() — an empty dict
+        # is rejected too.  The observable behaviour of the reference is therefore this error, reproduced verbatim.
+        if request.logit_bias is not None:
+            sequence_bias = {tuple(token): bias for token, bias in request.logit_bias.items()}
+            if len(sequence_bias) == 0:
+                raise ValueError(f"`sequence_bias` has to be a non-empty dictionary, or non-empty list of lists but is {sequence_bias}.")
+            raise ValueError(f"Each key in `sequence_bias` has to be a non-empty tuple of positive integers, but is {sequence_bias}.")
 
     # ------------------------------------------------------------------ tokenisation (:546-562)
     def _encode_prompts(self, prompt) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

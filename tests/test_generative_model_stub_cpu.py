@@ -270,3 +270,17 @@ def test_enable_batcher_installs_batch_handler_in_front_of_predict(served):
         # a failing downstream answers 200 with the message set and predictions null (handler.go:108-117)
         r = client.post("/v1/models/stub:predict", json={"instances": [["not", "ids", 1]]})
         assert r.status_code == 200 and r.json()["predictions"] is None and r.json()["message"]
+
+
+def test_logit_bias_reproduces_the_reference_error(served):
+    """q8: the reference turns logit_bias into sequence_bias keyed by tuple(str) (generative_model.py:396-401), which
+    transformers' SequenceBiasLogitsProcessor rejects inside generate(): the request fails with that ValueError."""
+    _, m, tok = served
+    client = TestClient(served[0].app, raise_server_exceptions=False)     # the 500 itself is what is being asserted
+    n0 = len(m._engine.calls)
+    r = client.post("/openai/v1/completions", json={"model": "stub", "prompt": "abc", "max_tokens": 3, "logit_bias": {"123": 5.0}})
+    assert r.status_code == 500
+    assert "Each key in `sequence_bias` has to be a non-empty tuple of positive integers, but is {('1', '2', '3'): 5.0}." in r.text
+    r = client.post("/openai/v1/completions", json={"model": "stub", "prompt": "abc", "max_tokens": 3, "logit_bias": {}})
+    assert r.status_code == 500 and "`sequence_bias` has to be a non-empty dictionary" in r.text
+    assert len(m._engine.calls) == n0          # nothing reached the engine, as nothing is generated in the reference

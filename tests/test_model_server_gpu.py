@@ -149,3 +149,64 @@ def test_batch_predict_ragged_rows_equal_padded_generate(served):
     pred, stop = model._engine.batch_predict(rows, max_new_tokens=c["T"], pad_token_id=256)
     ref = model._engine.generate(c["input_ids"], c["mask"], max_new_tokens=c["T"], pad_token_id=256)
     assert torch.equal(pred, ref.output_ids[:, c["S"]:]) and not stop
+
+
+def test_enable_batcher_served_over_http(served):
+    """--enable_batcher on the served path: the batcher sits in front of /v1/models/{m}:predict
+    (cmd/agent/main.go:431-433), concurrent requests are merged and run as ONE b200_batch_predict call (device-side concat
+    of the ragged rows + scatter), every caller gets its own slice under a shared batchId
+    (test/e2e/batcher/test_batcher.py:33-85)."""
+    import concurrent.futures
+    from kserve_b200.kserve_api import ModelServer
+    _, model, tok, c = served
+    rows = [c["input_ids"][b][c["mask"][b].bool()].tolist() for b in range(c["input_ids"].shape[0])]
+    want = model._engine.generate(c["input_ids"], c["mask"], max_new_tokens=16, pad_token_id=256).output_ids[:, c["S"]:]
+    calls = []
+    orig = model._engine.batch_predict
+    model._engine.batch_predict = lambda r, **kw: (calls.append(len(r)), orig(r, **kw))[1]
+    try:
+        with TestClient(ModelServer(batcher=(len(rows), 2000)).create_application([model])) as client:
+            with concurrent.futures.ThreadPoolExecutor(len(rows)) as ex:
+                rs = list(ex.map(lambda row: client.post("/v1/models/tiny:predict", json={"instances": [row]}), rows))
+            assert all(r.status_code == 200 for r in rs), [r.text for r in rs]
+            js = [r.json() for r in rs]
+            assert len({j["batchId"] for j in js}) == 1 and all(j["message"] == "" for j in js)
+            assert calls == [len(rows)]                                   # one engine call for the formed batch
+            for b, j in enumerate(js):                                    # the batcher forwards instances only: 16 = default max_tokens
+                assert j["predictions"] == [want[b].tolist()]
+    finally:
+        model._engine.batch_predict = orig
+
+
+def test_grpc_model_infer_on_the_cuda_engine(served):
+    """Open Inference Protocol gRPC `ModelInfer` (python/kserve/kserve/protocol/grpc/servicer.py:109-127) against the real
+    engine: INT64 token ids in as raw bytes, generated ids out as raw bytes — the same tensors as the V2 REST leg."""
+    import grpc
+    from kserve_b200.kserve_api.protocol.grpc import GRPCServer, pb
+    from kserve_b200.kserve_api.protocol.rest.openai.dataplane import OpenAIDataPlane
+    from kserve_b200.kserve_api.model_repository import ModelRepository
+    _, model, tok, c = served
+    ids, mask = c["input_ids"].numpy(), c["mask"].numpy()
+
+    async def main():
+        repo = ModelRepository()
+        repo.update(model)
+        srv = await GRPCServer(0, OpenAIDataPlane(model_registry=repo), host="127.0.0.1").start()
+        try:
+            async with grpc.aio.insecure_channel(f"127.0.0.1:{srv.bound_port}") as ch:
+                infer = ch.unary_unary(f"/{pb.SERVICE_NAME}/ModelInfer", request_serializer=pb.ModelInferRequest.SerializeToString,
+                                       response_deserializer=pb.ModelInferResponse.FromString)
+                req = pb.ModelInferRequest(model_name="tiny", id="g1", inputs=[
+                    {"name": "input_ids", "shape": list(ids.shape), "datatype": "INT64"},
+                    {"name": "attention_mask", "shape": list(mask.shape), "datatype": "INT64"}],
+                    raw_input_contents=[ids.tobytes(), mask.tobytes()])
+                req.parameters["max_tokens"].int64_param = c["meta"]["max_tokens"]
+                return await infer(req)
+        finally:
+            await srv.stop(0)
+    res = asyncio.run(main())
+    assert res.model_name == "tiny" and res.id == "g1"
+    out = res.outputs[0]
+    assert out.name == "output_ids" and out.datatype == "INT64"
+    got = np.frombuffer(res.raw_output_contents[0], dtype=np.int64).reshape(list(out.shape))
+    assert np.array_equal(got, c["gen"].numpy())
