@@ -65,13 +65,11 @@ __global__ void cb_gather_kernel(const int32_t* __restrict__ row_slot, int R, Cb
 // one thread per row: merge the argmax candidates, append the token, EOS / max_new / stop sequences per sequence
 __global__ void __launch_bounds__(128)
 cb_step_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, int ranks, int R,
-               const int32_t* __restrict__ row_slot, CbState st, const int32_t* __restrict__ eos, int num_eos,
-               unsigned int* pf_seq) {
+               const int32_t* __restrict__ row_slot, CbState st, const int32_t* __restrict__ eos, int num_eos) {
   TraceScope _ts(TK_STEP);
   pdl_launch_dependents();
   pdl_wait();
   _ts.mark();
-  if (pf_seq && threadIdx.x == 0) *pf_seq += 1;     // weight-stream prefetcher step sequence (prefetch.cuh)
   for (int r = threadIdx.x; r < R; r += blockDim.x) {
     const int slot = row_slot[r];
     if (st.finished[slot]) continue;

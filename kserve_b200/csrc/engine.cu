@@ -183,12 +183,13 @@ struct b200_engine {
   int32_t* h_cb = nullptr;           // pinned: init records / poll results / token reads
   bool cb_rows_dirty = false;
   int cb_num_eos = 0;
-  // weight-stream L2 prefetcher (prefetch.cuh): one table of the step's weight-streaming GEMMs per graph key
+  // weight-stream L2 prefetch (prefetch.cuh): the step's weight-streaming GEMMs in launch order, per graph key
   PfCtx pf;
-  std::unordered_map<int, PfGemm*> pf_tables;   // graph key -> device table
-  std::unordered_map<int, int> pf_counts;
+  std::unordered_map<int, std::vector<PfGemm>> pf_tables;
+  const std::vector<PfGemm>* pf_cur = nullptr;   // table of the step being captured (nullptr: no prefetch launches)
   cudaEvent_t ev_pf_fork = nullptr, ev_pf_join = nullptr;
-  int pf_lead = 24;
+  int pf_cap_kb = 16;                            // k-block tiles (16 KB each) prefetched per CTA of the next GEMM
+  bool pf_forked = false;
 };
 
 namespace b200 {
@@ -207,6 +208,20 @@ static ArKernel ar_kernel(const b200_engine* e) {
 // prefetcher's table (launch.cuh: PfCtx) without threading the context through each call site
 static int launch_gemm(b200_engine* e, GemmArgs& a, int sms, cudaStream_t s) {
   a.pf = &e->pf;
+  if (e->pf_cur && e->pf.active && pf_eligible(a) && s == e->stream) {
+    // capture: beside GEMM i (it starts when its predecessor in the chain has completed) prefetch the head of GEMM i+1's
+    // weight stream; after the step's last GEMM (LM head) that is the first GEMM of the next step (L2 survives the launch)
+    const std::vector<PfGemm>& tab = *e->pf_cur;
+    const int i = e->pf.count;
+    if (i < (int)tab.size()) {
+      const PfGemm& nxt = tab[(i + 1) % tab.size()];
+      B200_CUDA_OK(cudaEventRecord(e->ev_pf_fork, s));
+      B200_CUDA_OK(cudaStreamWaitEvent(e->stream2, e->ev_pf_fork, 0));
+      weight_prefetch_kernel<<<nxt.grid, 32, 0, e->stream2>>>(nxt, e->pf_cap_kb);
+      B200_CUDA_OK(cudaGetLastError());
+      e->pf_forked = true;
+    }
+  }
   return launch_gemm(e->tmaps, a, sms, s);
 }
 
@@ -526,8 +541,7 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
     cv = e->cand_val_all; ci = e->cand_idx_all; ranks = e->cfg.tp_size;
   }
   if (cb_row_slot) {   // continuous batching: per-slot bookkeeping
-    B200_CUDA_OK(launch_k(cb_step_kernel, dim3(1), dim3(128), 0, s, cv, ci, ranks, B, cb_row_slot, e->cb, (const int32_t*)e->d_eos, e->cb_num_eos,
-                          e->pf.d_seq));
+    B200_CUDA_OK(launch_k(cb_step_kernel, dim3(1), dim3(128), 0, s, cv, ci, ranks, B, cb_row_slot, e->cb, (const int32_t*)e->d_eos, e->cb_num_eos));
     e->launches++;
     return 0;
   }
@@ -541,7 +555,6 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
   sp.st = e->d_state;
   sp.pp = e->p2p; sp.use_p2p = use_p2p;
   sp.seen = e->st.rep_on ? e->d_seen : nullptr; sp.seen_words = e->seen_words; sp.V = e->Vl;
-  sp.pf_seq = e->pf.d_seq;
   B200_CUDA_OK(launch_k(step_update_kernel, dim3(1), dim3(128), 0, s, sp));
   e->launches++;
   return 0;
@@ -574,43 +587,33 @@ static int decode_step_enqueue(b200_engine* e) {
 // that walks the step's weight-streaming GEMMs ahead of the chain (prefetch.cuh).
 template <class Enqueue>
 static int graph_step(b200_engine* e, int key, Enqueue&& enqueue) {
-  static const bool pf_off = getenv("B200_NO_PREFETCHER") != nullptr;
-  const bool pf_on = !pf_off && e->pf.d_prog != nullptr;
+  // opt-in (B200_PREFETCHER=1): measured r02 (profiles/r02_prefetch_timelines.md) — the head prefetch does not shorten the
+  // step: each GEMM's post-wait time is a latency chain (B tiles -> MMA -> second ring fill -> epilogue), not HBM time,
+  // and the extra requests compete with the kernels that are streaming
+  static const bool pf_on = getenv("B200_PREFETCHER") != nullptr;
   auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
     const int before = e->launches;
-    e->pf.active = pf_on; e->pf.recording = pf_on; e->pf.count = 0; e->pf.table.clear();
+    e->pf.active = pf_on; e->pf.recording = pf_on; e->pf.count = 0; e->pf.table.clear(); e->pf_cur = nullptr;
     int rc = enqueue();
     e->pf.recording = false;
     if (rc) { e->pf.active = false; return rc; }
     const int per_step = e->launches - before;
-    PfGemm* d_tab = nullptr;
     const int n_pf = (int)e->pf.table.size();
-    if (pf_on && n_pf > 0) {
-      B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_tab), sizeof(PfGemm) * n_pf));
-      B200_CUDA_OK(cudaMemcpy(d_tab, e->pf.table.data(), sizeof(PfGemm) * n_pf, cudaMemcpyHostToDevice));   // synchronous
-      e->pf_tables[key] = d_tab; e->pf_counts[key] = n_pf;
+    if (pf_on && n_pf > 1) {
+      e->pf_tables[key] = e->pf.table;
+      e->pf_cur = &e->pf_tables[key];
     }
-    // the prefetcher's CTAs stay resident on every SM for the whole step: they must not pin the SMs to a small
-    // shared-memory carve-out, or no GEMM CTA (165 KB of dynamic shared memory) can become resident next to them
-    // (r02 timeline: with the default carve-out the first GEMM waited 3 ms for the prefetcher's time-out)
-    B200_CUDA_OK(cudaFuncSetAttribute(weight_prefetch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     B200_CUDA_OK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-    if (d_tab) {   // fork: the prefetcher runs beside the whole chain
-
-      B200_CUDA_OK(cudaEventRecord(e->ev_pf_fork, e->stream));
-      B200_CUDA_OK(cudaStreamWaitEvent(e->stream2, e->ev_pf_fork, 0));
-      weight_prefetch_kernel<<<e->num_sms, 32, 0, e->stream2>>>(d_tab, n_pf, e->pf.d_prog, e->pf.d_seq, e->pf_lead, 3000000ull,
-                                                                       getenv("B200_PF_MODE") ? atoi(getenv("B200_PF_MODE")) : 0,
-                                                                       getenv("B200_PF_SKIP") ? atoi(getenv("B200_PF_SKIP")) : 8);
-      B200_CUDA_OK(cudaGetLastError());
-      B200_CUDA_OK(cudaEventRecord(e->ev_pf_join, e->stream2));
-    }
-    e->pf.count = 0;
+    e->pf.count = 0; e->pf_forked = false;
     rc = enqueue();
-    if (rc == 0 && d_tab && e->pf.count != n_pf) { set_last_error("prefetcher table does not match the captured step"); rc = -6; }
-    if (d_tab) cudaStreamWaitEvent(e->stream, e->ev_pf_join, 0);
-    e->pf.active = false;
+    if (rc == 0 && e->pf_cur && e->pf.count != n_pf) { set_last_error("prefetch table does not match the captured step"); rc = -6; }
+    if (e->pf_forked) {   // join the prefetch branch (a capture must end with every forked stream merged back)
+      cudaEventRecord(e->ev_pf_join, e->stream2);
+      cudaStreamWaitEvent(e->stream, e->ev_pf_join, 0);
+    }
+    const int n_forks = e->pf_cur ? n_pf : 0;
+    e->pf.active = false; e->pf_cur = nullptr;
     cudaGraph_t g = nullptr;
     cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
     e->launches -= per_step;  // the captured enqueue did not execute
@@ -620,7 +623,7 @@ static int graph_step(b200_engine* e, int key, Enqueue&& enqueue) {
     B200_CUDA_OK(cudaGraphInstantiate(&ge, g, 0));
     cudaGraphDestroy(g);
     e->graphs[key] = ge;
-    e->graph_nodes[key] = per_step + (d_tab ? 1 : 0);
+    e->graph_nodes[key] = per_step + n_forks;
     return 0;  // the eager step above already advanced the sequences by one token
   }
   B200_CUDA_OK(cudaGraphLaunch(it->second, e->stream));
@@ -980,14 +983,7 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   B200_CUDA_OK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   B200_CUDA_OK(cudaEventCreateWithFlags(&e->ev_pf_fork, cudaEventDisableTiming));
   B200_CUDA_OK(cudaEventCreateWithFlags(&e->ev_pf_join, cudaEventDisableTiming));
-  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->pf.d_prog), sizeof(unsigned long long) * 1024));
-  B200_CUDA_OK(cudaMemset(e->pf.d_prog, 0, sizeof(unsigned long long) * 1024));
-  B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->pf.d_seq), sizeof(unsigned int)));
-  {
-    const unsigned int one = 1;     // prog slots start at sequence 0: nothing is "consumed" before the first step publishes
-    B200_CUDA_OK(cudaMemcpy(e->pf.d_seq, &one, sizeof(one), cudaMemcpyHostToDevice));
-  }
-  if (getenv("B200_PF_LEAD")) e->pf_lead = std::max(1, atoi(getenv("B200_PF_LEAD")));
+  if (getenv("B200_PF_CAP_KB")) e->pf_cap_kb = std::max(1, atoi(getenv("B200_PF_CAP_KB")));
   B200_CUDA_OK(cudaEventCreate(&e->ev0));
   B200_CUDA_OK(cudaEventCreate(&e->ev1));
   B200_CUDA_OK(cudaEventCreate(&e->ev2));
@@ -1144,9 +1140,6 @@ int b200_engine_destroy(b200_engine_t* e) {
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
-  for (auto& kv : e->pf_tables) cudaFree(kv.second);
-  if (e->pf.d_prog) cudaFree(e->pf.d_prog);
-  if (e->pf.d_seq) cudaFree(e->pf.d_seq);
   if (e->ev_pf_fork) cudaEventDestroy(e->ev_pf_fork);
   if (e->ev_pf_join) cudaEventDestroy(e->ev_pf_join);
   if (e->comm) Nccl::get().CommDestroy(e->comm);

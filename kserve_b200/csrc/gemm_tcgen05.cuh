@@ -55,14 +55,6 @@ struct GemmParams {
   // empty groups are skipped: their weights are never streamed) and whose outputs start at out + g * group_out_stride
   int group_m_tiles;
   long long group_out_stride;
-  // weight-stream L2 prefetcher (prefetch.cuh): when pf_prog != nullptr the TMA producer publishes how far this CTA has
-  // read its weight stream — (step sequence << 32 | pf_index << 16 | k-blocks requested so far) into pf_prog[blockIdx.x]
-  // — so that the concurrently running prefetch kernel stays a bounded distance ahead of it
-  unsigned long long* pf_prog;
-  const unsigned int* pf_seq;
-  int pf_index;
-  int pf_pub;              // who publishes: 1 producer thread with atomicMax, 2 producer thread with a plain store (requests),
-                           // 3 MMA-issuing thread with a plain store (k-blocks whose MMAs were issued)
   int sched;
   int sk_slots;            // partial slots per tile
   float* sk_ws;            // [m_tiles][sk_slots][BLOCK_N][128] fp32
@@ -154,16 +146,6 @@ __device__ __forceinline__ bool gemm_get_seg(const GemmParams& p, int idx, GemmS
   return gemm_get_seg(sc, idx, g, m_tiles_rt, (int)blockIdx.x, (int)gridDim.x);
 }
 
-__device__ __forceinline__ void pf_publish(const GemmParams& p, unsigned int seq, int count) {
-  const unsigned long long v = ((unsigned long long)seq << 32) | ((unsigned long long)(p.pf_index & 0xffff) << 16) |
-                               (unsigned long long)(count & 0xffff);
-  // A plain relaxed store: the slot may briefly step back when the successor kernel's CTA of the same index is already
-  // publishing (programmatic early launch) — the prefetcher then only waits a little longer.  (An atomicMax here cost
-  // the TMA producer thread 35 % of its issue rate: r02 timeline, gate/up 61 -> 82 us.)
-  if (p.pf_pub == 1) atomicMax(p.pf_prog + blockIdx.x, v);
-  else asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p.pf_prog + blockIdx.x), "l"(v) : "memory");
-}
-
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -221,8 +203,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       bool first = true;
-      int pf_count = 0;
-      const unsigned int pf_seq = p.pf_prog ? *reinterpret_cast<const volatile unsigned int*>(p.pf_seq) : 0u;
       GemmSeg sg;
       for (int idx = 0; gemm_get_seg(p, idx, sg, m_tiles_rt); ++idx) {
         const int m_t = sg.m_t, n_t = sg.n_t, kb0 = sg.kb0, kb1 = sg.kb1;
@@ -246,7 +226,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             const int npf = min(npre + p.l2_prefetch_kb, kb1 - kb0);
             for (int i = npre; i < npf; ++i) tma_prefetch_l2_2d(&tmap_a, (kb0 + i) * kGemmBlockK, m_t * kGemmBlockM);
-            if (p.pf_prog && p.pf_pub != 3) { pf_count += npre; pf_publish(p, pf_seq, pf_count); }
             pdl_wait();
             _ts.mark();
             for (int i = 0; i < npre; ++i)
@@ -264,7 +243,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kGemmBlockK, a_row, p.hint_a);
           tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n_t * BLOCK_N + b_off, p.hint_b);
-          if (p.pf_prog && p.pf_pub != 3 && ((++pf_count & 1) == 0 || kb + 1 == kb1)) pf_publish(p, pf_seq, pf_count);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -278,8 +256,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      int pf_count = 0;
-      const unsigned int pf_seq = (p.pf_prog && p.pf_pub == 3) ? *reinterpret_cast<const volatile unsigned int*>(p.pf_seq) : 0u;
       GemmSeg sg;
       for (int idx = 0; gemm_get_seg(p, idx, sg, m_tiles_rt); ++idx) {
         const int kb0 = sg.kb0, kb1 = sg.kb1;
@@ -299,7 +275,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (p.pf_prog && p.pf_pub == 3 && ((++pf_count & 3) == 0 || kb + 1 == kb1)) pf_publish(p, pf_seq, pf_count);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue

@@ -141,15 +141,14 @@ int launch_gemm_2cta_inst(const CUtensorMap* ta, const CUtensorMap* tb, const Ge
   return 0;
 }
 
-// Host side of the weight-stream prefetcher (prefetch.cuh): while a decode step is being enqueued, every weight-streaming
-// GEMM takes the next index of the step's table; in `recording` mode its descriptor is appended as well.
+// Host side of the weight-stream prefetch (prefetch.cuh): while a decode step is being enqueued, every weight-streaming
+// GEMM takes the next index of the step's table; in `recording` mode (first, eager enqueue of a graph key) its
+// descriptor is appended, in capture mode the engine launches the prefetch of the NEXT table entry beside it.
 struct PfCtx {
-  bool active = false;      // this enqueue publishes progress / is followed by a prefetch kernel
-  bool recording = false;   // first (eager) enqueue of a graph key: build the table
+  bool active = false;
+  bool recording = false;
   int count = 0;            // GEMMs seen so far in this enqueue
   std::vector<PfGemm> table;
-  unsigned long long* d_prog = nullptr;   // [num_sms]
-  unsigned int* d_seq = nullptr;
 };
 
 struct GemmArgs {
@@ -170,6 +169,9 @@ struct GemmArgs {
   long long group_out_stride = 0;   // n_rt / row_off are arrays of `groups` entries
   PfCtx* pf = nullptr;              // weight-stream prefetcher context of the step being enqueued (decode only)
 };
+
+// GEMMs whose weight operand depends on nothing the step computes (decode swap-AB, no device-side extents)
+inline bool pf_eligible(const GemmArgs& a) { return a.stream_a && !a.n_rt && !a.m_rt && a.groups == 0 && a.N <= a.block_n; }
 
 inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStream_t s) {
   B200_REQUIRE(a.K % 8 == 0, "K must be a multiple of 8");
@@ -220,20 +222,15 @@ inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStr
       p.sched = 1; p.sk_slots = slots; grid = g2;
     }
   }
-  p.pf_prog = nullptr; p.pf_seq = nullptr; p.pf_index = 0;
-  {
-    static const int pub = getenv("B200_PF_PUB") ? atoi(getenv("B200_PF_PUB")) : 3;
-    p.pf_pub = pub;
-  }
-  if (a.pf && a.pf->active && p.prefetch_a && a.groups == 0 && p.n_tiles == 1 && a.pf->count < kPfMaxGemms) {
-    p.pf_prog = a.pf->d_prog; p.pf_seq = a.pf->d_seq; p.pf_index = a.pf->count++;
-    if (a.pf->recording) {
+  if (a.pf && a.pf->active && pf_eligible(a) && p.n_tiles == 1) {
+    if (a.pf->recording && a.pf->count < kPfMaxGemms) {
       PfGemm g{};
       g.tmap_a = *ta;
       g.sched = GemmSched{p.m_tiles, p.n_tiles, p.splits, p.kb_total, p.kb_per_split, p.sched};
       g.grid = grid;
       a.pf->table.push_back(g);
     }
+    a.pf->count++;
   }
   B200_REQUIRE(p.splits == 1 || a.epi == EPI_T_PARTIAL, "split-K only with the fp32 partial epilogue");
   const bool use_2cta = getenv("B200_NO_2CTA") == nullptr;

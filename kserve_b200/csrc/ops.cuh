@@ -384,7 +384,6 @@ struct StepParams {
   StepState* st;
   P2P pp; int use_p2p;                    // vocab-parallel candidates arrive through peer memory
   uint32_t* seen; int seen_words; int V;  // repetition-penalty bitmap [B][seen_words] (null when the penalty is off)
-  unsigned int* pf_seq;                   // step sequence number of the weight-stream prefetcher (prefetch.cuh), bumped here
 };
 
 __global__ void __launch_bounds__(128) step_update_kernel(const StepParams p) {
@@ -395,7 +394,6 @@ __global__ void __launch_bounds__(128) step_update_kernel(const StepParams p) {
   __shared__ int s_stop, s_unfinished;
   StepState* st = p.st;
   if (p.use_p2p && threadIdx.x == 0) p.pp.row_epoch[0] += 1;   // epoch base of the next step's peer all-reduces
-  if (p.pf_seq && threadIdx.x == 0) *p.pf_seq += 1;            // every GEMM of this step has completed (PDL chain)
   if (st->done) return;
   const int step = st->step;
   if (threadIdx.x == 0) { s_stop = 0; s_unfinished = 0; }
