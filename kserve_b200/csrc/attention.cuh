@@ -205,7 +205,38 @@ struct AttnDecodeParams {
   const float* qkv_partial; int qkv_splits; long long qkv_split_stride; long long ld_qkv_partial;
   const bf16* cos_tab; const bf16* sin_tab;
   bf16* kcache_w; bf16* vcache_w;
+  // splits > 1: per-(sequence, kv head) arrival counters (zero between launches).  When set, the LAST split CTA to
+  // arrive merges the partials itself (in split order: deterministic) and no attn_combine_kernel follows — one kernel
+  // boundary less on the tensor-parallel decode path, where few (sequence, kv head) pairs per GPU force the split.
+  int* split_counter;
 };
+
+// called by every CTA of a split launch after its partial (or its "empty" marker) is in global memory
+__device__ __forceinline__ void attn_decode_arrive_and_merge(const AttnDecodeParams& p, int bh, int b, int kvh) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(p.split_counter + bh, 1) == p.splits - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) p.split_counter[bh] = 0;
+  __threadfence();
+  const int G = p.G, d = threadIdx.x;
+  const long long base = (long long)bh * p.splits * G;
+  for (int r = 0; r < G; ++r) {
+    float M = -INFINITY;
+    for (int s = 0; s < p.splits; ++s) M = fmaxf(M, __ldcg(p.part_ml + (base + (long long)s * G + r) * 2));
+    float L = 0.f, acc = 0.f;
+    for (int s = 0; s < p.splits; ++s) {
+      const long long row = base + (long long)s * G + r;
+      const float ms = __ldcg(p.part_ml + row * 2);
+      const float f = (ms == -INFINITY) ? 0.f : exp2f(ms - M);
+      L += __ldcg(p.part_ml + row * 2 + 1) * f;
+      acc += __ldcg(p.part_o + row * kHeadDim + d) * f;
+    }
+    p.out[(long long)b * p.ldo + (kvh * G + r) * kHeadDim + d] = __float2bfloat16_rn(acc / L);
+  }
+}
 
 __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDecodeParams p) {
   TraceScope _ts(TK_ATTN_DECODE);
@@ -226,6 +257,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
   float* pml = p.part_ml + ((long long)bh * p.splits + split) * G * 2;
   if (t0 >= t1) {  // empty split (uniform for the CTA)
     if (p.splits > 1 && threadIdx.x < G) { pml[threadIdx.x * 2] = -INFINITY; pml[threadIdx.x * 2 + 1] = 0.f; }
+    if (p.splits > 1 && p.split_counter) attn_decode_arrive_and_merge(p, bh, b, kvh);
     return;
   }
   const uint32_t sQ = smem_u32(smem);       // 16 rows x 256 B = 4 KB
@@ -457,6 +489,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnDec
       if (d == 0) { pml[r * 2] = M; pml[r * 2 + 1] = L; }
     }
   }
+  if (p.splits > 1 && p.split_counter) attn_decode_arrive_and_merge(p, bh, b, kvh);
 }
 
 // one CTA (128 threads) per (batch row, query head)

@@ -119,6 +119,7 @@ struct b200_engine {
   int sk_tiles = 0;
   size_t sk_ws_floats = 0;
   float *part_o = nullptr, *part_ml = nullptr;
+  int* attn_split_cnt = nullptr;   // [max_batch * nkv] arrival counters of the split decode attention
   float* cand_val = nullptr;
   int32_t* cand_idx = nullptr;
   float* cand_val_all = nullptr;
@@ -166,6 +167,9 @@ struct b200_engine {
   void* ar_peer_map[kMaxTp] = {nullptr};
   int *row_epoch = nullptr, *cand_epoch = nullptr;
   int ar_index = 0;   // index of the next peer all-reduce inside the forward pass being recorded
+  int big_epoch[2] = {0, 0};   // prefill all-reduce epochs, one per micro-batch stream (identical on every rank)
+  int* big_cnt = nullptr;      // [2] CTA arrival counters of allreduce_big_kernel
+  bool ybuf_in_block = false;  // ybuf lives inside the IPC-shared exchange block (tp > 1)
   bool p2p_ready = false;
   P2P p2p{};
   b200_timing_t timing{};
@@ -232,8 +236,21 @@ static int pick_splits(const b200_engine* e, int n_out, int K) {
   return effective_splits(K, s);
 }
 
+// prefill: all-reduce of a micro-batch's row-parallel GEMM output (bandwidth regime).  The engine's own peer-memory kernel
+// (p2p.cuh: allreduce_big_kernel) when the exchange block is mapped; NCCL otherwise or with B200_PREFILL_NCCL=1 (A/B).
 static int allreduce_bf16(b200_engine* e, bf16* buf, size_t count, cudaStream_t s) {
   if (e->cfg.tp_size == 1) return 0;
+  static const bool force_nccl = getenv("B200_PREFILL_NCCL") != nullptr;
+  static const int ar_ctas = getenv("B200_PREFILL_AR_CTAS") ? atoi(getenv("B200_PREFILL_AR_CTAS")) : 64;
+  if (e->p2p_ready && !force_nccl && buf >= e->ybuf && buf + count <= e->ybuf + (size_t)e->cap_T * e->H && count % 8 == 0) {
+    const int lane = (s == e->stream2) ? 1 : 0;
+    const int epoch = ++e->big_epoch[lane];
+    allreduce_big_kernel<<<ar_ctas, 256, 0, s>>>(e->p2p, (long long)e->p2p.lay.total, (long long)(buf - e->ybuf), (long long)count,
+                                                 epoch, lane, e->big_cnt + lane);
+    B200_CUDA_OK(cudaGetLastError());
+    e->launches++;
+    return 0;
+  }
   Nccl& n = Nccl::get();
   B200_NCCL_OK(n.AllReduce(buf, buf, count, Nccl::kBf16, Nccl::kSum, e->comm, s));
   return 0;
@@ -334,8 +351,10 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
       ap.fuse_rope = 1; ap.qkv = rp.qkv; ap.ld_qkv = rp.ld; ap.qkv_partial = rp.partial; ap.qkv_splits = rp.splits;
       ap.qkv_split_stride = rp.split_stride; ap.ld_qkv_partial = rp.ld_partial; ap.cos_tab = e->cos_tab; ap.sin_tab = e->sin_tab;
       ap.kcache_w = kc; ap.vcache_w = vc;
+      static const bool fold = getenv("B200_ATTN_COMBINE_KERNEL") == nullptr;   // =1: separate attn_combine_kernel (A/B)
+      ap.split_counter = fold ? e->attn_split_cnt : nullptr;
       if ((rc = launch_attn_decode(ap, B, s))) return rc;
-      e->launches += ap.splits > 1 ? 2 : 1;
+      e->launches += (ap.splits > 1 && !ap.split_counter) ? 2 : 1;
     } else {
       AttnPrefillParams ap{};
       ap.q = e->qkv; ap.ldq = e->qkv_cols; ap.out = e->attn; ap.ldo = e->nh * kHeadDim;
@@ -1044,7 +1063,7 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   if ((rc = dmalloc(&e->qkv, T * e->qkv_cols))) return rc;
   if ((rc = dmalloc(&e->attn, T * e->nh * kHeadDim))) return rc;
   if ((rc = dmalloc(&e->hbuf, T * e->I))) return rc;
-  if ((rc = dmalloc(&e->ybuf, T * H))) return rc;
+  if (tp == 1 && (rc = dmalloc(&e->ybuf, T * H))) return rc;   // tp > 1: inside the IPC-shared exchange block (below)
   if ((rc = dmalloc(&e->xl, (size_t)c->max_batch * H))) return rc;
   if ((rc = dmalloc(&e->qdec, (size_t)c->max_batch * e->nh * kHeadDim))) return rc;
   if ((rc = dmalloc(&e->logits, (size_t)c->max_batch * e->Vl))) return rc;
@@ -1076,6 +1095,8 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   B200_CUDA_OK(cudaMemset(e->sk_flags, 0, (size_t)e->sk_tiles * sizeof(int)));
   if ((rc = dmalloc(&e->part_o, (size_t)c->max_batch * e->nkv * 8 * e->G * kHeadDim))) return rc;
   if ((rc = dmalloc(&e->part_ml, (size_t)c->max_batch * e->nkv * 8 * e->G * 2))) return rc;
+  if ((rc = dmalloc(&e->attn_split_cnt, (size_t)c->max_batch * e->nkv))) return rc;
+  B200_CUDA_OK(cudaMemset(e->attn_split_cnt, 0, (size_t)c->max_batch * e->nkv * sizeof(int)));
   if ((rc = dmalloc(&e->cand_val, (size_t)c->max_batch * 16))) return rc;
   if ((rc = dmalloc(&e->cand_idx, (size_t)c->max_batch * 16))) return rc;
   if ((rc = dmalloc(&e->cand_val_all, (size_t)c->max_batch * tp))) return rc;
@@ -1116,8 +1137,13 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   if (tp > 1) {
     B200_REQUIRE(tp <= kMaxTp && c->max_batch <= kArRows, "tp_size / max_batch exceed the peer-exchange layout");
     const ArLayout lay = ArLayout::make(e->H);
-    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->ar_local), lay.total));
-    B200_CUDA_OK(cudaMemset(e->ar_local, 0, lay.total));
+    // one allocation = one IPC handle: [decode LL packets | candidate exchange | flags | prefill exchange buffer y[T][H]]
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->ar_local), lay.total + T * H * sizeof(bf16)));
+    B200_CUDA_OK(cudaMemset(e->ar_local, 0, lay.total + T * H * sizeof(bf16)));
+    e->ybuf = reinterpret_cast<bf16*>(e->ar_local + lay.total);
+    e->ybuf_in_block = true;
+    if ((rc = dmalloc(&e->big_cnt, (size_t)2))) return rc;
+    B200_CUDA_OK(cudaMemset(e->big_cnt, 0, 2 * sizeof(int)));
     if ((rc = dmalloc(&e->row_epoch, (size_t)kArRows))) return rc;
     if ((rc = dmalloc(&e->cand_epoch, (size_t)kArRows))) return rc;
     B200_CUDA_OK(cudaMemset(e->row_epoch, 0, kArRows * sizeof(int)));
@@ -1148,8 +1174,8 @@ int b200_engine_destroy(b200_engine_t* e) {
   if (e->row_epoch) cudaFree(e->row_epoch);
   if (e->cand_epoch) cudaFree(e->cand_epoch);
   void* ptrs[] = {e->embed, e->lm_head, e->final_norm, e->cos_tab, e->sin_tab, e->kcache, e->vcache, e->d_page_table,
-                  e->x, e->xn, e->qkv, e->attn, e->hbuf, e->ybuf, e->xl, e->qdec, e->logits, e->ws, e->sk_ws, e->sk_flags,
-                  e->tok_expert, e->tok_row, e->tok_weight, e->e_count, e->e_off, e->xg, e->hg, e->yg, e->part_o, e->part_ml,
+                  e->x, e->xn, e->qkv, e->attn, e->hbuf, e->ybuf_in_block ? nullptr : (void*)e->ybuf, e->big_cnt, e->xl, e->qdec, e->logits, e->ws, e->sk_ws, e->sk_flags,
+                  e->tok_expert, e->tok_row, e->tok_weight, e->e_count, e->e_off, e->xg, e->hg, e->yg, e->part_o, e->part_ml, e->attn_split_cnt,
                   e->cand_val, e->cand_idx, e->cand_val_all, e->cand_idx_all, e->d_tok, e->d_tok_seq, e->d_tok_pos, e->d_cu,
                   e->d_seq_slot, e->d_last_rows, e->d_cur_len, e->d_next_tok, e->d_dec_pos, e->d_finished, e->d_out_tokens,
                   e->d_forced, e->d_eos, e->d_stop_tok, e->d_stop_off, e->d_state};

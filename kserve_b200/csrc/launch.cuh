@@ -333,7 +333,7 @@ inline int launch_attn_decode(const AttnDecodeParams& p, int B, cudaStream_t s) 
   B200_REQUIRE(p.G >= 1 && p.G <= 8, "GQA group size must be in [1, 8]");
   dim3 grid(B * p.nkv, p.splits);
   B200_CUDA_OK(launch_k(attn_decode_kernel, grid, dim3(kAttnThreads), kDecodeSmem, s, p));
-  if (p.splits > 1) {
+  if (p.splits > 1 && !p.split_counter) {
     B200_CUDA_OK(launch_k(attn_combine_kernel, dim3(B * p.nh), dim3(128), 0, s, (const float*)p.part_o, (const float*)p.part_ml, p.out, p.ldo, p.nkv, p.G, p.splits));
   }
   return 0;

@@ -286,4 +286,89 @@ allreduce2_norm_kernel(const P2P pp, bf16* __restrict__ x, const bf16* __restric
   }
 }
 
+// ---- prefill: bandwidth-regime all-reduce over peer memory ---------------------------------------------------------
+// In place over the row-parallel GEMM output y[T][H] of one micro-batch (up to 256 MiB), which lives inside the
+// IPC-shared block of every rank (so peers can address it).  Two-shot by element ranges: rank j owns elements
+// [j * n/tp, (j+1) * n/tp): it reads that range from every rank (7 remote NVLink loads + 1 local per 16 bytes), sums in
+// rank order in fp32, rounds once and stores the result into EVERY rank's buffer (in place: a range is only ever read by
+// its owner).  Same bytes on the wire as NCCL's all-reduce, but:
+//   * the CTAs are light (256 threads, <= 128 registers, no shared memory) and co-reside with the persistent 200 KB-smem prefill GEMM CTAs
+//     of the OTHER micro-batch, so the exchange really overlaps that GEMM — NCCL's kernels do not fit beside them and
+//     only ran in the gaps (r01: TTFT 99.5 ms at TP = 8 for 46 ms of compute);
+//   * the sum order is fixed (rank order), every rank holds bit-identical rows.
+// Synchronisation: epoch flags in each rank's block.  arrive[rank] = "my y is complete" (the GEMM is an earlier kernel on
+// this stream), done[rank] = "my range has been written everywhere"; the kernel's last CTA waits for every done flag, so
+// the following rmsnorm kernel sees the complete rows.  `lane` selects one of two flag sets (the two micro-batch streams).
+__global__ void __launch_bounds__(256, 2)
+allreduce_big_kernel(const P2P pp, long long buf_off, long long elem0, long long n_elems, int epoch, int lane, int* cta_counter) {
+  TraceScope _ts(TK_OTHER);
+  const int tp = pp.tp;
+  int* my_flags = reinterpret_cast<int*>(pp.peer[pp.rank] + pp.lay.big_flag_off) + lane * 2 * kMaxTp;
+  if (blockIdx.x == 0 && threadIdx.x < tp) {
+    __threadfence_system();
+    int* f = reinterpret_cast<int*>(pp.peer[threadIdx.x] + pp.lay.big_flag_off) + lane * 2 * kMaxTp + pp.rank;
+    st_sys(f, epoch);
+  }
+  if (threadIdx.x < tp) spin_until(my_flags + threadIdx.x, epoch);
+  __syncthreads();
+  const long long vecs = n_elems / 8;                                  // 16-byte vectors (H % 8 == 0)
+  const long long per = (vecs + tp - 1) / tp;
+  const long long v0 = per * pp.rank, v1 = min(vecs, v0 + per);
+  const long long byte0 = buf_off + elem0 * 2;
+  // U vectors per thread per pass: tp * U 16-byte loads in flight per thread (U = 4 at tp = 2 ... 1 at tp = 8), enough to
+  // cover the ~2 us NVLink round trip at 64 CTAs
+  const int U = tp <= 2 ? 4 : (tp <= 4 ? 2 : 1);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long vb = v0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; vb < v1; vb += stride * U) {
+    uint4 q[4][kMaxTp];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long v = vb + u * stride;
+      if (u < U && v < v1) {
+#pragma unroll
+        for (int r = 0; r < kMaxTp; ++r)
+          if (r < tp && (u == 0 || r < 4)) q[u][r] = ld_nc_v4(pp.peer[r] + byte0 + v * 16);   // read once, written before the arrive flags
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long v = vb + u * stride;
+      if (u < U && v < v1) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int r = 0; r < kMaxTp; ++r) {
+          if (r < tp && (u == 0 || r < 4)) {
+            const uint32_t w[4] = {q[u][r].x, q[u][r].y, q[u][r].z, q[u][r].w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              float2 p2 = unpack_bf16x2(w[t]);
+              acc[2 * t] += p2.x;
+              acc[2 * t + 1] += p2.y;
+            }
+          }
+        }
+        const uint4 o = pack8(acc);
+#pragma unroll
+        for (int r = 0; r < kMaxTp; ++r)
+          if (r < tp)
+            *reinterpret_cast<uint4*>(pp.peer[r] + byte0 + v * 16) = o;     // weak stores; __threadfence_system() below orders them before "done"
+      }
+    }
+  }
+  // every CTA's stores must be out before this rank says "done"; the last CTA says it and waits for everybody's
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int last;
+  if (threadIdx.x == 0) last = (atomicAdd(cta_counter, 1) == (int)gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) *cta_counter = 0;
+  if (threadIdx.x < tp) {
+    __threadfence_system();
+    int* f = reinterpret_cast<int*>(pp.peer[threadIdx.x] + pp.lay.big_flag_off) + lane * 2 * kMaxTp + kMaxTp + pp.rank;
+    st_sys(f, epoch);
+    spin_until(my_flags + kMaxTp + threadIdx.x, epoch);
+  }
+}
+
 }  // namespace b200

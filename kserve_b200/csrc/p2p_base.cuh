@@ -21,7 +21,7 @@ constexpr int kArRows = 64;   // max decode batch
 
 // Layout of the IPC-shared block (offsets in bytes, computed on the host for a given H)
 struct ArLayout {
-  size_t y_off, flag_off, cval_off, cidx_off, cflag_off, total;
+  size_t y_off, flag_off, cval_off, cidx_off, cflag_off, big_flag_off, total;
   int H;
   __host__ __device__ static ArLayout make(int H) {
     ArLayout l;
@@ -31,7 +31,8 @@ struct ArLayout {
     l.cval_off = l.flag_off + (size_t)2 * kMaxTp * kArRows * 4;    // float cand_val[2][kMaxTp][kArRows]
     l.cidx_off = l.cval_off + (size_t)2 * kMaxTp * kArRows * 4;    // int cand_idx[2][kMaxTp][kArRows]
     l.cflag_off = l.cidx_off + (size_t)2 * kMaxTp * kArRows * 4;   // int cand_flag[2][kMaxTp][kArRows]
-    l.total = l.cflag_off + (size_t)2 * kMaxTp * kArRows * 4;
+    l.big_flag_off = l.cflag_off + (size_t)2 * kMaxTp * kArRows * 4;   // int big_flag[2 streams][2 phases][kMaxTp] (prefill all-reduce)
+    l.total = (l.big_flag_off + (size_t)2 * 2 * kMaxTp * 4 + 255) & ~(size_t)255;   // the prefill exchange buffer starts here
     return l;
   }
 };

@@ -38,7 +38,10 @@ def main():
     torch.cuda.synchronize()
     cap = 400000
     _lib.check(lib.b200_debug_trace(cap), "trace")
-    eng.run_staged(False, 1)         # one traced decode step (graph replay)
+    if os.environ.get("PHASE", "decode") == "prefill":
+        eng.run_staged(True, 0)      # one traced prefill (eager launches, micro-batched under tensor parallelism)
+    else:
+        eng.run_staged(False, 1)     # one traced decode step (graph replay)
     torch.cuda.synchronize()
     buf = np.zeros((cap, 4), dtype=np.uint64)
     n = C.c_int32()
@@ -70,6 +73,8 @@ def main():
     rows = []
     for k, a, b, c, last_start, wmin, wmax in launches:
         name = KIND.get(k % 100, "?")
+        if k % 100 == 51:
+            name = f"gemm2cta:{EPI.get((k // 100) % 10)}"
         if k % 100 == 1:
             name += f":{EPI.get((k // 100) % 10)}:M{(k // 1000) * 128}"
         rows.append((name, (a - base) / 1e3, (b - base) / 1e3, (b - a) / 1e3, (a - prev_end) / 1e3, c, (last_start - a) / 1e3,
@@ -77,7 +82,7 @@ def main():
         prev_end = max(prev_end, b)
     per = (len(rows) - 4) // layers if layers else len(rows)
     print("name                          start     end     dur  gap_prev  ctas  cta_start_spread  wait_done(min,max)")
-    for r in rows[: 2 + 2 * per + 6]:
+    for r in rows[: int(os.environ.get("ROWS", 2 + 2 * per + 6))]:
         print(f"{r[0]:28s} {r[1]:7.1f} {r[2]:7.1f} {r[3]:7.1f} {r[4]:8.1f} {r[5]:5d} {r[6]:8.1f}   {r[7]:7.1f} {r[8]:7.1f}")
     eng.close()
 
