@@ -236,11 +236,13 @@ static int pick_splits(const b200_engine* e, int n_out, int K) {
   return effective_splits(K, s);
 }
 
-// prefill: all-reduce of a micro-batch's row-parallel GEMM output (bandwidth regime).  The engine's own peer-memory kernel
-// (p2p.cuh: allreduce_big_kernel) when the exchange block is mapped; NCCL otherwise or with B200_PREFILL_NCCL=1 (A/B).
+// prefill: all-reduce of a micro-batch's row-parallel GEMM output (bandwidth regime): ncclAllReduce by default.  The
+// engine's own peer-memory kernel (p2p.cuh: allreduce_big_kernel, B200_PREFILL_OWN_AR=1) is correct (tests/test_tp_gpu.py
+// run it too) but measured slower — TTFT 228.9 vs 220.6 ms at TP = 2, 108.5 vs 99.7 ms at TP = 8 (r02): its pull-based
+// reduce-scatter reaches ~300 GB/s per direction over NVLink, short of NCCL's NVLS path.
 static int allreduce_bf16(b200_engine* e, bf16* buf, size_t count, cudaStream_t s) {
   if (e->cfg.tp_size == 1) return 0;
-  static const bool force_nccl = getenv("B200_PREFILL_NCCL") != nullptr;
+  static const bool force_nccl = getenv("B200_PREFILL_OWN_AR") == nullptr;
   static const int ar_ctas = getenv("B200_PREFILL_AR_CTAS") ? atoi(getenv("B200_PREFILL_AR_CTAS")) : 64;
   if (e->p2p_ready && !force_nccl && buf >= e->ybuf && buf + count <= e->ybuf + (size_t)e->cap_T * e->H && count % 8 == 0) {
     const int lane = (s == e->stream2) ? 1 : 0;

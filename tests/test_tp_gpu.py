@@ -47,20 +47,24 @@ def _check(ret, name, exact_ids=False):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("overlap_min_t", ["2048", "1"])   # "1": force the chunked / overlapped prefill path on the tiny prompts
+@pytest.mark.parametrize("overlap_min_t", ["2048", "1", "own_ar"])   # "1": force the two-micro-batch prefill on the tiny prompts
 def test_tp2_matches_oracle_fixture(overlap_min_t):
     names = ["tiny_g4_ids", "tiny_g2_ids", "tiny_moe8_ids", "tiny_kv8_ids"]
-    ret = _run(2, names + ["tiny_kv8_peaked"], env=dict(B200_PREFILL_OVERLAP_MIN_T=overlap_min_t))
+    env = dict(B200_PREFILL_OVERLAP_MIN_T="1", B200_PREFILL_OWN_AR="1") if overlap_min_t == "own_ar" else \
+        dict(B200_PREFILL_OVERLAP_MIN_T=overlap_min_t)        # own_ar: the engine's peer-memory prefill all-reduce instead of NCCL
+    ret = _run(2, names + ["tiny_kv8_peaked"], env=env)
     for name in names:
         _check(ret, name)
     _check(ret, "tiny_kv8_peaked", exact_ids=True)
 
 
 @pytest.mark.parametrize("world", [4, 8])
-@pytest.mark.parametrize("overlap_min_t", ["2048", "1"])
+@pytest.mark.parametrize("overlap_min_t", ["2048", "own_ar"])
 def test_tp4_tp8_match_oracle_fixture(world, overlap_min_t):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    ret = _run(world, ["tiny_kv8_ids", "tiny_kv8_peaked"], env=dict(B200_PREFILL_OVERLAP_MIN_T=overlap_min_t), port=29640 + world)
+    env = dict(B200_PREFILL_OVERLAP_MIN_T="1", B200_PREFILL_OWN_AR="1") if overlap_min_t == "own_ar" else \
+        dict(B200_PREFILL_OVERLAP_MIN_T=overlap_min_t)
+    ret = _run(world, ["tiny_kv8_ids", "tiny_kv8_peaked"], env=env, port=29640 + world)
     _check(ret, "tiny_kv8_ids")
     _check(ret, "tiny_kv8_peaked", exact_ids=True)
