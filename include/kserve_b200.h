@@ -188,31 +188,47 @@ int b200_op_argmax(const void* logits, int64_t ld, int B, int V, float* out_val,
 int b200_kv_swap_out(b200_engine_t* e, int32_t slot, int32_t scrub);
 int b200_kv_swap_in(b200_engine_t* e, int32_t slot);
 
-/* Continuous (iteration-level) batching — SURVEY.md §8(f) rank 1.  Replaces the reference's strictly serial request
- * loop (python/huggingfaceserver/huggingfaceserver/generative_model.py:341-354: one `generate` at a time) and the
- * throughput role of the Go batcher (pkg/batcher/handler.go:157-188): sequences join and leave the running batch
- * between decode steps.  One engine, one scheduler thread (calls are not re-entrant); tp_size must be 1.
+/* Continuous (iteration-level) batching — SURVEY.md §8(f) ranks 1 and 4.  Replaces the reference's strictly serial
+ * request loop (python/huggingfaceserver/huggingfaceserver/generative_model.py:341-354: one `generate` at a time) and the
+ * throughput role of the Go batcher (pkg/batcher/handler.go:157-188): sequences join and leave the running batch between
+ * decode steps.  One engine per GPU, one scheduler thread (calls are not re-entrant); under tensor parallelism every rank
+ * makes the same calls in the same order (kserve_b200/tp.py replicates them), all host-side decisions are deterministic.
  *
- *   b200_cb_begin   enter the mode (slot s owns KV pages [s * pages_per_seq, (s+1) * pages_per_seq)); eos ids apply to
- *                   every sequence, as `generation_config.eos_token_id` does in the reference
- *   b200_cb_admit   prefill n new prompts (host int64 token rows) into free slots and emit their first token;
- *                   per-sequence max_new and up to 4 stop sequences of <= 8 tokens each:
- *                   stop_count[i] sequences for prompt i, stop_offsets = running offsets (sum(stop_count) + 1 entries)
- *                   into stop_tokens; slots_out[i] receives the slot of prompt i
- *   b200_cb_step    n decode iterations over every running slot (CUDA graph per row count); finished sequences are
- *                   frozen on the device until released
+ *   b200_cb_begin   enter the mode: every KV page goes to the free pool; eos ids apply to every sequence, as
+ *                   `generation_config.eos_token_id` does in the reference
+ *   b200_cb_config  prefill_chunk_tokens: 0 = a prompt is prefilled completely inside b200_cb_admit; >= 128 = prompts
+ *                   are prefilled in chunks of at most that many packed tokens (multiples of 128 per prompt), ONE chunk
+ *                   pass before every decode step of b200_cb_step, so an admit never stalls the running sequences for
+ *                   longer than a chunk.  prefix_cache != 0: full 128-token blocks of a finished prefill stay in the
+ *                   pool (reference counted, least-recently-used eviction) keyed by the chain hash of the tokens up to
+ *                   and including the block; a later prompt with the same leading blocks shares those pages and only
+ *                   its remaining tokens are computed (greedy results are identical to a full prefill).
+ *   b200_cb_admit   n new prompts (host int64 token rows) into free slots: KV pages for len + max_new tokens each (rc -7
+ *                   and "KV page pool exhausted" when the pool, after evicting unused cached blocks, cannot supply
+ *                   them: nothing is admitted), per-sequence max_new, up to 4 stop sequences of <= 8 tokens each
+ *                   (stop_count[i] sequences for prompt i, stop_offsets = running offsets, sum(stop_count) + 1 entries,
+ *                   into stop_tokens) and, optionally, per-sequence logits processors / sampling: `sampling[i]` uses the
+ *                   repetition_penalty / do_sample / temperature / top_p / top_k / seed fields of b200_gen_params_t
+ *                   (NULL = greedy; tp_size must be 1 when any is active); slots_out[i] receives the slot of prompt i
+ *   b200_cb_step    n iterations; each = one prefill chunk pass if prompts are pending, then one decode step over every
+ *                   running slot (CUDA graph per row count); finished sequences are frozen on the device until released
  *   b200_cb_poll    per slot: tokens generated so far, finished flag, stop-sequence flag ([max_batch] each)
  *   b200_cb_read    generated tokens [first, first + cap) of a slot (for streaming reads as well as final results)
- *   b200_cb_release free the slot (its row leaves the decode batch at the next step)
+ *   b200_cb_release free the slot and drop its page references (its row leaves the decode batch at the next step)
+ *   b200_cb_stats   out8 = {prompt tokens admitted, of those served from shared pages, prefilled tokens, cache evictions,
+ *                   prefill passes, pages an admit could obtain now, cached blocks, prompts still being prefilled}
  *   b200_cb_end     leave the mode
  * Greedy results per sequence are identical to b200_generate on that prompt alone. */
 int b200_cb_begin(b200_engine_t* e, int64_t pad_token_id, const int64_t* eos_token_ids, int32_t num_eos);
+int b200_cb_config(b200_engine_t* e, int32_t prefill_chunk_tokens, int32_t prefix_cache);
 int b200_cb_admit(b200_engine_t* e, int32_t n, const int64_t* const* rows, const int32_t* lens, const int32_t* max_new,
-                  const int32_t* stop_count, const int32_t* stop_offsets, const int64_t* stop_tokens, int32_t* slots_out);
+                  const int32_t* stop_count, const int32_t* stop_offsets, const int64_t* stop_tokens,
+                  const b200_gen_params_t* sampling, int32_t* slots_out);
 int b200_cb_step(b200_engine_t* e, int32_t n_steps);
 int b200_cb_poll(b200_engine_t* e, int32_t* n_gen, int32_t* finished, int32_t* stop_hit);
 int b200_cb_read(b200_engine_t* e, int32_t slot, int32_t first, int64_t* out, int32_t cap, int32_t* n_out);
 int b200_cb_release(b200_engine_t* e, int32_t slot);
+int b200_cb_stats(b200_engine_t* e, int64_t* out8);
 int b200_cb_end(b200_engine_t* e);
 
 /* Debug timeline: capacity > 0 enables per-CTA {t0, t1 (globaltimer ns), kind, block} records (24 bytes each),

@@ -23,6 +23,10 @@ def main(argv=None):
     parser.add_argument("--max_batch", type=int, default=32)
     parser.add_argument("--continuous_batching", action="store_true",
                         help="iteration-level batching: requests join / leave the running decode batch between steps")
+    parser.add_argument("--prefill_chunk_tokens", type=int, default=2048,
+                        help="with --continuous_batching: prompts are prefilled in chunks of this many tokens between decode steps (0 = whole prompts at admit)")
+    parser.add_argument("--enable_prefix_caching", action="store_true",
+                        help="with --continuous_batching: share the KV pages of common 128-token prompt prefixes between requests")
     parser.add_argument("--tensor_parallel_size", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
     # the agent's flags (cmd/agent/main.go:66-68 --enable-batcher / --max-batchsize / --max-latency), same defaults
     parser.add_argument("--enable_batcher", "--enable-batcher", dest="enable_batcher", action="store_true",
@@ -49,6 +53,7 @@ def main(argv=None):
     model = B200GenerativeModel(args.model_name, path, max_model_len=args.max_model_len, max_batch=args.max_batch,
                                 device=int(os.environ.get("LOCAL_RANK", "0")), tensor_parallel_size=args.tensor_parallel_size,
                                 tp_rank=rank, nccl_id=nccl_id, continuous_batching=args.continuous_batching)
+    model.prefill_chunk_tokens, model.prefix_cache = max(0, args.prefill_chunk_tokens), args.enable_prefix_caching
     model.load()
     if rank != 0:
         from .tp import follower_loop

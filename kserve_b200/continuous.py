@@ -25,7 +25,29 @@ from typing import Callable, Deque, Dict, List, Optional, Sequence
 
 import torch
 
-from .engine import B200Engine, GenerateResult
+from .engine import B200Engine, GenerateResult, PoolExhausted
+
+
+class ReplicatedEngine:
+    """Tensor parallel: the scheduler runs on rank 0 only; every b200_cb_* call it makes is first replicated to the
+    follower ranks (tp.leader_call -> tp.follower_loop), which execute it on their engine in the same order.  All
+    host-side decisions of the engine (slots, pages, prefix hits, chunk boundaries) are deterministic, so the ranks stay
+    in lockstep and their poll / read results are identical."""
+    _REPLICATED = ("cb_begin", "cb_config", "cb_admit", "cb_step", "cb_poll", "cb_read", "cb_release", "cb_end")
+
+    def __init__(self, engine: B200Engine):
+        self._e = engine
+
+    def __getattr__(self, name):
+        attr = getattr(self._e, name)
+        if name not in self._REPLICATED:
+            return attr
+
+        def call(*args, **kwargs):
+            from .tp import leader_call
+            leader_call(name, args, kwargs)
+            return attr(*args, **kwargs)
+        return call
 
 
 @dataclass
@@ -37,6 +59,7 @@ class _Request:
     pad: int
     done: Callable[[Optional[GenerateResult], Optional[BaseException]], None]
     on_tokens: Optional[Callable[[int, List[int]], None]] = None   # (step, one token per row) for streaming
+    sampling: Optional[dict] = None          # repetition_penalty / do_sample / temperature / top_p / top_k / seed (None: greedy)
     slots: List[int] = field(default_factory=list)
     streamed: int = 0
     t_submit: float = field(default_factory=time.perf_counter)
@@ -46,8 +69,13 @@ class _Request:
 
 class ContinuousBatcher:
     def __init__(self, engine: B200Engine, pad_token_id: int = 0, eos_token_ids: Sequence[int] = (),
-                 steps_per_poll: int = 4, max_prefill_tokens: Optional[int] = None):
-        self.engine = engine
+                 steps_per_poll: int = 4, max_prefill_tokens: Optional[int] = None, prefill_chunk_tokens: int = 0,
+                 prefix_cache: bool = False):
+        """prefill_chunk_tokens > 0: admitted prompts are prefilled in chunks of that many packed tokens, one chunk pass
+        before every decode step, so a long admit never stalls the running sequences (0: whole prompts at admit).
+        prefix_cache: 128-token blocks of earlier prompts stay in the KV pool and are shared by later requests."""
+        self.engine = ReplicatedEngine(engine) if getattr(engine, "tp_size", 1) > 1 else engine
+        self.prefill_chunk_tokens, self.prefix_cache = int(prefill_chunk_tokens), bool(prefix_cache)
         self.pad = int(pad_token_id or 0)
         self.eos = [int(e) for e in eos_token_ids]
         self.steps_per_poll = max(1, int(steps_per_poll))
@@ -58,6 +86,7 @@ class ContinuousBatcher:
         self._stop = False
         self._thread: Optional[threading.Thread] = None
         self.free_slots = engine.max_batch
+        self._pool_blocked = False      # the last admit hit "KV page pool exhausted": retry only after a release
         self.fatal: Optional[BaseException] = None      # set when the scheduler thread died: submit raises it from then on
         self.on_fatal: Optional[Callable[[BaseException], None]] = None   # the model flips `ready` to False here
         # counters for the load tests / metrics
@@ -66,6 +95,8 @@ class ContinuousBatcher:
     # ------------------------------------------------------------------ lifecycle
     def start(self) -> None:
         self.engine.cb_begin(self.pad, self.eos)
+        if self.prefill_chunk_tokens or self.prefix_cache:
+            self.engine.cb_config(self.prefill_chunk_tokens, self.prefix_cache)
         self._thread = threading.Thread(target=self._loop, name="b200-continuous-batcher", daemon=True)
         self._thread.start()
 
@@ -79,7 +110,7 @@ class ContinuousBatcher:
 
     # ------------------------------------------------------------------ submission
     def submit_nowait(self, prompts: List[List[int]], padded: torch.Tensor, max_new_tokens: int,
-                      stop_sequences: Sequence[Sequence[int]], done, on_tokens=None) -> "_Request":
+                      stop_sequences: Sequence[Sequence[int]], done, on_tokens=None, sampling: Optional[dict] = None) -> "_Request":
         stops = [list(map(int, s)) for s in stop_sequences if len(s)]
         if len(prompts) > self.engine.max_batch:
             raise ValueError(f"request of {len(prompts)} prompts exceeds max_batch {self.engine.max_batch}")
@@ -88,7 +119,7 @@ class ContinuousBatcher:
         if any(len(p) < 1 or len(p) + int(max_new_tokens) > self.engine.max_seq_len for p in prompts) or int(max_new_tokens) < 1:
             raise ValueError("prompt + max_new_tokens exceeds the engine's max_seq_len (or empty prompt / max_new_tokens < 1)")
         req = _Request(prompts=[list(map(int, p)) for p in prompts], padded=padded, max_new=int(max_new_tokens),
-                       stops=stops, pad=self.pad, done=done, on_tokens=on_tokens)
+                       stops=stops, pad=self.pad, done=done, on_tokens=on_tokens, sampling=sampling or None)
         with self._cv:
             if self.fatal is not None:
                 raise RuntimeError(f"continuous batcher is down: {self.fatal}")
@@ -104,7 +135,7 @@ class ContinuousBatcher:
             self._cv.notify_all()
 
     async def submit(self, prompts: List[List[int]], padded: torch.Tensor, max_new_tokens: int,
-                     stop_sequences: Sequence[Sequence[int]] = (), on_tokens=None) -> GenerateResult:
+                     stop_sequences: Sequence[Sequence[int]] = (), on_tokens=None, sampling: Optional[dict] = None) -> GenerateResult:
         loop = asyncio.get_running_loop()
         fut: asyncio.Future = loop.create_future()
 
@@ -117,7 +148,7 @@ class ContinuousBatcher:
                 else:
                     fut.set_result(result)
             loop.call_soon_threadsafe(_set)
-        req = self.submit_nowait(prompts, padded, max_new_tokens, stop_sequences, done, on_tokens)
+        req = self.submit_nowait(prompts, padded, max_new_tokens, stop_sequences, done, on_tokens, sampling)
         try:
             return await fut
         except asyncio.CancelledError:
@@ -150,20 +181,38 @@ class ContinuousBatcher:
                     budget -= toks
         if not batch:
             return
-        prompts = [p for r in batch for p in r.prompts]
-        max_new = [r.max_new for r in batch for _ in r.prompts]
-        stops = [r.stops for r in batch for _ in r.prompts]
-        try:
-            slots = self.engine.cb_admit(prompts, max_new, stops)
-        except BaseException as e:       # the whole admit call failed: fail these requests, keep serving
-            for r in batch:
-                r.done(None, e)
-            return
+        while True:
+            prompts = [p for r in batch for p in r.prompts]
+            max_new = [r.max_new for r in batch for _ in r.prompts]
+            stops = [r.stops for r in batch for _ in r.prompts]
+            sampling = [r.sampling for r in batch for _ in r.prompts]
+            try:
+                slots = self.engine.cb_admit(prompts, max_new, stops, sampling if any(sampling) else None)
+                break
+            except PoolExhausted:            # nothing was admitted
+                if len(batch) > 1:           # retry with the head of the queue alone, the others wait their turn
+                    with self._cv:
+                        for r in reversed(batch[1:]):
+                            self._pending.appendleft(r)
+                    batch = batch[:1]
+                    continue
+                if self._running:            # wait for a release
+                    with self._cv:
+                        self._pending.appendleft(batch[0])
+                    self._pool_blocked = True
+                else:                        # the pool is idle and still too small for this request
+                    batch[0].done(None, ValueError("request does not fit the KV page pool"))
+                return
+            except BaseException as e:       # the whole admit call failed: fail these requests, keep serving
+                for r in batch:
+                    r.done(None, e)
+                return
+        self._pool_blocked = False
         now = time.perf_counter()
         i = 0
         for r in batch:
             r.slots = slots[i:i + len(r.prompts)]
-            r.t_first = now
+            r.t_first = 0.0 if self.prefill_chunk_tokens else now
             i += len(r.prompts)
             self._running.append(r)
         self.free_slots -= len(prompts)
@@ -179,9 +228,10 @@ class ContinuousBatcher:
             out[b, S:S + len(toks)] = torch.tensor(toks, dtype=torch.int64)
             self.engine.cb_release(sl)
         self.free_slots += len(r.slots)
+        self._pool_blocked = False
         self.stats["finished"] += 1
         res = GenerateResult(output_ids=out, stop_triggered=stop, num_generated=n_out, logits=None,
-                             prefill_ms=(r.t_first - r.t_submit) * 1e3, decode_ms=(time.perf_counter() - r.t_first) * 1e3,
+                             prefill_ms=((r.t_first or time.perf_counter()) - r.t_submit) * 1e3, decode_ms=(time.perf_counter() - (r.t_first or r.t_submit)) * 1e3,
                              decode_steps=max(0, n_out - 1), kernel_launches=0)
         r.done(res, None)
 
@@ -194,9 +244,12 @@ class ContinuousBatcher:
                 for sl in r.slots:
                     self.engine.cb_release(sl)
                 self.free_slots += len(r.slots)
+                self._pool_blocked = False
                 self.stats["cancelled"] += 1
                 continue
             g = [n_gen[s] for s in r.slots]
+            if r.t_first == 0.0 and min(g) >= 1:
+                r.t_first = time.perf_counter()          # chunked prefill: the first token appears some steps after the admit
             stopped = [s for s in r.slots if stop[s]]
             if stopped:
                 n_out = min(n_gen[s] for s in stopped)          # lockstep rows: everything after the match is dropped
@@ -232,7 +285,7 @@ class ContinuousBatcher:
                         self._cv.wait()
                     if self._stop:
                         break
-                if self._pending and self.free_slots > 0:
+                if self._pending and self.free_slots > 0 and not self._pool_blocked:
                     self._admit()
                 if self._running:
                     rows = sum(len(r.slots) for r in self._running)

@@ -27,6 +27,10 @@ struct AttnTcParams {
   const int32_t* cu_seqlens; const int32_t* seq_slot;
   int nh, nkv;
   float scale_log2;
+  // Chunked prefill / prefix reuse: tokens [0, kv_off[b]) of sequence b are already in the paged cache (an earlier
+  // chunk, or pages shared with a previous request) and the packed query rows are positions kv_off[b] ... of it.
+  // Must be a multiple of 128 (query tiles stay aligned with KV tiles); nullptr == all zero.
+  const int32_t* kv_off;
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -84,7 +88,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   if (q0 >= len) return;
   const int kvh = h / (p.nh / p.nkv);
   const int32_t* pages = p.page_table + (long long)p.seq_slot[b] * p.max_pages;
-  const int ntiles = qt + 1;   // causal: KV tiles 0..qt (tile size == q tile size)
+  const int off_tiles = p.kv_off ? (p.kv_off[b] >> 7) : 0;    // KV tiles that precede this chunk's first query row
+  const int ntiles = off_tiles + qt + 1;   // causal: KV tiles 0..off_tiles + qt (tile size == q tile size)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
@@ -179,14 +184,15 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     // ------------------------------------------------------------------ softmax / correction / epilogue
     const int q = warp & 3;
     const int r = q * 32 + lane;               // row of the tile handled by this thread
-    const int qpos = q0 + r;
+    const int qrow = q0 + r;                   // row inside this chunk (bounds / output row)
+    const int qpos = off_tiles * kTcKv + qrow;  // position in the sequence (causal mask)
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float m_ref = -INFINITY, l_run = 0.f;
     for (int j = 0; j < ntiles; ++j) {
       const int buf = j & 1;
       mbar_wait(&s_full[buf], (j >> 1) & 1);
       tcgen05_fence_after();
-      const bool diag = (j == qt);
+      const bool diag = (j == ntiles - 1);
       // pass 1: row max (log2 domain)
       float mx = -INFINITY;
 #pragma unroll 1
@@ -256,8 +262,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     mbar_wait(pv_done, (ntiles - 1) & 1);
     tcgen05_fence_after();
     const float inv = 1.0f / l_run;
-    const bool valid = qpos < len;
-    bf16* orow = p.out + (long long)(tok0 + qpos) * p.ldo + h * kHeadDim;
+    const bool valid = qrow < len;
+    bf16* orow = p.out + (long long)(tok0 + qrow) * p.ldo + h * kHeadDim;
 #pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 32) {
       uint32_t orr[32];

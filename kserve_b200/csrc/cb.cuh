@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include "ops.cuh"
+#include "p2p_base.cuh"
 
 namespace b200 {
 
@@ -62,30 +63,37 @@ __global__ void cb_gather_kernel(const int32_t* __restrict__ row_slot, int R, Cb
   dec_pos[r] = st.len[slot];     // a finished slot keeps rewriting the same cache position: harmless, never read
 }
 
-// one thread per row: merge the argmax candidates, append the token, EOS / max_new / stop sequences per sequence
+// one thread per row: merge the argmax candidates, append the token, EOS / max_new / stop sequences per sequence.
+// use_p2p: tensor parallel — the vocab-parallel candidates of every rank arrive through peer memory (argmax_kernel
+// pushes them); every row merges them even when its slot is finished, so the exchange epochs stay in step on all ranks.
+// seen: per-SLOT token-presence bitmaps of the repetition penalty (null when no running sequence uses one).
 __global__ void __launch_bounds__(128)
 cb_step_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx, int ranks, int R,
-               const int32_t* __restrict__ row_slot, CbState st, const int32_t* __restrict__ eos, int num_eos) {
+               const int32_t* __restrict__ row_slot, CbState st, const int32_t* __restrict__ eos, int num_eos,
+               P2P pp, int use_p2p, uint32_t* __restrict__ seen, int seen_words, int V) {
   TraceScope _ts(TK_STEP);
   pdl_launch_dependents();
   pdl_wait();
   _ts.mark();
+  if (use_p2p && threadIdx.x == 0) pp.row_epoch[0] += 1;   // epoch base of the next forward pass's peer all-reduces
   for (int r = threadIdx.x; r < R; r += blockDim.x) {
     const int slot = row_slot[r];
-    if (st.finished[slot]) continue;
     float best = cand_val[r];
     int tok = cand_idx[r];
-    for (int k = 1; k < ranks; ++k) {
+    if (use_p2p) merge_candidates(pp, r, best, tok);
+    for (int k = 1; k < ranks && !use_p2p; ++k) {
       const float v = cand_val[k * R + r];
       const int i = cand_idx[k * R + r];
       if (v > best || (v == best && i < tok)) { best = v; tok = i; }
     }
+    if (st.finished[slot]) continue;
     const int g = st.n_gen[slot];
     int32_t* out = st.out + (long long)slot * st.out_ld;
     out[g] = tok;
     st.n_gen[slot] = g + 1;
     st.len[slot] += 1;
     st.next_tok[slot] = tok;
+    if (seen && tok >= 0 && tok < V) atomicOr(seen + (long long)slot * seen_words + (tok >> 5), 1u << (tok & 31));
     int fin = 0;
     for (int e = 0; e < num_eos; ++e) fin |= (tok == eos[e]);
     if (g + 1 >= st.max_new[slot]) fin = 1;
@@ -97,7 +105,7 @@ cb_step_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ c
       for (int i = 0; i < n && eq; ++i) eq = out[g + 1 - n + i] == sq[i];
       if (eq) { fin = 1; st.stop_hit[slot] = 1; }
     }
-    st.finished[slot] = fin;
+    if (fin) st.finished[slot] = 1;
   }
 }
 

@@ -8,6 +8,8 @@
 #include <math.h>
 
 #include <algorithm>
+#include <deque>
+#include <climits>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -187,6 +189,27 @@ struct b200_engine {
   int32_t* h_cb = nullptr;           // pinned: init records / poll results / token reads
   bool cb_rows_dirty = false;
   int cb_num_eos = 0;
+  // KV page pool of the continuous-batching mode: pages are reference counted so that 128-token blocks of a prompt
+  // can be shared between requests (prefix reuse); a slot's page-table row is filled at admit
+  struct CbPending {                     // a prompt whose tokens are not all in the cache yet (chunked prefill)
+    int slot;
+    std::vector<int32_t> toks;
+    int done;                            // tokens already in the cache (shared prefix + prefilled chunks), multiple of 128
+    std::vector<unsigned long long> block_hash;   // chain hash of every full 128-token block of the prompt
+  };
+  struct PrefixEntry { int p0, p1; unsigned long long parent, tick; std::vector<int32_t> toks; };
+  std::deque<CbPending> cb_pending;
+  std::vector<std::vector<int>> cb_slot_pages;
+  std::vector<int> cb_free_pages, cb_page_ref;
+  std::unordered_map<unsigned long long, PrefixEntry> cb_prefix;
+  unsigned long long cb_tick = 0;
+  int cb_chunk_tokens = 0;               // 0: a prompt is prefilled completely inside b200_cb_admit
+  bool cb_prefix_on = false;
+  long long cb_stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // prompt tokens admitted / served from shared pages / prefilled, evictions, prefill passes
+  SampleCfg* d_cb_cfg = nullptr;         // [max_batch] per-slot logits-processor / sampling configuration
+  std::vector<char> cb_slot_sampling;    // slot uses the processed-score path
+  int cb_sampling_slots = 0;
+  int32_t* d_kv_off = nullptr;           // [80] tokens of each prefill row's sequence that are already cached
   // weight-stream L2 prefetch (prefetch.cuh): the step's weight-streaming GEMMs in launch order, per graph key
   PfCtx pf;
   std::unordered_map<int, std::vector<PfGemm>> pf_tables;
@@ -261,7 +284,7 @@ static int allreduce_bf16(b200_engine* e, bf16* buf, size_t count, cudaStream_t 
 // ---- one transformer stack pass over T token rows --------------------------------------------------
 // decode == true : T == B rows, swap-AB GEMMs (+ split-K), flash-decoding attention
 // decode == false: packed prompt tokens, row-major GEMMs, causal flash attention
-static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, bool decode) {
+static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, bool decode, const int32_t* kv_off = nullptr) {
   const int H = e->H, bn = pick_block_n(B_all);
   const float eps = e->cfg.rms_eps;
   const float scale_log2 = (1.0f / sqrtf((float)kHeadDim)) * 1.4426950408889634f;
@@ -364,11 +387,13 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
       ap.cu_seqlens = e->d_cu + vw.b0; ap.seq_slot = e->d_seq_slot + vw.b0; ap.nh = e->nh; ap.nkv = e->nkv; ap.scale_log2 = scale_log2;
       static const bool attn_mma = getenv("B200_ATTN_MMA") != nullptr;   // legacy mma.sync kernel for A/B runs
       if (attn_mma) {
+        B200_REQUIRE(kv_off == nullptr, "chunked prefill / prefix reuse needs the tcgen05 attention kernel (unset B200_ATTN_MMA)");
         if ((rc = launch_attn_prefill(ap, B, max_len, s))) return rc;
       } else {
         AttnTcParams tp_{};
         tp_.out = e->attn; tp_.ldo = e->nh * kHeadDim; tp_.page_table = e->d_page_table; tp_.max_pages = e->max_pages;
         tp_.cu_seqlens = e->d_cu + vw.b0; tp_.seq_slot = e->d_seq_slot + vw.b0; tp_.nh = e->nh; tp_.nkv = e->nkv; tp_.scale_log2 = scale_log2;
+        tp_.kv_off = kv_off ? kv_off + vw.b0 : nullptr;
         if ((rc = launch_attn_prefill_tc(e->tmaps, e->qkv, e->cap_T, e->qkv_cols, kc, vc, e->num_pages, tp_, B, max_len, s))) return rc;
       }
       e->launches++;
@@ -542,11 +567,13 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
   const int use_p2p = (e->cfg.tp_size > 1 && e->p2p_ready) ? 1 : 0;
   // one GPU: 16 CTAs per row scan slices of the 128k-entry row (a single CTA per row took 65 us of the 4.3 ms step)
   const int chunks = (e->cfg.tp_size == 1 && e->Vl >= 16384) ? 16 : 1;
-  const bool processed = e->st.sample_on && !cb_row_slot;   // repetition penalty / sampling: sampling.cuh
+  const bool processed = cb_row_slot ? e->cb_sampling_slots > 0 : e->st.sample_on;   // repetition penalty / sampling: sampling.cuh
   if (processed) {
     SampleParams sp{};
-    sp.logits = e->logits; sp.ld = e->Vl; sp.V = e->Vl; sp.seen = e->st.rep_on ? e->d_seen : nullptr; sp.words = e->seen_words;
-    sp.cfg = e->d_sample_cfg; sp.st = e->d_state; sp.out_val = e->cand_val; sp.out_idx = e->cand_idx;
+    sp.logits = e->logits; sp.ld = e->Vl; sp.V = e->Vl; sp.words = e->seen_words;
+    sp.out_val = e->cand_val; sp.out_idx = e->cand_idx;
+    if (cb_row_slot) { sp.seen = e->d_seen; sp.cfg = e->d_cb_cfg; sp.row_slot = cb_row_slot; sp.n_gen = e->cb.n_gen; }
+    else { sp.seen = e->st.rep_on ? e->d_seen : nullptr; sp.cfg = e->d_sample_cfg; sp.st = e->d_state; }
     B200_CUDA_OK(launch_k(sample_kernel, dim3(B), dim3(1024), 0, s, sp));
   } else {
     B200_CUDA_OK(launch_k(argmax_kernel, dim3(B, chunks), dim3(1024), 0, s, (const bf16*)e->logits, (long long)e->Vl, e->Vl, e->v0, e->cand_val, e->cand_idx, e->p2p, use_p2p));
@@ -562,7 +589,8 @@ static int head_and_step(b200_engine* e, const bf16* rows_xn, int rows_cap, int 
     cv = e->cand_val_all; ci = e->cand_idx_all; ranks = e->cfg.tp_size;
   }
   if (cb_row_slot) {   // continuous batching: per-slot bookkeeping
-    B200_CUDA_OK(launch_k(cb_step_kernel, dim3(1), dim3(128), 0, s, cv, ci, ranks, B, cb_row_slot, e->cb, (const int32_t*)e->d_eos, e->cb_num_eos));
+    B200_CUDA_OK(launch_k(cb_step_kernel, dim3(1), dim3(128), 0, s, cv, ci, ranks, B, cb_row_slot, e->cb, (const int32_t*)e->d_eos, e->cb_num_eos,
+                          e->p2p, use_p2p, processed ? e->d_seen : (uint32_t*)nullptr, e->seen_words, e->Vl));
     e->launches++;
     return 0;
   }
@@ -833,6 +861,8 @@ static int cb_alloc(b200_engine* e) {
   if ((rc = dmalloc(&e->cb.stop_tok, nb * kCbMaxStop * kCbMaxStopLen))) return rc;
   if ((rc = dmalloc(&e->d_cb_row_slot, nb))) return rc;
   if ((rc = dmalloc(&e->d_cb_rec, nb * kCbInitInts))) return rc;
+  if ((rc = dmalloc(&e->d_cb_cfg, nb))) return rc;
+  if ((rc = dmalloc(&e->d_kv_off, (size_t)80))) return rc;
   e->cb.out = e->d_out_tokens; e->cb.out_ld = e->out_ld;
   const size_t host_ints = std::max(nb * kCbInitInts, std::max((size_t)e->out_ld, 4 * nb));
   B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_cb), host_ints * 4));
@@ -860,60 +890,81 @@ static int cb_decode_step(b200_engine* e) {
   }
   static const bool eager = getenv("B200_NO_GRAPH") != nullptr;
   if (eager) return cb_decode_enqueue(e, R);
-  const int key = R | (1 << 20) | (e->cb_num_eos << 9);
+  const int key = R | (1 << 20) | (e->cb_num_eos << 9) | (e->cb_sampling_slots > 0 ? 1 << 21 : 0);
   return graph_step(e, key, [&] { return cb_decode_enqueue(e, R); });
 }
 
-// prefill `n` new sequences into free slots and produce their first token
-static int cb_admit(b200_engine* e, int n, const int64_t* const* rows, const int32_t* lens, const int32_t* max_new,
-                    const int32_t* stop_count, const int32_t* stop_offsets, const int64_t* stop_tokens, int32_t* slots_out) {
-  B200_REQUIRE(e->cb_on, "b200_cb_begin was not called");
-  B200_REQUIRE(n >= 1, "nothing to admit");
-  int free_slots = 0;
-  for (char u : e->cb_used) free_slots += u ? 0 : 1;
-  B200_REQUIRE(n <= free_slots, "not enough free slots");
-  int T = 0, max_len = 0;
-  for (int i = 0; i < n; ++i) {
-    B200_REQUIRE(lens[i] >= 1 && max_new[i] >= 1, "empty sequence / max_new < 1");
-    B200_REQUIRE(lens[i] + max_new[i] <= e->cfg.max_seq_len && lens[i] + max_new[i] <= e->cfg.max_position, "prompt + max_new exceeds max_seq_len");
-    T += lens[i];
-    max_len = std::max(max_len, lens[i]);
+// ---- KV page pool + prefix cache ---------------------------------------------------------------------
+static unsigned long long cb_block_hash(unsigned long long parent, const int32_t* toks) {   // FNV-1a over 128 tokens, chained
+  unsigned long long h = parent ^ 0xcbf29ce484222325ull;
+  for (int i = 0; i < 128; ++i) { h ^= (unsigned long long)(uint32_t)toks[i]; h *= 0x100000001b3ull; }
+  return h ? h : 1ull;
+}
+
+static void cb_unref_page(b200_engine* e, int pg) {
+  if (--e->cb_page_ref[pg] == 0) e->cb_free_pages.push_back(pg);
+}
+
+// frees the least recently used cached block nobody else references; false when nothing can be evicted
+static bool cb_evict_one(b200_engine* e) {
+  unsigned long long best_key = 0, best_tick = ~0ull;
+  for (auto& kv : e->cb_prefix) {
+    const auto& en = kv.second;
+    if (e->cb_page_ref[en.p0] == 1 && e->cb_page_ref[en.p1] == 1 && en.tick < best_tick) { best_tick = en.tick; best_key = kv.first; }
   }
-  B200_REQUIRE(T <= e->cap_T, "packed prompt tokens exceed max_prefill_tokens");
+  if (best_tick == ~0ull) return false;
+  auto it = e->cb_prefix.find(best_key);
+  cb_unref_page(e, it->second.p0);
+  cb_unref_page(e, it->second.p1);
+  e->cb_prefix.erase(it);
+  e->cb_stat[3]++;
+  return true;
+}
+
+static int cb_take_page(b200_engine* e) {
+  while (e->cb_free_pages.empty())
+    if (!cb_evict_one(e)) return -1;
+  const int pg = e->cb_free_pages.back();
+  e->cb_free_pages.pop_back();
+  e->cb_page_ref[pg] = 1;
+  return pg;
+}
+
+// One prefill pass over (chunks of) the pending prompts, at most `budget` packed tokens: sequences whose last chunk is
+// in this pass get their first token and join the decode batch.  Chunks end on multiples of 128 tokens (the attention
+// kernel's query tiles stay aligned with its KV tiles); a prompt's cached prefix (shared pages) is never recomputed.
+static int cb_prefill_pending(b200_engine* e, long long budget) {
+  if (e->cb_pending.empty()) return 0;
+  budget = std::min<long long>(budget, e->cap_T);
+  struct Part { size_t idx; int start, count; bool fin; };
+  std::vector<Part> parts;
+  long long left = budget;
+  for (size_t i = 0; i < e->cb_pending.size() && (int)parts.size() < std::min(e->cfg.max_batch, 64); ++i) {
+    const auto& pd = e->cb_pending[i];
+    const int rem = (int)pd.toks.size() - pd.done;
+    int c = rem <= left ? rem : (int)((left / 128) * 128);
+    if (c <= 0) break;
+    parts.push_back(Part{i, pd.done, c, c == rem});
+    left -= c;
+    if (c < rem) break;       // budget exhausted inside this prompt: FIFO, later prompts wait
+  }
+  if (parts.empty()) return 0;
+  const int n = (int)parts.size();
+  int T = 0, max_len = 0, nfin = 0;
+  for (auto& pt : parts) { T += pt.count; max_len = std::max(max_len, pt.count); nfin += pt.fin ? 1 : 0; }
   cudaStream_t s = e->stream;
-  // slots + init records
-  std::vector<int> slots;
-  for (int sl = 0; sl < (int)e->cb_used.size() && (int)slots.size() < n; ++sl)
-    if (!e->cb_used[sl]) slots.push_back(sl);
-  int so = 0;   // running index into stop_offsets
+  int32_t* flat = e->h_stage;   // tok | tok_seq | tok_pos | cu | seq_slot | kv_off | last_rows | fin_slot
+  B200_REQUIRE((size_t)(3 * T + 5 * n + 1) <= e->h_stage_elems, "prompt staging buffer too small");
+  int32_t *h_tok = flat, *h_seq = flat + T, *h_pos = flat + 2 * T, *h_cu = flat + 3 * T, *h_slot = h_cu + n + 1, *h_off = h_slot + n,
+          *h_last = h_off + n, *h_fin = h_last + n;
+  int t = 0, f = 0;
+  std::vector<int> lens(n);
   for (int i = 0; i < n; ++i) {
-    int32_t* r = e->h_cb + (size_t)i * kCbInitInts;
-    for (int j = 0; j < kCbInitInts; ++j) r[j] = 0;
-    r[0] = slots[i]; r[1] = lens[i]; r[2] = max_new[i];
-    const int ns = stop_count ? stop_count[i] : 0;
-    B200_REQUIRE(ns <= kCbMaxStop, "too many stop sequences for one sequence");
-    r[3] = ns;
-    for (int j = 0; j < ns; ++j, ++so) {
-      const int o = stop_offsets[so], len = stop_offsets[so + 1] - o;
-      B200_REQUIRE(len >= 0 && len <= kCbMaxStopLen, "stop sequence too long");
-      r[4 + j] = len;
-      for (int k = 0; k < len; ++k) r[4 + kCbMaxStop + j * kCbMaxStopLen + k] = (int32_t)stop_tokens[o + k];
-    }
-  }
-  B200_CUDA_OK(cudaMemcpyAsync(e->d_cb_rec, e->h_cb, (size_t)n * kCbInitInts * 4, cudaMemcpyHostToDevice, s));
-  cb_init_kernel<<<n, 64, 0, s>>>(e->d_cb_rec, n, e->cb);
-  B200_CUDA_OK(cudaGetLastError());
-  B200_CUDA_OK(cudaStreamSynchronize(s));   // h_cb is reused below
-  // packed prompt layout, built on the host (3 ints per prompt token)
-  int32_t* flat = e->h_stage;   // tok | tok_seq | tok_pos | cu | seq_slot | last_rows
-  int32_t *h_tok = flat, *h_seq = flat + T, *h_pos = flat + 2 * T, *h_cu = flat + 3 * T, *h_slot = h_cu + n + 1, *h_last = h_slot + n;
-  B200_REQUIRE((size_t)(3 * T + 3 * n + 1) <= e->h_stage_elems, "prompt staging buffer too small");
-  int t = 0;
-  for (int i = 0; i < n; ++i) {
+    const auto& pd = e->cb_pending[parts[i].idx];
     h_cu[i] = t;
-    for (int k = 0; k < lens[i]; ++k, ++t) { h_tok[t] = (int32_t)rows[i][k]; h_seq[t] = slots[i]; h_pos[t] = k; }
-    h_slot[i] = slots[i];
-    h_last[i] = t - 1;
+    for (int k = 0; k < parts[i].count; ++k, ++t) { h_tok[t] = pd.toks[parts[i].start + k]; h_seq[t] = pd.slot; h_pos[t] = parts[i].start + k; }
+    h_slot[i] = pd.slot; h_off[i] = parts[i].start; lens[i] = parts[i].count;
+    if (parts[i].fin) { h_last[f] = t - 1; h_fin[f] = pd.slot; ++f; }
   }
   h_cu[n] = t;
   B200_CUDA_OK(cudaMemcpyAsync(e->d_tok, h_tok, (size_t)T * 4, cudaMemcpyHostToDevice, s));
@@ -921,21 +972,195 @@ static int cb_admit(b200_engine* e, int n, const int64_t* const* rows, const int
   B200_CUDA_OK(cudaMemcpyAsync(e->d_tok_pos, h_pos, (size_t)T * 4, cudaMemcpyHostToDevice, s));
   B200_CUDA_OK(cudaMemcpyAsync(e->d_cu, h_cu, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
   B200_CUDA_OK(cudaMemcpyAsync(e->d_seq_slot, h_slot, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-  B200_CUDA_OK(cudaMemcpyAsync(e->d_last_rows, h_last, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-  B200_CUDA_OK(cudaMemcpyAsync(e->d_cb_rec, h_slot, (size_t)n * 4, cudaMemcpyHostToDevice, s));   // row -> slot of this prefill
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_kv_off, h_off, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+  if (nfin) {
+    B200_CUDA_OK(cudaMemcpyAsync(e->d_last_rows, h_last, (size_t)nfin * 4, cudaMemcpyHostToDevice, s));
+    B200_CUDA_OK(cudaMemcpyAsync(e->d_cb_rec, h_fin, (size_t)nfin * 4, cudaMemcpyHostToDevice, s));   // row -> slot of the finishing rows
+  }
   int rc;
-  e->st.lens.assign(lens, lens + n);
-  if ((rc = forward_layers(e, T, n, max_len, false))) return rc;
-  B200_CUDA_OK(launch_k(gather_rows_kernel, dim3(n), dim3(128), 0, s, (const bf16*)e->xn, (const int32_t*)e->d_last_rows, e->xl, e->H));
-  e->launches++;
-  if ((rc = head_and_step(e, e->xl, e->cfg.max_batch, n, e->d_cb_rec))) return rc;
-  B200_CUDA_OK(cudaStreamSynchronize(s));   // h_stage is reused by the next admit
+  e->st.lens = lens;
+  if ((rc = forward_layers(e, T, n, max_len, false, e->d_kv_off))) return rc;
+  if (nfin) {
+    B200_CUDA_OK(launch_k(gather_rows_kernel, dim3(nfin), dim3(128), 0, s, (const bf16*)e->xn, (const int32_t*)e->d_last_rows, e->xl, e->H));
+    e->launches++;
+    if ((rc = head_and_step(e, e->xl, e->cfg.max_batch, nfin, e->d_cb_rec))) return rc;
+  }
+  B200_CUDA_OK(cudaStreamSynchronize(s));   // h_stage is reused by the next pass
+  e->cb_stat[2] += T; e->cb_stat[4]++;
+  // bookkeeping (front to back so that erasing does not disturb the indices still to be visited)
+  for (int i = n - 1; i >= 0; --i) {
+    auto& pd = e->cb_pending[parts[i].idx];
+    pd.done += parts[i].count;
+    if (!parts[i].fin) continue;
+    if (e->cb_prefix_on) {   // every full 128-token block of the prompt can now be shared with later requests
+      const auto& pages = e->cb_slot_pages[pd.slot];
+      unsigned long long parent = 0;
+      for (size_t k = 0; k < pd.block_hash.size(); ++k) {
+        const unsigned long long key = pd.block_hash[k];
+        if (!e->cb_prefix.count(key)) {
+          b200_engine::PrefixEntry en{pages[2 * k], pages[2 * k + 1], parent, ++e->cb_tick,
+                                      std::vector<int32_t>(pd.toks.begin() + 128 * k, pd.toks.begin() + 128 * (k + 1))};
+          e->cb_page_ref[en.p0]++; e->cb_page_ref[en.p1]++;
+          e->cb_prefix.emplace(key, std::move(en));
+        }
+        parent = key;
+      }
+    }
+    e->cb_active.push_back(pd.slot);
+    e->cb_rows_dirty = true;
+    e->cb_pending.erase(e->cb_pending.begin() + parts[i].idx);
+  }
+  return 0;
+}
+
+// admit `n` new sequences: slots, KV pages (shared with cached prefixes where possible), per-sequence state; their
+// prompts are prefilled here (cb_chunk_tokens == 0) or chunk by chunk between the following decode steps
+static int cb_admit(b200_engine* e, int n, const int64_t* const* rows, const int32_t* lens, const int32_t* max_new,
+                    const int32_t* stop_count, const int32_t* stop_offsets, const int64_t* stop_tokens,
+                    const b200_gen_params_t* sampling, int32_t* slots_out) {
+  B200_REQUIRE(e->cb_on, "b200_cb_begin was not called");
+  B200_REQUIRE(n >= 1 && n <= e->cfg.max_batch, "nothing to admit / more prompts than slots");
+  int free_slots = 0;
+  for (char u : e->cb_used) free_slots += u ? 0 : 1;
+  B200_REQUIRE(n <= free_slots, "not enough free slots");
+  long long T = 0;
+  for (int i = 0; i < n; ++i) {
+    B200_REQUIRE(lens[i] >= 1 && max_new[i] >= 1, "empty sequence / max_new < 1");
+    B200_REQUIRE(lens[i] + max_new[i] <= e->cfg.max_seq_len && lens[i] + max_new[i] <= e->cfg.max_position, "prompt + max_new exceeds max_seq_len");
+    T += lens[i];
+  }
+  B200_REQUIRE(e->cb_chunk_tokens > 0 || T <= e->cap_T, "packed prompt tokens exceed max_prefill_tokens (enable chunked prefill: b200_cb_config)");
+  cudaStream_t s = e->stream;
+  std::vector<int> slots;
+  for (int sl = 0; sl < (int)e->cb_used.size() && (int)slots.size() < n; ++sl)
+    if (!e->cb_used[sl]) slots.push_back(sl);
+  // ---- pages: plan every prompt first; on exhaustion everything taken so far is handed back
+  std::vector<b200_engine::CbPending> plans(n);
+  auto rollback = [&](int upto) {
+    for (int i = 0; i < upto; ++i) {
+      for (int pg : e->cb_slot_pages[slots[i]]) cb_unref_page(e, pg);
+      e->cb_slot_pages[slots[i]].clear();
+    }
+  };
+  for (int i = 0; i < n; ++i) {
+    auto& pd = plans[i];
+    pd.slot = slots[i];
+    pd.toks.resize(lens[i]);
+    for (int k = 0; k < lens[i]; ++k) pd.toks[k] = (int32_t)rows[i][k];
+    const int need = (lens[i] + max_new[i] + kPageTokens - 1) / kPageTokens;
+    std::vector<int>& pages = e->cb_slot_pages[slots[i]];
+    pages.clear();
+    int hit_blocks = 0;
+    const int full_blocks = lens[i] / 128;
+    if (e->cb_prefix_on) {
+      unsigned long long parent = 0;
+      bool chain = true;
+      for (int k = 0; k < full_blocks; ++k) {
+        const unsigned long long key = cb_block_hash(parent, pd.toks.data() + 128 * k);
+        pd.block_hash.push_back(key);
+        // at least one token must be left to compute (its logits select the first generated token)
+        if (chain && 128 * (k + 1) < lens[i]) {
+          auto it = e->cb_prefix.find(key);
+          if (it != e->cb_prefix.end() && it->second.parent == parent &&
+              memcmp(it->second.toks.data(), pd.toks.data() + 128 * k, 128 * sizeof(int32_t)) == 0) {
+            it->second.tick = ++e->cb_tick;
+            e->cb_page_ref[it->second.p0]++; e->cb_page_ref[it->second.p1]++;
+            pages.push_back(it->second.p0); pages.push_back(it->second.p1);
+            hit_blocks = k + 1;
+          } else {
+            chain = false;
+          }
+        } else {
+          chain = false;
+        }
+        parent = key;
+      }
+    }
+    pd.done = hit_blocks * 128;
+    while ((int)pages.size() < need) {
+      const int pg = cb_take_page(e);
+      if (pg < 0) {
+        rollback(i + 1);
+        set_last_error("KV page pool exhausted: release finished sequences first");
+        return -7;
+      }
+      pages.push_back(pg);
+    }
+    e->cb_stat[0] += lens[i]; e->cb_stat[1] += pd.done;
+  }
+  for (int i = 0; i < n; ++i) {
+    const std::vector<int>& pages = e->cb_slot_pages[slots[i]];
+    int32_t* row = e->h_page_table.data() + (size_t)slots[i] * e->max_pages;
+    for (int k = 0; k < e->max_pages; ++k) row[k] = k < (int)pages.size() ? pages[k] : pages.back();
+    B200_CUDA_OK(cudaMemcpyAsync(e->d_page_table + (size_t)slots[i] * e->max_pages, row, (size_t)e->max_pages * 4, cudaMemcpyHostToDevice, s));
+  }
+  // ---- per-sequence device state
+  int so = 0;   // running index into stop_offsets
+  for (int i = 0; i < n; ++i) {
+    int32_t* r = e->h_cb + (size_t)i * kCbInitInts;
+    for (int j = 0; j < kCbInitInts; ++j) r[j] = 0;
+    r[0] = slots[i]; r[1] = lens[i]; r[2] = max_new[i];
+    const int ns = stop_count ? stop_count[i] : 0;
+    if (ns > kCbMaxStop) { rollback(n); set_last_error("too many stop sequences for one sequence"); return -2; }
+    r[3] = ns;
+    for (int j = 0; j < ns; ++j, ++so) {
+      const int o = stop_offsets[so], len = stop_offsets[so + 1] - o;
+      if (len < 0 || len > kCbMaxStopLen) { rollback(n); set_last_error("stop sequence too long"); return -2; }
+      r[4 + j] = len;
+      for (int k = 0; k < len; ++k) r[4 + kCbMaxStop + j * kCbMaxStopLen + k] = (int32_t)stop_tokens[o + k];
+    }
+  }
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_cb_rec, e->h_cb, (size_t)n * kCbInitInts * 4, cudaMemcpyHostToDevice, s));
+  cb_init_kernel<<<n, 64, 0, s>>>(e->d_cb_rec, n, e->cb);
+  B200_CUDA_OK(cudaGetLastError());
+  // ---- logits processors / sampling per sequence (build_generation_config, generative_model.py:388-402)
+  for (int i = 0; i < n; ++i) {
+    SampleCfg sc{};
+    sc.rep_penalty = 1.0f; sc.temperature = 1.0f; sc.top_p = 1.0f; sc.top_k = 50;
+    bool on = false;
+    if (sampling) {
+      const b200_gen_params_t& gp = sampling[i];
+      sc.rep_penalty = (gp.repetition_penalty > 0.f) ? gp.repetition_penalty : 1.0f;
+      sc.temperature = (gp.temperature > 0.f) ? gp.temperature : 1.0f;
+      sc.do_sample = gp.do_sample ? 1 : 0;
+      sc.top_p = (gp.top_p > 0.f && gp.top_p < 1.f) ? gp.top_p : 1.0f;
+      sc.top_k = gp.top_k > 0 ? std::min(gp.top_k, kSampleMaxCand) : 50;
+      sc.seed = gp.seed;
+      on = sc.rep_penalty != 1.0f || sc.do_sample;
+    }
+    if (on && e->cfg.tp_size != 1) { rollback(n); set_last_error("logits processors / sampling run on one GPU per engine (tp_size == 1)"); return -2; }
+    B200_CUDA_OK(cudaMemcpyAsync(e->d_cb_cfg + slots[i], &sc, sizeof(sc), cudaMemcpyHostToDevice, s));   // (pageable source: staged before return)
+    if (on && sc.rep_penalty != 1.0f) {
+      if (!e->d_seen) {
+        e->seen_words = (e->Vl + 31) / 32;
+        B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->d_seen), (size_t)e->cfg.max_batch * e->seen_words * 4));
+      }
+      std::vector<uint32_t> bits(e->seen_words, 0u);      // the reference's input_ids = the prompt tokens
+      for (int32_t tk : plans[i].toks)
+        if (tk >= 0 && tk < e->Vl) bits[tk >> 5] |= 1u << (tk & 31);
+      B200_CUDA_OK(cudaMemcpy(e->d_seen + (size_t)slots[i] * e->seen_words, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+    } else if (e->d_seen && on) {
+      B200_CUDA_OK(cudaMemsetAsync(e->d_seen + (size_t)slots[i] * e->seen_words, 0, (size_t)e->seen_words * 4, s));
+    }
+    if (on) { e->cb_slot_sampling[slots[i]] = 1; e->cb_sampling_slots++; }
+  }
+  if (e->cb_sampling_slots > 0 && !e->d_seen) {   // the step kernel updates the bitmaps whenever the processed path is on
+    e->seen_words = (e->Vl + 31) / 32;
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->d_seen), (size_t)e->cfg.max_batch * e->seen_words * 4));
+    B200_CUDA_OK(cudaMemset(e->d_seen, 0, (size_t)e->cfg.max_batch * e->seen_words * 4));
+  }
+  B200_CUDA_OK(cudaStreamSynchronize(s));   // h_cb / sc are reused
   for (int i = 0; i < n; ++i) {
     e->cb_used[slots[i]] = 1;
-    e->cb_active.push_back(slots[i]);
     slots_out[i] = slots[i];
+    e->cb_pending.push_back(std::move(plans[i]));
   }
-  e->cb_rows_dirty = true;
+  if (e->cb_chunk_tokens == 0) {
+    while (!e->cb_pending.empty()) {
+      int rc = cb_prefill_pending(e, LLONG_MAX);
+      if (rc) return rc;
+    }
+  }
   return 0;
 }
 
@@ -1121,7 +1346,7 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   if ((rc = dmalloc(&e->d_stop_tok, 1024))) return rc;
   if ((rc = dmalloc(&e->d_stop_off, 32))) return rc;
   if ((rc = dmalloc(&e->d_state, 1))) return rc;
-  e->h_stage_elems = 3 * T + 6 * 80;
+  e->h_stage_elems = 3 * T + 8 * 80;
   B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_stage), e->h_stage_elems * 4));
   B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_state), sizeof(StepState)));
   B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_out_tokens), (size_t)c->max_batch * e->out_ld * 4));
@@ -1570,9 +1795,8 @@ int b200_kv_swap_in(b200_engine_t* e, int32_t slot) { B200_REQUIRE(e, "null engi
 int b200_cb_begin(b200_engine_t* e, int64_t pad_token_id, const int64_t* eos_token_ids, int32_t num_eos) {
   B200_REQUIRE(e, "null engine");
   B200_REQUIRE(e->finalized, "weights not finalized");
-  B200_REQUIRE(e->cfg.tp_size == 1, "continuous batching runs on one GPU per engine (tensor-parallel ranks would need a command broadcast)");
   B200_REQUIRE(num_eos >= 0 && num_eos <= 16, "too many eos tokens");
-  B200_REQUIRE((long long)e->cfg.max_batch * e->max_pages <= e->num_pages, "KV page pool smaller than max_batch * pages per sequence");
+  B200_REQUIRE(e->max_pages <= e->num_pages, "KV page pool smaller than one full-length sequence");
   B200_CUDA_OK(cudaSetDevice(e->cfg.device));
   int rc = cb_alloc(e);
   if (rc) return rc;
@@ -1581,9 +1805,16 @@ int b200_cb_begin(b200_engine_t* e, int64_t pad_token_id, const int64_t* eos_tok
   for (int i = 0; i < num_eos; ++i) tmp[i] = (int32_t)eos_token_ids[i];
   if (num_eos) B200_CUDA_OK(cudaMemcpy(e->d_eos, tmp.data(), (size_t)num_eos * 4, cudaMemcpyHostToDevice));
   e->cb_num_eos = num_eos;
-  for (int sl = 0; sl < e->cfg.max_batch; ++sl)
-    for (int i = 0; i < e->max_pages; ++i) e->h_page_table[(size_t)sl * e->max_pages + i] = sl * e->max_pages + i;
-  B200_CUDA_OK(cudaMemcpy(e->d_page_table, e->h_page_table.data(), e->h_page_table.size() * 4, cudaMemcpyHostToDevice));
+  // every page is free; slots get their page-table rows at admit
+  e->cb_free_pages.clear();
+  for (int pg = e->num_pages - 1; pg >= 0; --pg) e->cb_free_pages.push_back(pg);
+  e->cb_page_ref.assign(e->num_pages, 0);
+  e->cb_prefix.clear();
+  e->cb_pending.clear();
+  e->cb_slot_pages.assign(e->cfg.max_batch, {});
+  e->cb_slot_sampling.assign(e->cfg.max_batch, 0);
+  e->cb_sampling_slots = 0;
+  for (auto& v : e->cb_stat) v = 0;
   e->cb_used.assign(e->cfg.max_batch, 0);
   e->cb_active.clear();
   e->cb_rows_dirty = true;
@@ -1591,26 +1822,50 @@ int b200_cb_begin(b200_engine_t* e, int64_t pad_token_id, const int64_t* eos_tok
   return 0;
 }
 
+int b200_cb_config(b200_engine_t* e, int32_t prefill_chunk_tokens, int32_t prefix_cache) {
+  B200_REQUIRE(e, "null engine");
+  B200_REQUIRE(prefill_chunk_tokens == 0 || prefill_chunk_tokens >= 128, "prefill chunks are multiples of 128 tokens (0 = whole prompts at admit)");
+  e->cb_chunk_tokens = (prefill_chunk_tokens / 128) * 128;
+  e->cb_prefix_on = prefix_cache != 0;
+  return 0;
+}
+
+int b200_cb_stats(b200_engine_t* e, int64_t* out8) {
+  B200_REQUIRE(e && out8, "null argument");
+  int64_t evictable = 0;
+  for (auto& kv : e->cb_prefix)
+    if (e->cb_page_ref[kv.second.p0] == 1 && e->cb_page_ref[kv.second.p1] == 1) evictable += 2;
+  out8[0] = e->cb_stat[0]; out8[1] = e->cb_stat[1]; out8[2] = e->cb_stat[2]; out8[3] = e->cb_stat[3]; out8[4] = e->cb_stat[4];
+  out8[5] = (int64_t)e->cb_free_pages.size() + evictable;     // pages an admit could obtain right now
+  out8[6] = (int64_t)e->cb_prefix.size();
+  out8[7] = (int64_t)e->cb_pending.size();
+  return 0;
+}
+
 int b200_cb_end(b200_engine_t* e) {
   B200_REQUIRE(e, "null engine");
   e->cb_on = false;
   e->cb_active.clear();
+  e->cb_pending.clear();
+  e->cb_prefix.clear();
   return 0;
 }
 
 int b200_cb_admit(b200_engine_t* e, int32_t n, const int64_t* const* rows, const int32_t* lens, const int32_t* max_new,
-                  const int32_t* stop_count, const int32_t* stop_offsets, const int64_t* stop_tokens, int32_t* slots_out) {
+                  const int32_t* stop_count, const int32_t* stop_offsets, const int64_t* stop_tokens,
+                  const b200_gen_params_t* sampling, int32_t* slots_out) {
   B200_REQUIRE(e && rows && lens && max_new && slots_out, "null argument");
   B200_CUDA_OK(cudaSetDevice(e->cfg.device));
-  return cb_admit(e, n, rows, lens, max_new, stop_count, stop_offsets, stop_tokens, slots_out);
+  return cb_admit(e, n, rows, lens, max_new, stop_count, stop_offsets, stop_tokens, sampling, slots_out);
 }
 
 int b200_cb_step(b200_engine_t* e, int32_t n_steps) {
   B200_REQUIRE(e && e->cb_on, "b200_cb_begin was not called");
   B200_CUDA_OK(cudaSetDevice(e->cfg.device));
   for (int i = 0; i < n_steps; ++i) {
-    int rc = cb_decode_step(e);
-    if (rc) return rc;
+    int rc;
+    if (!e->cb_pending.empty() && (rc = cb_prefill_pending(e, e->cb_chunk_tokens > 0 ? e->cb_chunk_tokens : LLONG_MAX))) return rc;
+    if ((rc = cb_decode_step(e))) return rc;
   }
   return 0;
 }
@@ -1657,6 +1912,11 @@ int b200_cb_release(b200_engine_t* e, int32_t slot) {
   e->cb_used[slot] = 0;
   auto it = std::find(e->cb_active.begin(), e->cb_active.end(), (int)slot);
   if (it != e->cb_active.end()) { e->cb_active.erase(it); e->cb_rows_dirty = true; }
+  for (auto pd = e->cb_pending.begin(); pd != e->cb_pending.end(); ++pd)
+    if (pd->slot == slot) { e->cb_pending.erase(pd); break; }      // cancelled before its prompt was in the cache
+  for (int pg : e->cb_slot_pages[slot]) cb_unref_page(e, pg);       // shared prefix pages stay alive through the cache's reference
+  e->cb_slot_pages[slot].clear();
+  if (e->cb_slot_sampling[slot]) { e->cb_slot_sampling[slot] = 0; e->cb_sampling_slots--; }
   return 0;
 }
 

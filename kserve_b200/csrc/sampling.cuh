@@ -71,6 +71,10 @@ struct SampleParams {
   const SampleCfg* cfg;
   const StepState* st;                   // step counter -> RNG counter
   float* out_val; int32_t* out_idx;      // [B]
+  // continuous batching: row b belongs to slot row_slot[b]; cfg[] and the seen bitmaps are per SLOT and the RNG counter
+  // of a sequence is its own generated-token count, so a request's stream does not depend on who shares its batch
+  const int32_t* row_slot;               // null: static batch (one cfg for all rows, bitmap row == batch row)
+  const int32_t* n_gen;                  // [slots]
 };
 
 // one CTA of 1024 threads per row
@@ -87,10 +91,11 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleParams p) {
   __shared__ float sv[32];
   __shared__ int si[32];
   const int b = blockIdx.x, tid = threadIdx.x;
-  const SampleCfg cfg = *p.cfg;
+  const int srow = p.row_slot ? p.row_slot[b] : b;        // row of the per-sequence state
+  const SampleCfg cfg = p.cfg[p.row_slot ? srow : 0];
   const bf16* row = p.logits + (long long)b * p.ld;
-  const uint32_t* seen = p.seen ? p.seen + (long long)b * p.words : nullptr;
   const float pen = cfg.rep_penalty;
+  const uint32_t* seen = (p.seen && pen != 1.0f) ? p.seen + (long long)srow * p.words : nullptr;
   const bool sampling = cfg.do_sample != 0;
   const float temp = sampling ? cfg.temperature : 1.0f;
   auto score = [&](int i) -> float {
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleParams p) {
     }
     float Zk = 0.f;
     for (int j = 0; j < keep; ++j) Zk += expf(c_key[j] - m);
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)p.st->step, (uint32_t)b, 0x5eed5eedu, 0u),
+    const uint4 r = philox4x32_10(make_uint4(p.row_slot ? (uint32_t)p.n_gen[srow] : (uint32_t)p.st->step, p.row_slot ? 0u : (uint32_t)b, 0x5eed5eedu, 0u),
                                   make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32)));
     const float u = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
     const float target = u * Zk;

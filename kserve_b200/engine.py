@@ -35,6 +35,10 @@ def hf_rope_tables(rope_theta_or_cfg, head_dim: int, max_pos: int) -> Tuple[torc
     return _tables(cfg, head_dim, max_pos)
 
 
+class PoolExhausted(_lib.B200Error):
+    """b200_cb_admit could not obtain KV pages (rc -7): nothing was admitted, retry after a release"""
+
+
 class B200Engine:
     def __init__(self, cfg: dict, *, max_batch: int = 8, max_seq_len: int = 2048,
                  max_prefill_tokens: Optional[int] = None, num_kv_pages: int = 0, device: int = 0,
@@ -259,9 +263,24 @@ class B200Engine:
         _lib.check(self.lib.b200_cb_begin(self.h, int(pad_token_id or 0), arr, len(eos)), "b200_cb_begin")
         self._cb_slots = self.max_batch
 
+    def cb_config(self, prefill_chunk_tokens: int = 0, prefix_cache: bool = False) -> None:
+        """chunked prefill (one chunk pass before every decode step) / prefix KV reuse across requests"""
+        _lib.check(self.lib.b200_cb_config(self.h, int(prefill_chunk_tokens), 1 if prefix_cache else 0), "b200_cb_config")
+
+    def cb_stats(self) -> dict:
+        out = (C.c_int64 * 8)()
+        _lib.check(self.lib.b200_cb_stats(self.h, out), "b200_cb_stats")
+        keys = ("prompt_tokens", "prefix_hit_tokens", "prefilled_tokens", "evictions", "prefill_passes", "available_pages",
+                "cached_blocks", "pending_prompts")
+        return dict(zip(keys, [int(v) for v in out]))
+
     def cb_admit(self, prompts: Sequence[Sequence[int]], max_new_tokens: Sequence[int],
-                 stop_sequences: Optional[Sequence[Sequence[Sequence[int]]]] = None) -> List[int]:
-        """Prefill `prompts` into free slots; returns the slot of each prompt."""
+                 stop_sequences: Optional[Sequence[Sequence[Sequence[int]]]] = None,
+                 sampling: Optional[Sequence[Optional[dict]]] = None) -> List[int]:
+        """Admit `prompts` into free slots (prefilled here, or chunk by chunk during the following cb_step calls when
+        chunked prefill is configured); returns the slot of each prompt.  `sampling[i]`: None (greedy) or a dict with
+        repetition_penalty / do_sample / temperature / top_p / top_k / seed.  Raises PoolExhausted when the KV page
+        pool cannot supply the pages: nothing was admitted."""
         n = len(prompts)
         rows = [(C.c_int64 * len(p))(*[int(t) for t in p]) for p in prompts]
         ptrs = (C.POINTER(C.c_int64) * n)(*[C.cast(r, C.POINTER(C.c_int64)) for r in rows])
@@ -276,8 +295,22 @@ class B200Engine:
                 offs.append(len(flat))
         offs_a = (C.c_int32 * len(offs))(*offs)
         flat_a = (C.c_int64 * max(1, len(flat)))(*flat)
+        samp = None
+        if sampling is not None and any(sp for sp in sampling):
+            samp = (_lib.GenParams * n)()
+            for i, sp in enumerate(sampling):
+                sp = sp or {}
+                samp[i].repetition_penalty = float(sp.get("repetition_penalty") or 0.0)
+                samp[i].do_sample = 1 if sp.get("do_sample") else 0
+                samp[i].temperature = float(sp.get("temperature") or 0.0)
+                samp[i].top_p = float(sp.get("top_p") or 0.0)
+                samp[i].top_k = int(sp.get("top_k") or 0)
+                samp[i].seed = int(sp.get("seed") or 0) & 0xFFFFFFFFFFFFFFFF
         slots = (C.c_int32 * n)()
-        _lib.check(self.lib.b200_cb_admit(self.h, n, ptrs, lens, mx, cnt, offs_a, flat_a, slots), "b200_cb_admit")
+        rc = self.lib.b200_cb_admit(self.h, n, ptrs, lens, mx, cnt, offs_a, flat_a, samp, slots)
+        if rc == -7:
+            raise PoolExhausted(self.lib.b200_last_error().decode("utf-8", "replace"))
+        _lib.check(rc, "b200_cb_admit")
         return list(slots)
 
     def cb_step(self, n_steps: int = 1) -> None:

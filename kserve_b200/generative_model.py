@@ -140,7 +140,8 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         # iteration-level batching instead of the reference's one-request-at-a-time loop (continuous.py)
         self._generation_defaults = generation_defaults
         self._seed_counter = 0
-        self.continuous_batching = bool(continuous_batching) and tensor_parallel_size == 1
+        self.continuous_batching = bool(continuous_batching)
+        self.prefill_chunk_tokens, self.prefix_cache = 0, False     # set before load(): see kserve_b200/__main__.py
         self._cb = None
 
     # ------------------------------------------------------------------ load / stop (generative_model.py:203-285)
@@ -241,9 +242,10 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         self.vocab_rows = vocab_rows
         self._thread = Thread(target=self._process_requests, daemon=True)   # :267-269
         self._thread.start()
-        if self.continuous_batching:
+        if self.continuous_batching and self.tp_rank == 0:     # followers replay the scheduler's engine calls (tp.follower_loop)
             from .continuous import ContinuousBatcher
-            self._cb = ContinuousBatcher(self._engine, self._pad_token_id or 0, self.eos_token_ids)
+            self._cb = ContinuousBatcher(self._engine, self._pad_token_id or 0, self.eos_token_ids,
+                                         prefill_chunk_tokens=self.prefill_chunk_tokens, prefix_cache=self.prefix_cache)
 
             def _cb_down(err):           # a dead scheduler thread must not leave the model advertised as ready
                 self.ready = False
@@ -358,10 +360,8 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
     async def _agenerate(self, ids, mask, *, max_new_tokens, pad_token_id, eos_token_ids, stop_sequences=(), **sampling) -> GenerateResult:
         """One request through the engine: the continuous batcher when enabled, else the serial generation thread."""
         if self._cb is not None:
-            if sampling:
-                raise OpenAIError("repetition penalty / sampling are not available with --continuous_batching (greedy only)")
             try:
-                return await self._cb.submit(self._unpadded_rows(ids, mask), ids, max_new_tokens, stop_sequences)
+                return await self._cb.submit(self._unpadded_rows(ids, mask), ids, max_new_tokens, stop_sequences, sampling=sampling or None)
             except (ValueError, RuntimeError) as e:
                 raise OpenAIError(str(e))
         return await self._submit(lambda: self._generate(ids, mask, max_new_tokens=max_new_tokens, pad_token_id=pad_token_id,
@@ -471,8 +471,6 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                 put(None)
                 return None
             if self._cb is not None:
-                if self.build_generation_config(request):
-                    raise OpenAIError("repetition penalty / sampling are not available with --continuous_batching (greedy only)")
                 detok = IncrementalDetokenizer(self._tokenizer)
                 if echo:
                     piece = detok.put(self._unpadded_rows(ids, mask)[0])
@@ -495,7 +493,8 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                             put(piece)
                     put(None)
                 try:
-                    cb_req = self._cb.submit_nowait(self._unpadded_rows(ids, mask), ids, request.max_tokens, stop_sequences, cb_done, on_tokens)
+                    cb_req = self._cb.submit_nowait(self._unpadded_rows(ids, mask), ids, request.max_tokens, stop_sequences, cb_done, on_tokens,
+                                                    sampling=self.build_generation_config(request) or None)
                 except (ValueError, RuntimeError) as e:
                     raise OpenAIError(str(e))
             else:

@@ -175,3 +175,149 @@ def test_openai_route_with_continuous_batching():
             assert pred.status_code == 200 and len(pred.json()["predictions"][0]) == 4
     finally:
         model.stop()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: KV page pool, prefix reuse across requests, chunked prefill, per-sequence sampling, pool exhaustion
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def peaked():
+    """tiny_g2 with the peaked LM head: every greedy step is decisive, so ids can be compared EXACTLY between the paths"""
+    import torch
+    c = load_case("tiny_g2_peaked")
+    m = c["meta"]
+    e = make_engine(m["cfg"], m["seed"], vocab_rows=m["vocab_rows"], max_batch=8, max_seq_len=512)
+    g = torch.Generator().manual_seed(7)
+    long_prompts = torch.randint(3, 1000, (3, 300), generator=g)
+    long_prompts[1, :256] = long_prompts[0, :256]          # shares two 128-token blocks with prompt 0
+    long_prompts[2, :128] = long_prompts[0, :128]          # shares one
+    ref = e.generate(long_prompts, None, max_new_tokens=12, pad_token_id=m["pad_token_id"]).output_ids[:, 300:]
+    yield e, c, long_prompts, ref
+    e.close()
+
+
+def test_prefix_reuse_skips_prefill_and_yields_identical_ids(peaked):
+    """128-token blocks of a finished prefill stay in the pool (hash of the tokens up to the block ->
+    reference-counted pages); a later prompt with the same leading blocks shares the pages, only its tail is computed,
+    and its greedy ids are those of a full prefill."""
+    e, c, prompts, ref = peaked
+    rows = [r.tolist() for r in prompts]
+    e.cb_begin(0, [])
+    e.cb_config(0, True)
+    try:
+        s0 = e.cb_admit([rows[0]], [12])[0]
+        st = e.cb_stats()
+        assert st["prefix_hit_tokens"] == 0 and st["prefilled_tokens"] == 300 and st["cached_blocks"] == 2
+        _run_until_done(e, [s0])
+        assert e.cb_read(s0, 0, 12) == ref[0].tolist()
+        # the same prompt again, while the first one still holds its slot: 256 of 300 tokens come from shared pages
+        s1 = e.cb_admit([rows[0]], [12])[0]
+        st = e.cb_stats()
+        assert st["prefix_hit_tokens"] == 256 and st["prefilled_tokens"] == 300 + 44
+        # ... and prompts that share two / one leading block(s), admitted together
+        s2, s3 = e.cb_admit([rows[1], rows[2]], [12, 12])
+        st = e.cb_stats()
+        assert st["prefix_hit_tokens"] == 256 + 256 + 128 and st["prefilled_tokens"] == 300 + 44 + 44 + 172
+        _run_until_done(e, [s1, s2, s3])
+        assert e.cb_read(s1, 0, 12) == ref[0].tolist()
+        assert e.cb_read(s2, 0, 12) == ref[1].tolist() and e.cb_read(s3, 0, 12) == ref[2].tolist()
+        # releasing every sequence keeps the cached blocks alive (the cache holds its own references) ...
+        for s in (s0, s1, s2, s3):
+            e.cb_release(s)
+        s4 = e.cb_admit([rows[0]], [12])[0]
+        assert e.cb_stats()["prefix_hit_tokens"] == 256 + 256 + 128 + 256
+        _run_until_done(e, [s4])
+        assert e.cb_read(s4, 0, 12) == ref[0].tolist()
+        e.cb_release(s4)
+    finally:
+        e.cb_end()
+
+
+def test_chunked_prefill_interleaves_with_decode_and_matches_full_prefill(peaked):
+    """with prefill chunks an admit is one chunk pass per decode step — the running sequence keeps
+    generating while a long prompt is being prefilled — and the chunked prompt's ids equal those of a one-pass prefill."""
+    e, c, prompts, ref = peaked
+    rows = [r.tolist() for r in prompts]
+    short = c["input_ids"][0].tolist()
+    e.cb_begin(0, [])
+    e.cb_config(128, False)
+    try:
+        a = e.cb_admit([short], [16])[0]
+        e.cb_step(1)
+        assert e.cb_poll()[0][a] == 1                           # 48-token prompt: one chunk, first token after one step
+        b = e.cb_admit([rows[0]], [12])[0]                       # 300 tokens = chunks of 128 + 128 + 44
+        assert e.cb_stats()["pending_prompts"] == 1 and e.cb_poll()[0][b] == 0
+        gen_a = []
+        for _ in range(3):
+            e.cb_step(1)
+            n_gen, _, _ = e.cb_poll()
+            gen_a.append(n_gen[a])
+        assert gen_a == [2, 3, 4]                               # the short sequence never stalled
+        assert e.cb_poll()[0][b] == 2 and e.cb_stats()["pending_prompts"] == 0   # first token from its last chunk + the same iteration's decode step
+        _run_until_done(e, [a, b])
+        assert e.cb_read(b, 0, 12) == ref[0].tolist()
+        assert e.cb_read(a, 0, 16) == c["gen"][0].tolist()      # the oracle's ids (every step of this fixture is decisive)
+        assert e.cb_stats()["prefill_passes"] == 4
+    finally:
+        e.cb_end()
+
+
+def test_pool_exhaustion_admits_nothing_and_recovers():
+    from kserve_b200.engine import PoolExhausted
+    c = load_case("tiny_g2_peaked")
+    m = c["meta"]
+    e = make_engine(m["cfg"], m["seed"], vocab_rows=m["vocab_rows"], max_batch=4, max_seq_len=512, num_kv_pages=10)   # 8 pages = one full-length sequence
+    try:
+        prompts = [row.tolist() for row in c["input_ids"]]      # 48 tokens each
+        e.cb_begin(0, [])
+        a = e.cb_admit([prompts[0]], [200])[0]                   # 248 tokens -> 4 pages
+        with pytest.raises(PoolExhausted):
+            e.cb_admit([prompts[1], prompts[2]], [200, 200])     # 8 more pages: only 6 are left
+        assert e.cb_stats()["available_pages"] == 6              # nothing leaked
+        b = e.cb_admit([prompts[1]], [200])[0]
+        e.cb_step(4)
+        assert e.cb_read(a, 0, 5) == c["gen"][0][:5].tolist() and e.cb_read(b, 0, 5) == c["gen"][1][:5].tolist()
+        e.cb_release(a)
+        assert e.cb_stats()["available_pages"] == 6
+        e.cb_end()
+    finally:
+        e.close()
+
+
+def test_per_sequence_logits_processors_in_the_running_batch():
+    """Sampling parameters ride along per sequence: a repetition-penalty row reproduces the oracle's greedy-with-penalty
+    ids (fixture tiny_g2_reppen), next to a plain greedy row (fixture tiny_g2_ids) and a seeded sampling row."""
+    cp, cg = load_case("tiny_g2_reppen"), load_case("tiny_g2_ids")
+    m = cp["meta"]
+    e = make_engine(m["cfg"], m["seed"], vocab_rows=m["vocab_rows"], max_batch=8, max_seq_len=512)
+    try:
+        pen = m["presence_penalty"]
+        rows_p = [r.tolist() for r in cp["input_ids"]]
+        e.cb_begin(0, [])
+        outs = []
+        for trial in range(2):
+            slots = e.cb_admit([rows_p[0], cg["input_ids"][1].tolist(), rows_p[2], rows_p[3]], [cp["T"], cg["T"], cp["T"], 12],
+                               sampling=[dict(repetition_penalty=pen), None, dict(repetition_penalty=pen),
+                                         dict(do_sample=True, temperature=0.8, top_p=0.9, top_k=20, seed=1234)])
+            _run_until_done(e, slots)
+            outs.append([e.cb_read(s, 0, 64) for s in slots])
+            for s in slots:
+                e.cb_release(s)
+        o = outs[0]
+        tolp, tolg = logits_tol(cp["step_logits"]), logits_tol(cg["step_logits"])
+        for row, fix_row in ((0, 0), (2, 2)):                  # penalty rows == the oracle's, up to a non-decisive step
+            ref = cp["gen"][fix_row].tolist()
+            for t, (x, y) in enumerate(zip(o[row], ref)):
+                if x != y:
+                    assert float(cp["margin"][fix_row, t]) <= 2 * tolp, f"penalty row {row} diverges at decisive step {t}"
+                    break
+        ref = cg["gen"][1].tolist()
+        for t, (x, y) in enumerate(zip(o[1], ref)):
+            if x != y:
+                assert float(cg["margin"][1, t]) <= 2 * tolg
+                break
+        assert len(o[3]) == 12 and outs[1][3] == o[3]           # the seed fixes the sampled stream, whoever shares the batch
+        assert outs[1][:3] == o[:3]
+        e.cb_end()
+    finally:
+        e.close()

@@ -9,8 +9,11 @@ from kserve_b200.continuous import ContinuousBatcher
 
 class ScriptedEngine:
     """cb_* surface of B200Engine; sequence i emits script[i][k] as its k-th token."""
-    def __init__(self, max_batch, scripts, eos=(), step_delay=0.0):
+    def __init__(self, max_batch, scripts, eos=(), step_delay=0.0, pages=None, first_token_after=0):
         self.step_delay = step_delay
+        self.pages = pages                # KV pool size in "pages" (1 page per prompt token here); None = unlimited
+        self.first_token_after = first_token_after   # chunked prefill: the first token appears after this many steps
+        self.configured = None
         self.max_batch, self.max_seq_len = max_batch, 4096
         self.scripts = scripts            # prompt tuple -> token list
         self.eos = set(eos)
@@ -34,14 +37,25 @@ class ScriptedEngine:
             if len(q) <= len(st["out"]) and st["out"][-len(q):] == q:
                 st["fin"] = st["stop"] = True
 
-    def cb_admit(self, prompts, max_new, stops):
+    def cb_config(self, chunk, prefix):
+        self.configured = (chunk, prefix)
+
+    def cb_admit(self, prompts, max_new, stops, sampling=None):
+        from kserve_b200.engine import PoolExhausted
         free = [s for s in range(self.max_batch) if s not in self.slots]
         assert len(prompts) <= len(free)
+        if self.pages is not None:
+            used = sum(st["pages"] for st in self.slots.values())
+            if used + sum(len(p) for p in prompts) > self.pages:
+                self.calls.append(("exhausted", len(prompts)))
+                raise PoolExhausted("KV page pool exhausted")
         out = []
-        for p, m, ss in zip(prompts, max_new, stops):
+        for i, (p, m, ss) in enumerate(zip(prompts, max_new, stops)):
             s = free.pop(0)
-            self.slots[s] = dict(script=self.scripts[tuple(p)], out=[], max_new=m, stops=[list(q) for q in ss], fin=False, stop=False)
-            self._emit(self.slots[s])
+            self.slots[s] = dict(script=self.scripts[tuple(p)], out=[], max_new=m, stops=[list(q) for q in ss], fin=False, stop=False,
+                                 pages=len(p), wait=self.first_token_after, sampling=(sampling or [None] * len(prompts))[i])
+            if not self.first_token_after:
+                self._emit(self.slots[s])
             out.append(s)
         self.calls.append(("admit", len(prompts)))
         return out
@@ -52,6 +66,10 @@ class ScriptedEngine:
             time.sleep(self.step_delay * n)
         for _ in range(n):
             for st in self.slots.values():
+                if st["wait"] > 0:
+                    st["wait"] -= 1           # still being prefilled (one chunk per step)
+                    if st["wait"] > 0:
+                        continue
                 self._emit(st)
         self.calls.append(("step", n, len(self.slots)))
 
@@ -217,3 +235,60 @@ def test_randomised_arrivals_keep_every_invariant():
         done += 1
     assert done >= 180 and cb.free_slots == 8 and not eng.slots
     assert cb.stats["finished"] + cb.stats["cancelled"] >= done
+
+
+def test_pool_exhaustion_defers_admission_until_a_release():
+    """b200_cb_admit answers "KV page pool exhausted" (nothing admitted): the scheduler keeps the request queued and
+    retries after the next release instead of failing it; a request that can never fit an idle pool is failed."""
+    scripts = {(1,) * 6: list(range(10, 20)), (2,) * 6: list(range(20, 30)), (3,) * 50: list(range(30, 40))}
+    eng = ScriptedEngine(4, scripts, pages=10)       # two 6-token prompts do not fit together
+    cb = ContinuousBatcher(eng, steps_per_poll=1)
+
+    async def main():
+        pad = lambda p: torch.tensor([p])
+        a = cb.submit([[1] * 6], pad([1] * 6), 5)
+        b = cb.submit([[2] * 6], pad([2] * 6), 5)
+        ra, rb = await asyncio.gather(a, b)
+        assert ra.output_ids[0, 6:].tolist() == list(range(10, 15)) and rb.output_ids[0, 6:].tolist() == list(range(20, 25))
+        try:
+            await cb.submit([[3] * 50], pad([3] * 50), 5)
+        except ValueError as e:
+            return str(e)
+    msg = _run(cb, main())
+    assert "does not fit the KV page pool" in msg
+    kinds = [c[0] for c in eng.calls]
+    assert "exhausted" in kinds and kinds.count("admit") == 2       # the second request waited for the first one's release
+
+
+def test_chunked_prefill_config_sampling_passthrough_and_first_token_time():
+    scripts = {(7, 8, 9): list(range(50, 60))}
+    eng = ScriptedEngine(2, scripts, first_token_after=3)
+    cb = ContinuousBatcher(eng, steps_per_poll=1, prefill_chunk_tokens=256, prefix_cache=True)
+
+    async def main():
+        return await cb.submit([[7, 8, 9]], torch.tensor([[7, 8, 9]]), 4, sampling=dict(do_sample=True, temperature=0.7, seed=5))
+    r = _run(cb, main())
+    assert eng.configured == (256, True)
+    assert r.output_ids[0, 3:].tolist() == [50, 51, 52, 53] and r.num_generated == 4
+    assert r.prefill_ms > 0 and r.decode_ms >= 0       # first token observed some steps after the admit
+
+
+def test_replicated_engine_broadcasts_every_scheduler_call(monkeypatch):
+    """Tensor parallel: the scheduler's b200_cb_* calls go to the follower ranks first (same order, same arguments)."""
+    from kserve_b200 import continuous, tp
+    sent = []
+    monkeypatch.setattr(tp, "leader_call", lambda m, a, k: sent.append((m, a, k)))
+    eng = ScriptedEngine(2, {(1, 2): [5, 6, 7]})
+    eng.tp_size = 2
+    cb = ContinuousBatcher(eng, steps_per_poll=1)
+    assert isinstance(cb.engine, continuous.ReplicatedEngine)
+
+    async def main():
+        return await cb.submit([[1, 2]], torch.tensor([[1, 2]]), 3)
+    r = _run(cb, main())
+    assert r.output_ids[0, 2:].tolist() == [5, 6, 7]
+    names = [m for m, _, _ in sent]
+    assert names[0] == "cb_begin" and "cb_admit" in names and "cb_step" in names and "cb_poll" in names and "cb_release" in names
+    assert names[-1] == "cb_end"
+    admit = next(a for m, a, _ in sent if m == "cb_admit")
+    assert admit[0] == [[1, 2]] and admit[1] == [3]

@@ -177,8 +177,9 @@ class ScriptedCbEngine(ScriptedEngine):
     def cb_end(self):
         pass
 
-    def cb_admit(self, prompts, max_new, stops):
+    def cb_admit(self, prompts, max_new, stops, sampling=None):
         out = []
+        self.last_sampling = sampling
         for p, m_, ss in zip(prompts, max_new, stops):
             s = next(i for i in range(self.max_batch) if i not in self.slots)
             self.slots[s] = dict(last=p[-1], out=[], max_new=m_, fin=False)
@@ -224,7 +225,9 @@ def test_continuous_batching_wiring_and_stream_disconnect(served):
             lines = [l for l in r.iter_lines() if l]
         assert lines[-1] == "data: [DONE]"
         assert "".join(json.loads(l[6:])["choices"][0]["text"] for l in lines[:-1]) == tok.decode(_continuation(tok, "abc", 9), skip_special_tokens=True)
-        assert client.post("/openai/v1/completions", json={"model": "stub", "prompt": "x", "presence_penalty": 1.5}).status_code == 500
+        # logits processors ride along per sequence (round 2: b200_cb_admit takes per-sequence sampling parameters)
+        assert client.post("/openai/v1/completions", json={"model": "stub", "prompt": "x", "presence_penalty": 1.5}).status_code == 200
+        assert eng.last_sampling == [{"repetition_penalty": 1.5}]
 
         async def abandon():          # start a long stream, read one chunk, close the generator
             from kserve_b200.kserve_api.protocol.rest.openai.types import CompletionRequest

@@ -68,3 +68,19 @@ def test_tp4_tp8_match_oracle_fixture(world, overlap_min_t):
     ret = _run(world, ["tiny_kv8_ids", "tiny_kv8_peaked"], env=env, port=29640 + world)
     _check(ret, "tiny_kv8_ids")
     _check(ret, "tiny_kv8_peaked", exact_ids=True)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_continuous_batching_under_tp():
+    """the continuous batcher under tensor parallelism — the scheduler's admit / step / poll / release
+    commands are broadcast to the follower ranks; chunked prefill + prefix cache on.  The peaked fixture's greedy ids must
+    come out exactly, for requests that joined the running batch at different times."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29651", os.path.join(HERE, "tp_cb_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    out = json.loads([l for l in res.stdout.splitlines() if l.startswith("TPCB ")][0][5:])
+    c = load_case("tiny_kv8_peaked")
+    assert out["r1"] == c["gen"][0:1].tolist()
+    assert out["r2"] == c["gen"][1:3].tolist()
+    assert out["r3"] == c["gen"][3:4, :6].tolist()
