@@ -64,6 +64,7 @@ class _Request:
     streamed: int = 0
     t_submit: float = field(default_factory=time.perf_counter)
     t_first: float = 0.0
+    ttft_recorded: bool = False
     cancelled: bool = False                  # set from the event loop when the awaiting task went away (client disconnect)
 
 
@@ -86,6 +87,7 @@ class ContinuousBatcher:
         self._stop = False
         self._thread: Optional[threading.Thread] = None
         self.free_slots = engine.max_batch
+        self.ttft_samples: Deque[float] = deque(maxlen=100000)   # submit -> first token, seconds (load tests / metrics)
         self._pool_blocked = False      # the last admit hit "KV page pool exhausted": retry only after a release
         self.fatal: Optional[BaseException] = None      # set when the scheduler thread died: submit raises it from then on
         self.on_fatal: Optional[Callable[[BaseException], None]] = None   # the model flips `ready` to False here
@@ -250,6 +252,9 @@ class ContinuousBatcher:
             g = [n_gen[s] for s in r.slots]
             if r.t_first == 0.0 and min(g) >= 1:
                 r.t_first = time.perf_counter()          # chunked prefill: the first token appears some steps after the admit
+            if not r.ttft_recorded and r.t_first:
+                r.ttft_recorded = True
+                self.ttft_samples.append(r.t_first - r.t_submit)
             stopped = [s for s in r.slots if stop[s]]
             if stopped:
                 n_out = min(n_gen[s] for s in stopped)          # lockstep rows: everything after the match is dropped

@@ -112,6 +112,7 @@ struct b200_engine {
   std::vector<int32_t> h_page_table;
   // activations
   int cap_T = 0;  // rows of the token-major buffers
+  int rows_cap = 0;   // min(max_batch, kMaxRows): rows of the per-step buffers (logits, xl, partials, candidates)
   bf16 *x = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr, *ybuf = nullptr, *xl = nullptr,
        *qdec = nullptr, *logits = nullptr;
   float* ws = nullptr;
@@ -188,6 +189,8 @@ struct b200_engine {
   int32_t* d_cb_rec = nullptr;       // [max_batch][kCbInitInts]
   int32_t* h_cb = nullptr;           // pinned: init records / poll results / token reads
   bool cb_rows_dirty = false;
+  int32_t* h_cb_rows = nullptr;      // pinned ring [8][kMaxRows]: the row -> slot list of the next decode pass
+  unsigned long long cb_ring_pos = 0, cb_window = 0;
   int cb_num_eos = 0;
   // KV page pool of the continuous-batching mode: pages are reference counted so that 128-token blocks of a prompt
   // can be shared between requests (prefix reuse); a slot's page-table row is filled at admit
@@ -221,6 +224,7 @@ struct b200_engine {
 
 namespace b200 {
 
+constexpr int kMaxRows = 64;   // rows of one decode / LM-head pass (swap-AB GEMM block_n, peer-exchange rows)
 static int pick_block_n(int B) { return B <= 16 ? 16 : (B <= 32 ? 32 : 64); }
 
 // peer-memory all-reduce + residual + RMSNorm of the decode step: one-shot LL below 4 ranks, two-shot (reduce-scatter +
@@ -621,7 +625,7 @@ static int prefill(b200_engine* e) {
   if ((rc = forward_layers(e, st.T, st.B, st.max_len, false))) return rc;
   B200_CUDA_OK(launch_k(gather_rows_kernel, dim3(st.B), dim3(128), 0, e->stream, (const bf16*)e->xn, (const int32_t*)e->d_last_rows, e->xl, e->H));
   e->launches++;
-  return head_and_step(e, e->xl, e->cfg.max_batch, st.B);
+  return head_and_step(e, e->xl, e->rows_cap, st.B);
 }
 
 static int decode_step_enqueue(b200_engine* e) {
@@ -692,7 +696,7 @@ static int decode_step(b200_engine* e, bool use_graph) {
 static int stage_common(b200_engine* e, int B, int S, const std::vector<int>& lens, const b200_gen_params_t* gp) {
   B200_REQUIRE(e->finalized, "weights not finalized");
   B200_REQUIRE(!e->cb_on, "engine is in continuous-batching mode (b200_cb_end first)");
-  B200_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch size out of range");
+  B200_REQUIRE(B >= 1 && B <= e->rows_cap, "batch size out of range (one generate call covers at most 64 rows)");
   B200_REQUIRE(gp->max_new_tokens >= 1, "max_new_tokens must be >= 1");
   B200_REQUIRE(gp->num_eos <= 16 && gp->num_stop <= 16, "too many eos / stop sequences");
   auto& st = e->st;
@@ -773,7 +777,7 @@ static PackOut pack_out(b200_engine* e) {
 // the device once and concatenated into the packed layout by pack_padded_kernel.
 static int stage_prompt(b200_engine* e, const int64_t* ids, const int64_t* mask, int B, int S,
                         const b200_gen_params_t* gp) {
-  B200_REQUIRE(B >= 1 && B <= e->cfg.max_batch && S >= 1 && S <= e->cfg.max_seq_len, "bad batch shape");
+  B200_REQUIRE(B >= 1 && B <= e->rows_cap && S >= 1 && S <= e->cfg.max_seq_len, "bad batch shape");
   std::vector<int> lens(B, S);
   if (mask) {
     for (int b = 0; b < B; ++b) {
@@ -805,7 +809,7 @@ static int stage_prompt(b200_engine* e, const int64_t* ids, const int64_t* mask,
 // Ragged rows as the batcher hands them over (one row per instance of every waiting request).
 static int stage_ragged(b200_engine* e, const int64_t* const* rows, const int32_t* row_lens, int B,
                         const b200_gen_params_t* gp) {
-  B200_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch size out of range");
+  B200_REQUIRE(B >= 1 && B <= e->rows_cap, "batch size out of range");
   std::vector<int> lens(row_lens, row_lens + B);
   int rc = stage_common(e, B, 0, lens, gp);
   if (rc) return rc;
@@ -866,6 +870,7 @@ static int cb_alloc(b200_engine* e) {
   e->cb.out = e->d_out_tokens; e->cb.out_ld = e->out_ld;
   const size_t host_ints = std::max(nb * kCbInitInts, std::max((size_t)e->out_ld, 4 * nb));
   B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_cb), host_ints * 4));
+  B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_cb_rows), (size_t)8 * kMaxRows * 4));
   return 0;
 }
 
@@ -878,14 +883,22 @@ static int cb_decode_enqueue(b200_engine* e, int R) {
   return head_and_step(e, e->xn, e->cap_T, R, e->d_cb_row_slot);
 }
 
-// one decode iteration over the running slots through a CUDA graph keyed by the row count
+// one decode iteration through a CUDA graph keyed by the row count.  At most kMaxRows sequences ride in one pass: with
+// more than that running, a window rotates over them (round robin), so every admitted sequence keeps advancing — the
+// pass streams the weights once whatever the row count, so aggregate tokens/s is that of a full 64-row batch while new
+// requests do not queue for a slot (config 5: 512 concurrent clients).
 static int cb_decode_step(b200_engine* e) {
-  const int R = (int)e->cb_active.size();
-  if (R == 0) return 0;
-  if (e->cb_rows_dirty) {
-    for (int r = 0; r < R; ++r) e->h_cb[r] = e->cb_active[r];
-    B200_CUDA_OK(cudaMemcpyAsync(e->d_cb_row_slot, e->h_cb, (size_t)R * 4, cudaMemcpyHostToDevice, e->stream));
-    B200_CUDA_OK(cudaStreamSynchronize(e->stream));   // h_cb is reused; membership changes are rare
+  const int Rt = (int)e->cb_active.size();
+  if (Rt == 0) return 0;
+  const int R = std::min(Rt, kMaxRows);
+  if (e->cb_rows_dirty || Rt > kMaxRows) {
+    int32_t* ring = e->h_cb_rows + (size_t)(e->cb_ring_pos % 8) * kMaxRows;
+    if (e->cb_ring_pos && (e->cb_ring_pos % 8) == 0) B200_CUDA_OK(cudaStreamSynchronize(e->stream));   // the ring slot's last copy is long done
+    ++e->cb_ring_pos;
+    const int start = Rt > kMaxRows ? (int)(e->cb_window % Rt) : 0;
+    for (int r = 0; r < R; ++r) ring[r] = e->cb_active[(start + r) % Rt];
+    if (Rt > kMaxRows) e->cb_window += R;
+    B200_CUDA_OK(cudaMemcpyAsync(e->d_cb_row_slot, ring, (size_t)R * 4, cudaMemcpyHostToDevice, e->stream));
     e->cb_rows_dirty = false;
   }
   static const bool eager = getenv("B200_NO_GRAPH") != nullptr;
@@ -939,7 +952,7 @@ static int cb_prefill_pending(b200_engine* e, long long budget) {
   struct Part { size_t idx; int start, count; bool fin; };
   std::vector<Part> parts;
   long long left = budget;
-  for (size_t i = 0; i < e->cb_pending.size() && (int)parts.size() < std::min(e->cfg.max_batch, 64); ++i) {
+  for (size_t i = 0; i < e->cb_pending.size() && (int)parts.size() < e->rows_cap; ++i) {
     const auto& pd = e->cb_pending[i];
     const int rem = (int)pd.toks.size() - pd.done;
     int c = rem <= left ? rem : (int)((left / 128) * 128);
@@ -983,7 +996,7 @@ static int cb_prefill_pending(b200_engine* e, long long budget) {
   if (nfin) {
     B200_CUDA_OK(launch_k(gather_rows_kernel, dim3(nfin), dim3(128), 0, s, (const bf16*)e->xn, (const int32_t*)e->d_last_rows, e->xl, e->H));
     e->launches++;
-    if ((rc = head_and_step(e, e->xl, e->cfg.max_batch, nfin, e->d_cb_rec))) return rc;
+    if ((rc = head_and_step(e, e->xl, e->rows_cap, nfin, e->d_cb_rec))) return rc;
   }
   B200_CUDA_OK(cudaStreamSynchronize(s));   // h_stage is reused by the next pass
   e->cb_stat[2] += T; e->cb_stat[4]++;
@@ -1200,7 +1213,10 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   B200_REQUIRE(c->num_heads % c->tp_size == 0 && c->num_kv_heads % c->tp_size == 0, "heads must divide tp_size");
   B200_REQUIRE(c->intermediate_size % (16 * c->tp_size) == 0, "intermediate_size must be a multiple of 16*tp_size");
   B200_REQUIRE(c->hidden_size % 64 == 0, "hidden_size must be a multiple of 64");
-  B200_REQUIRE(c->max_batch >= 1 && c->max_batch <= 64, "max_batch must be in [1, 64]");
+  // max_batch = sequences the engine can hold at once (KV pages, per-sequence state).  One forward pass still covers at most
+  // kMaxRows = 64 of them: a static generate call is limited to 64 rows, the continuous batcher rotates a 64-row window
+  // over the running sequences when more than 64 are live.
+  B200_REQUIRE(c->max_batch >= 1 && c->max_batch <= 512, "max_batch must be in [1, 512]");
   B200_REQUIRE(c->num_heads % c->num_kv_heads == 0 && c->num_heads / c->num_kv_heads <= 8, "GQA group must be <= 8");
   int ndev = 0;
   B200_CUDA_OK(cudaGetDeviceCount(&ndev));
@@ -1291,17 +1307,19 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   if ((rc = dmalloc(&e->attn, T * e->nh * kHeadDim))) return rc;
   if ((rc = dmalloc(&e->hbuf, T * e->I))) return rc;
   if (tp == 1 && (rc = dmalloc(&e->ybuf, T * H))) return rc;   // tp > 1: inside the IPC-shared exchange block (below)
-  if ((rc = dmalloc(&e->xl, (size_t)c->max_batch * H))) return rc;
-  if ((rc = dmalloc(&e->qdec, (size_t)c->max_batch * e->nh * kHeadDim))) return rc;
-  if ((rc = dmalloc(&e->logits, (size_t)c->max_batch * e->Vl))) return rc;
+  e->rows_cap = std::min(c->max_batch, kMaxRows);
+  const size_t RC = (size_t)e->rows_cap;
+  if ((rc = dmalloc(&e->xl, RC * H))) return rc;
+  if ((rc = dmalloc(&e->qdec, RC * e->nh * kHeadDim))) return rc;
+  if ((rc = dmalloc(&e->logits, RC * e->Vl))) return rc;
   B200_CUDA_OK(cudaMemset(e->x, 0, T * H * 2));
   B200_CUDA_OK(cudaMemset(e->xn, 0, T * H * 2));
   B200_CUDA_OK(cudaMemset(e->attn, 0, T * e->nh * kHeadDim * 2));
   B200_CUDA_OK(cudaMemset(e->hbuf, 0, T * e->I * 2));
-  B200_CUDA_OK(cudaMemset(e->xl, 0, (size_t)c->max_batch * H * 2));
-  e->ws_elems = (size_t)16 * c->max_batch * std::max(std::max(e->qkv_cols, e->H), 2 * e->I);
+  B200_CUDA_OK(cudaMemset(e->xl, 0, RC * H * 2));
+  e->ws_elems = (size_t)16 * RC * std::max(std::max(e->qkv_cols, e->H), 2 * e->I);
   if (e->E) {
-    e->ws_elems = std::max(e->ws_elems, (size_t)e->E * 16 * c->max_batch * e->H);
+    e->ws_elems = std::max(e->ws_elems, (size_t)e->E * 16 * RC * e->H);
     e->g_rows = 2 * e->cap_T + 8 * e->E + 256;
     if ((rc = dmalloc(&e->tok_expert, (size_t)2 * T))) return rc;
     if ((rc = dmalloc(&e->tok_row, (size_t)2 * T))) return rc;
@@ -1320,14 +1338,14 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   if ((rc = dmalloc(&e->sk_ws, e->sk_ws_floats))) return rc;
   if ((rc = dmalloc(&e->sk_flags, (size_t)e->sk_tiles))) return rc;
   B200_CUDA_OK(cudaMemset(e->sk_flags, 0, (size_t)e->sk_tiles * sizeof(int)));
-  if ((rc = dmalloc(&e->part_o, (size_t)c->max_batch * e->nkv * 8 * e->G * kHeadDim))) return rc;
-  if ((rc = dmalloc(&e->part_ml, (size_t)c->max_batch * e->nkv * 8 * e->G * 2))) return rc;
-  if ((rc = dmalloc(&e->attn_split_cnt, (size_t)c->max_batch * e->nkv))) return rc;
-  B200_CUDA_OK(cudaMemset(e->attn_split_cnt, 0, (size_t)c->max_batch * e->nkv * sizeof(int)));
-  if ((rc = dmalloc(&e->cand_val, (size_t)c->max_batch * 16))) return rc;
-  if ((rc = dmalloc(&e->cand_idx, (size_t)c->max_batch * 16))) return rc;
-  if ((rc = dmalloc(&e->cand_val_all, (size_t)c->max_batch * tp))) return rc;
-  if ((rc = dmalloc(&e->cand_idx_all, (size_t)c->max_batch * tp))) return rc;
+  if ((rc = dmalloc(&e->part_o, RC * e->nkv * 8 * e->G * kHeadDim))) return rc;
+  if ((rc = dmalloc(&e->part_ml, RC * e->nkv * 8 * e->G * 2))) return rc;
+  if ((rc = dmalloc(&e->attn_split_cnt, RC * e->nkv))) return rc;
+  B200_CUDA_OK(cudaMemset(e->attn_split_cnt, 0, RC * e->nkv * sizeof(int)));
+  if ((rc = dmalloc(&e->cand_val, RC * 16))) return rc;
+  if ((rc = dmalloc(&e->cand_idx, RC * 16))) return rc;
+  if ((rc = dmalloc(&e->cand_val_all, RC * tp))) return rc;
+  if ((rc = dmalloc(&e->cand_idx_all, RC * tp))) return rc;
   // bookkeeping
   e->out_ld = c->max_seq_len;
   if ((rc = dmalloc(&e->d_tok, T))) return rc;
@@ -1362,7 +1380,7 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
     B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&e->h_pred), raw * 8));
   }
   if (tp > 1) {
-    B200_REQUIRE(tp <= kMaxTp && c->max_batch <= kArRows, "tp_size / max_batch exceed the peer-exchange layout");
+    B200_REQUIRE(tp <= kMaxTp && kMaxRows <= kArRows, "tp_size exceeds the peer-exchange layout");
     const ArLayout lay = ArLayout::make(e->H);
     // one allocation = one IPC handle: [decode LL packets | candidate exchange | flags | prefill exchange buffer y[T][H]]
     B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e->ar_local), lay.total + T * H * sizeof(bf16)));

@@ -64,7 +64,7 @@ class B200Engine:
         mc.rope_theta = float(rope_parameters(cfg)["rope_theta"])
         mc.max_batch = max_batch
         mc.max_seq_len = max_seq_len
-        mc.max_prefill_tokens = max_prefill_tokens or max_batch * max_seq_len
+        mc.max_prefill_tokens = max_prefill_tokens or min(max_batch, 64) * max_seq_len     # one pass covers at most 64 sequences
         mc.num_kv_pages = num_kv_pages
         mc.tp_rank, mc.tp_size, mc.device = tp_rank, tp_size, device
         mc.num_experts = int(cfg.get("num_local_experts", 0) or 0)

@@ -424,8 +424,8 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                 f"{request.max_tokens} in the completion). "
                 f"Please reduce the length of the messages or completion.")
         self.validate_supported_completion_params(request)
-        if B > self.max_batch:
-            raise OpenAIError(f"batch of {B} prompts exceeds this engine's max batch {self.max_batch}")
+        if B > min(self.max_batch, 64):
+            raise OpenAIError(f"batch of {B} prompts exceeds this engine's max batch {min(self.max_batch, 64)}")
         stop_sequences: List[List[int]] = []
         if request.stop is not None:                            # :578-593 (stop defaults to [], q2)
             stop = request.stop if isinstance(request.stop, list) else [request.stop]
@@ -635,8 +635,8 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         B, S = ids.shape
         if mask is not None and tuple(mask.shape) != (B, S):
             raise InvalidInput(f"attention_mask shape {list(mask.shape)} differs from input_ids shape {[B, S]}")
-        if B > self.max_batch:
-            raise InvalidInput(f"batch of {B} exceeds this engine's max batch {self.max_batch}")
+        if B > min(self.max_batch, 64):
+            raise InvalidInput(f"batch of {B} exceeds this engine's max batch {min(self.max_batch, 64)}")
         if S + max_tokens > self.max_length:
             raise InvalidInput(f"prompt ({S}) + max_tokens ({max_tokens}) exceeds the model's maximum context length {self.max_length}")
         if mask is not None:

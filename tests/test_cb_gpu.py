@@ -244,7 +244,7 @@ def test_chunked_prefill_interleaves_with_decode_and_matches_full_prefill(peaked
     try:
         a = e.cb_admit([short], [16])[0]
         e.cb_step(1)
-        assert e.cb_poll()[0][a] == 1                           # 48-token prompt: one chunk, first token after one step
+        assert e.cb_poll()[0][a] == 2                           # one iteration = its only chunk (first token) + a decode step
         b = e.cb_admit([rows[0]], [12])[0]                       # 300 tokens = chunks of 128 + 128 + 44
         assert e.cb_stats()["pending_prompts"] == 1 and e.cb_poll()[0][b] == 0
         gen_a = []
@@ -252,7 +252,7 @@ def test_chunked_prefill_interleaves_with_decode_and_matches_full_prefill(peaked
             e.cb_step(1)
             n_gen, _, _ = e.cb_poll()
             gen_a.append(n_gen[a])
-        assert gen_a == [2, 3, 4]                               # the short sequence never stalled
+        assert gen_a == [3, 4, 5]                               # the short sequence never stalled
         assert e.cb_poll()[0][b] == 2 and e.cb_stats()["pending_prompts"] == 0   # first token from its last chunk + the same iteration's decode step
         _run_until_done(e, [a, b])
         assert e.cb_read(b, 0, 12) == ref[0].tolist()
