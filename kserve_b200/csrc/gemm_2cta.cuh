@@ -66,12 +66,19 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {  // arrive o
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
+// output tiles are written once and read by a LATER kernel: with stream_out they go out as cache-streaming stores so that
+// the (up to 940 MB per GEMM) output stream does not push the A / B tiles the other CTAs are about to re-read out of L2
+__device__ __forceinline__ void st_out_v4(bf16* p, const uint4& o, int stream_out) {
+  if (stream_out) asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+  else *reinterpret_cast<uint4*>(p) = o;
+}
+
 struct Gemm2Unit { int m_pair, n_t; };
 __device__ __forceinline__ bool gemm2_get_unit(const GemmParams& p, int idx, int cluster_id, int num_clusters, Gemm2Unit& u, int m_tiles_rt) {
   const int m_pairs = (m_tiles_rt + 1) >> 1;
   const int t = cluster_id + idx * num_clusters;
   if (t >= m_pairs * p.n_tiles) return false;
-  constexpr int G = kGemmGroupM / 2;            // 8 pairs = 16 m-tiles per raster group
+  const int G = p.group_pairs > 0 ? p.group_pairs : kGemmGroupM / 2;   // m-pairs (256 rows each) per raster group; default 8
   const int per_group = G * p.n_tiles;
   const int grp = t / per_group;
   const int first = grp * G;
@@ -231,7 +238,7 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               uint4 o;
               o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
               o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-              *reinterpret_cast<uint4*>(orow + j) = o;
+              st_out_v4(orow + j, o, p.stream_out);
             }
           } else {
             for (int j = 0; j < nvalid; ++j) {
@@ -252,8 +259,8 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             o0.z = pack_bf16x2(h[4], h[5]);   o0.w = pack_bf16x2(h[6], h[7]);
             o1.x = pack_bf16x2(h[8], h[9]);   o1.y = pack_bf16x2(h[10], h[11]);
             o1.z = pack_bf16x2(h[12], h[13]); o1.w = pack_bf16x2(h[14], h[15]);
-            reinterpret_cast<uint4*>(orow)[0] = o0;
-            reinterpret_cast<uint4*>(orow)[1] = o1;
+            st_out_v4(orow, o0, p.stream_out);
+            st_out_v4(orow + 8, o1, p.stream_out);
           } else {
             for (int j = 0; j < 16 && oc + j < p.out_cols; ++j) orow[j] = __float2bfloat16_rn(h[j]);
           }

@@ -55,6 +55,8 @@ struct GemmParams {
   // empty groups are skipped: their weights are never streamed) and whose outputs start at out + g * group_out_stride
   int group_m_tiles;
   long long group_out_stride;
+  int group_pairs;         // 2-CTA prefill kernel: m-pairs per raster group (0 = default 8)
+  int stream_out;          // 2-CTA prefill kernel: cache-streaming output stores
   int sched;
   int sk_slots;            // partial slots per tile
   float* sk_ws;            // [m_tiles][sk_slots][BLOCK_N][128] fp32
