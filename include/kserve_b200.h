@@ -121,6 +121,14 @@ typedef struct b200_timing {
 } b200_timing_t;
 int b200_engine_last_timing(b200_engine_t* e, b200_timing_t* out);
 
+/* Failure handling of the device-side waits (peer-memory all-reduce packets / flags, candidate exchange, stream-K pieces):
+ * a wait that times out — a tensor-parallel peer died or fell out of step — does NOT trap the CUDA context; it records a
+ * code, the kernels run to completion with whatever data they have, and the entry point that next synchronises
+ * (b200_generate, b200_batch_predict, b200_fetch_staged, b200_cb_poll) returns -8 with the text in b200_last_error();
+ * the engine then refuses further work until it is re-created (or the fault is reset for a diagnostic retry).
+ * code: 0 none, 1 peer flag, 2 all-reduce packet, 3 candidate exchange, 4 stream-K piece. */
+int b200_engine_fault(b200_engine_t* e, int32_t* code, int32_t reset);
+
 /* Device-resident variant for benchmarking the kernels alone: prompt already staged with
  * b200_stage_prompt (no H2D/D2H inside), runs prefill + `steps` decode steps, no result copy. */
 int b200_stage_prompt(b200_engine_t* e, const int64_t* input_ids, const int64_t* attention_mask, int32_t B,

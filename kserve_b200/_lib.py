@@ -60,6 +60,7 @@ def load() -> C.CDLL:
     lib.b200_generate.argtypes = [vp, vp, vp, i32, i32, C.POINTER(GenParams), vp, C.POINTER(i32),
                                   C.POINTER(i32), vp, TOKEN_CALLBACK, vp]
     lib.b200_engine_last_timing.argtypes = [vp, C.POINTER(Timing)]
+    lib.b200_engine_fault.argtypes = [vp, C.POINTER(i32), i32]
     lib.b200_stage_prompt.argtypes = [vp, vp, vp, i32, i32, C.POINTER(GenParams)]
     lib.b200_run_staged.argtypes = [vp, i32, i32]
     lib.b200_run_staged_timed.argtypes = [vp, i32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -101,7 +102,11 @@ def load() -> C.CDLL:
     return lib
 
 
+class EngineFault(B200Error):
+    """rc -8: a device-side wait timed out (tensor-parallel peer lost); the engine must be re-created"""
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().b200_last_error().decode("utf-8", "replace")
-        raise B200Error(f"{what} failed (rc={rc}): {msg}")
+        raise (EngineFault if rc == -8 else B200Error)(f"{what} failed (rc={rc}): {msg}")

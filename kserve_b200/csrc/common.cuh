@@ -109,6 +109,31 @@ struct TraceScope {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Recoverable faults of the cross-GPU / cross-CTA waits.  A tensor-parallel peer that died, or was never launched, must
+// not take this rank's CUDA context with it: a wait that times out records a code here and the kernel carries on with
+// whatever data it has (every later wait then gives up at once), instead of __trap()ing — which would poison the context
+// of every rank for good.  The host reads the code at its next synchronisation point (b200_engine_fault), fails the call,
+// marks the engine unusable, and the model server reports the model as not ready.  Codes: 1 peer flag, 2 all-reduce
+// packet, 3 candidate exchange, 4 stream-K piece.
+// ---------------------------------------------------------------------------------------------
+__device__ int g_fault_code = 0;
+__device__ __forceinline__ bool fault_raised() { return *reinterpret_cast<volatile int*>(&g_fault_code) != 0; }
+__device__ __forceinline__ void fault_raise(int code) { atomicCAS(&g_fault_code, 0, code); }
+// One step of a bounded spin: false = keep waiting, true = give up (time-out reached, or another wait already failed).
+// The bound is wall time (%globaltimer, looked at every 1024 polls): g_wait_timeout_ns, default 5 s — far beyond any
+// legitimate wait of a decode step, short enough that a lost peer fails the request instead of hanging the server.
+__device__ unsigned long long g_wait_timeout_ns = 5000000000ull;
+struct SpinGuard { uint32_t polls = 0; unsigned long long t0 = 0; };
+__device__ __forceinline__ bool spin_give_up(SpinGuard& g, int code) {
+  if ((++g.polls & 0x3ff) != 0) return false;
+  if (fault_raised()) return true;
+  const unsigned long long now = global_timer();
+  if (g.t0 == 0) { g.t0 = now; return false; }
+  if (now - g.t0 > *reinterpret_cast<volatile unsigned long long*>(&g_wait_timeout_ns)) { fault_raise(code); return true; }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch: a kernel lets its successor start (prologue, weight prefetch) while it is
 // still running, and blocks only where it first touches data the predecessor produced.  Both are no-ops when
 // the kernel was launched without the programmatic-stream-serialization attribute.

@@ -218,6 +218,7 @@ struct b200_engine {
   std::unordered_map<int, std::vector<PfGemm>> pf_tables;
   const std::vector<PfGemm>* pf_cur = nullptr;   // table of the step being captured (nullptr: no prefetch launches)
   cudaEvent_t ev_pf_fork = nullptr, ev_pf_join = nullptr;
+  bool faulted = false;                          // a cross-GPU / cross-CTA wait timed out (common.cuh: g_fault_code)
   int pf_cap_kb = 16;                            // k-block tiles (16 KB each) prefetched per CTA of the next GEMM
   bool pf_forked = false;
 };
@@ -363,7 +364,8 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
     rp.cos_tab = e->cos_tab; rp.sin_tab = e->sin_tab; rp.nh = e->nh; rp.nkv = e->nkv;
     e->launches++;
     if (!decode) {   // decode: RoPE + KV append are fused into attn_decode_kernel
-      B200_CUDA_OK(launch_k(rope_kv_kernel, dim3(T), dim3(512), 0, s, rp));
+      rp.T = T; rp.tokens_per_cta = T >= 4096 ? 4 : 1;
+      B200_CUDA_OK(launch_k(rope_kv_kernel, dim3((T + rp.tokens_per_cta - 1) / rp.tokens_per_cta), dim3(512), 0, s, rp));
       e->launches++;
     }
     // ---- attention
@@ -695,6 +697,7 @@ static int decode_step(b200_engine* e, bool use_graph) {
 // (un-padded) sequence lengths; S is the padded prompt width (0 for ragged batcher input).
 static int stage_common(b200_engine* e, int B, int S, const std::vector<int>& lens, const b200_gen_params_t* gp) {
   B200_REQUIRE(e->finalized, "weights not finalized");
+  B200_REQUIRE(!e->faulted, "engine fault: an earlier device-side wait timed out; re-create the engine");
   B200_REQUIRE(!e->cb_on, "engine is in continuous-batching mode (b200_cb_end first)");
   B200_REQUIRE(B >= 1 && B <= e->rows_cap, "batch size out of range (one generate call covers at most 64 rows)");
   B200_REQUIRE(gp->max_new_tokens >= 1, "max_new_tokens must be >= 1");
@@ -831,12 +834,25 @@ static int stage_ragged(b200_engine* e, const int64_t* const* rows, const int32_
   return 0;
 }
 
+// called right after a stream synchronisation: did any wait of the kernels just run give up?
+static int check_fault(b200_engine* e) {
+  int code = 0;
+  B200_CUDA_OK(cudaMemcpyFromSymbol(&code, g_fault_code, sizeof(int)));
+  if (code == 0) return 0;
+  e->faulted = true;
+  static const char* what[] = {"", "peer flag", "peer all-reduce packet", "peer candidate exchange", "stream-K piece"};
+  set_last_error(std::string("engine fault: a device-side wait timed out (") + (code >= 1 && code <= 4 ? what[code] : "?") +
+                 ") — a tensor-parallel peer is gone or out of step; this engine is unusable until it is re-created");
+  return -8;
+}
+
 static int fetch_result(b200_engine* e, int64_t* out_ids, int32_t* out_len, int32_t* stop_triggered) {
   auto& st = e->st;
   cudaStream_t s = e->stream;
   B200_CUDA_OK(cudaMemcpyAsync(e->h_state, e->d_state, sizeof(StepState), cudaMemcpyDeviceToHost, s));
   B200_CUDA_OK(cudaMemcpyAsync(e->h_out_tokens, e->d_out_tokens, (size_t)st.B * e->out_ld * 4, cudaMemcpyDeviceToHost, s));
   B200_CUDA_OK(cudaStreamSynchronize(s));
+  { int frc = check_fault(e); if (frc) return frc; }
   const int Tn = e->h_state->step;
   const int W = st.S + st.max_new;
   for (int b = 0; b < st.B; ++b) {
@@ -1246,6 +1262,10 @@ int b200_engine_create(const b200_model_config_t* c, const void* nccl_id, b200_e
   B200_CUDA_OK(cudaEventCreateWithFlags(&e->ev_pf_fork, cudaEventDisableTiming));
   B200_CUDA_OK(cudaEventCreateWithFlags(&e->ev_pf_join, cudaEventDisableTiming));
   if (getenv("B200_PF_CAP_KB")) e->pf_cap_kb = std::max(1, atoi(getenv("B200_PF_CAP_KB")));
+  if (getenv("B200_WAIT_TIMEOUT_MS")) {   // bound of the device-side waits (default 5 s), see common.cuh
+    const unsigned long long ns = 1000000ull * (unsigned long long)std::max(1, atoi(getenv("B200_WAIT_TIMEOUT_MS")));
+    B200_CUDA_OK(cudaMemcpyToSymbol(g_wait_timeout_ns, &ns, sizeof(ns)));
+  }
   B200_CUDA_OK(cudaEventCreate(&e->ev0));
   B200_CUDA_OK(cudaEventCreate(&e->ev1));
   B200_CUDA_OK(cudaEventCreate(&e->ev2));
@@ -1709,6 +1729,7 @@ int b200_batch_predict(b200_engine_t* e, const int64_t* const* rows, const int32
   B200_CUDA_OK(cudaEventRecord(e->ev2, s));
   B200_CUDA_OK(cudaMemcpyAsync(e->h_state, e->d_state, sizeof(StepState), cudaMemcpyDeviceToHost, s));
   B200_CUDA_OK(cudaStreamSynchronize(s));
+  { int frc = check_fault(e); if (frc) return frc; }
   const int T = e->h_state->step;
   scatter_predictions_kernel<<<n_rows, 128, 0, s>>>(e->d_out_tokens, e->out_ld, n_rows, T, e->d_pred);
   B200_CUDA_OK(cudaGetLastError());
@@ -1754,6 +1775,20 @@ int b200_batcher_tick(b200_batcher_t* b, int64_t now_us, int32_t cap, int64_t* t
   const int n = b->core.tick(now_us, tk, first, count, cap, total_instances);
   B200_REQUIRE(n >= 0, "ticket buffer too small");
   *n_requests = n;
+  return 0;
+}
+
+int b200_engine_fault(b200_engine_t* e, int32_t* code, int32_t reset) {
+  B200_REQUIRE(e && code, "null argument");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  int c = 0;
+  B200_CUDA_OK(cudaMemcpyFromSymbol(&c, g_fault_code, sizeof(int)));
+  *code = c;
+  if (reset) {
+    const int zero = 0;
+    B200_CUDA_OK(cudaMemcpyToSymbol(g_fault_code, &zero, sizeof(int)));
+    e->faulted = false;
+  }
   return 0;
 }
 
@@ -1879,6 +1914,7 @@ int b200_cb_admit(b200_engine_t* e, int32_t n, const int64_t* const* rows, const
 
 int b200_cb_step(b200_engine_t* e, int32_t n_steps) {
   B200_REQUIRE(e && e->cb_on, "b200_cb_begin was not called");
+  B200_REQUIRE(!e->faulted, "engine fault: an earlier device-side wait timed out; re-create the engine");
   B200_CUDA_OK(cudaSetDevice(e->cfg.device));
   for (int i = 0; i < n_steps; ++i) {
     int rc;
@@ -1897,6 +1933,7 @@ int b200_cb_poll(b200_engine_t* e, int32_t* n_gen, int32_t* finished, int32_t* s
   B200_CUDA_OK(cudaMemcpyAsync(e->h_cb + nb, e->cb.finished, nb * 4, cudaMemcpyDeviceToHost, s));
   B200_CUDA_OK(cudaMemcpyAsync(e->h_cb + 2 * nb, e->cb.stop_hit, nb * 4, cudaMemcpyDeviceToHost, s));
   B200_CUDA_OK(cudaStreamSynchronize(s));
+  { int frc = check_fault(e); if (frc) return frc; }
   for (size_t i = 0; i < nb; ++i) {
     const bool used = e->cb_used[i] != 0;
     n_gen[i] = used ? e->h_cb[i] : 0;
@@ -2070,7 +2107,8 @@ int b200_op_rope_kv(const void* qkv, int64_t ld, void* q_out, int64_t ldq, void*
   p.qkv = (const bf16*)qkv; p.ld = ld; p.q_out = (bf16*)q_out; p.ldq = ldq; p.kcache = (bf16*)kcache; p.vcache = (bf16*)vcache;
   p.page_table = page_table; p.max_pages = max_pages; p.tok_seq = tok_seq; p.tok_pos = tok_pos;
   p.cos_tab = (const bf16*)cos_tab; p.sin_tab = (const bf16*)sin_tab; p.nh = nh; p.nkv = nkv;
-  rope_kv_kernel<<<T, 512, 0, (cudaStream_t)stream>>>(p);
+  p.T = T; p.tokens_per_cta = T >= 4096 ? 4 : 1;
+  rope_kv_kernel<<<(T + p.tokens_per_cta - 1) / p.tokens_per_cta, 512, 0, (cudaStream_t)stream>>>(p);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }

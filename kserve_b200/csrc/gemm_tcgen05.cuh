@@ -311,10 +311,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float* skw = (sg.type != 0) ? p.sk_ws + ((long long)sg.m_t * p.sk_slots) * sk_piece + q * 32 + lane : nullptr;
       if (sg.type == 2) {   // wait until every other piece of this tile has been parked
         if (threadIdx.x == 64) {
-          uint32_t spins = 0;
-          while (*reinterpret_cast<volatile int*>(p.sk_flags + sg.m_t) != sg.slot) {
-            if (++spins > (1u << 28)) { printf("b200: stream-K flag timeout (tile %d)\n", sg.m_t); __trap(); }
-          }
+          SpinGuard spins;
+          while (*reinterpret_cast<volatile int*>(p.sk_flags + sg.m_t) != sg.slot)
+            if (spin_give_up(spins, 4)) break;
           __threadfence();
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");

@@ -292,6 +292,18 @@ inline int launch_rmsnorm(int mode, bf16* x, const bf16* w, bf16* xn, int rows, 
   if (rows == 0) return 0;
   const float* np = nullptr;
   const bf16* ny = nullptr;
+  // prefill-sized launches of the plain / post-all-reduce norm: the warp-per-row kernel
+  static const bool rows_off = getenv("B200_NORM_ROWS_OFF") != nullptr;
+  if (!rows_off && mode != 1 && rows >= 256) {
+#define B200_NORM_ROWS(NVV)                                                                                                       \
+    if (H == NVV * 256) {                                                                                                          \
+      if (mode == 0) B200_CUDA_OK(launch_k(rmsnorm_rows_kernel<0, NVV>, dim3((rows + 7) / 8), dim3(256), 0, s, x, w, xn, rows, eps, ny)); \
+      else B200_CUDA_OK(launch_k(rmsnorm_rows_kernel<2, NVV>, dim3((rows + 7) / 8), dim3(256), 0, s, x, w, xn, rows, eps, y));           \
+      return 0;                                                                                                                    \
+    }
+    B200_NORM_ROWS(2) B200_NORM_ROWS(4) B200_NORM_ROWS(8) B200_NORM_ROWS(16) B200_NORM_ROWS(32)
+#undef B200_NORM_ROWS
+  }
   if (mode == 0) B200_CUDA_OK(launch_k(rmsnorm_kernel<0>, dim3(rows), dim3(kNormThreads), smem, s, x, w, xn, H, eps, np, 0, 0LL, 0LL, ny));
   else if (mode == 1) B200_CUDA_OK(launch_k(rmsnorm_kernel<1>, dim3(rows), dim3(kNormThreads), smem, s, x, w, xn, H, eps, partial, splits, split_stride, ld_partial, ny));
   else B200_CUDA_OK(launch_k(rmsnorm_kernel<2>, dim3(rows), dim3(kNormThreads), smem, s, x, w, xn, H, eps, np, 0, 0LL, 0LL, y));

@@ -162,6 +162,73 @@ rmsnorm_kernel(bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restric
   }
 }
 
+// Many-row variant for the prefill (thousands of rows): one WARP per row, the whole row in registers (NV 16-byte
+// vectors per lane, all loads issued before the first use), warp-shuffle reduction, no shared memory, no block
+// barriers; 8 rows per CTA.  The one-CTA-per-row kernel above spends most of its time launching 32768 CTAs and in two
+// block-wide barriers per row (r01 ncu: 0.47 of the HBM peak).  MODE 0: xn = norm(x) * w;  MODE 2: x += y first.
+// Same rounding points; the sum of squares is accumulated lane-wise then across lanes (fp32) instead of thread-wise
+// then across warps.
+template <int MODE, int NV>
+__global__ void __launch_bounds__(256)
+rmsnorm_rows_kernel(bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ xn, int rows, float eps,
+                    const bf16* __restrict__ y) {
+  TraceScope _ts(TK_RMSNORM);
+  pdl_launch_dependents();
+  pdl_wait();
+  _ts.mark();
+  constexpr int H = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  bf16* xr = x + (long long)r * H;
+  uint4 u[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) u[v] = *reinterpret_cast<const uint4*>(xr + (v * 32 + lane) * 8);
+  if constexpr (MODE == 2) {
+    uint4 yu[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) yu[v] = ld_nc_v4(y + (long long)r * H + (v * 32 + lane) * 8);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const uint32_t uw[4] = {u[v].x, u[v].y, u[v].z, u[v].w}, yw[4] = {yu[v].x, yu[v].y, yu[v].z, yu[v].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float2 p2 = unpack_bf16x2(uw[t]), q2 = unpack_bf16x2(yw[t]);
+        o[t] = pack_bf16x2(p2.x + q2.x, p2.y + q2.y);
+      }
+      u[v] = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(xr + (v * 32 + lane) * 8) = u[v];
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint32_t uw[4] = {u[v].x, u[v].y, u[v].z, u[v].w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 p2 = unpack_bf16x2(uw[t]);
+      ss += p2.x * p2.x;
+      ss += p2.y * p2.y;
+    }
+  }
+  const float tot = warp_sum(ss);
+  const float rs = 1.0f / sqrtf(tot / (float)H + eps);
+  bf16* o = xn + (long long)r * H;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const uint4 wu = *reinterpret_cast<const uint4*>(w + (v * 32 + lane) * 8);
+    const uint32_t uw[4] = {u[v].x, u[v].y, u[v].z, u[v].w}, ww[4] = {wu.x, wu.y, wu.z, wu.w};
+    uint32_t ov[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float2 p2 = unpack_bf16x2(uw[t]), w2 = unpack_bf16x2(ww[t]);
+      ov[t] = pack_bf16x2(w2.x * bf16_round(p2.x * rs), w2.y * bf16_round(p2.y * rs));   // cast to bf16 BEFORE the weight multiply
+    }
+    *reinterpret_cast<uint4*>(o + (v * 32 + lane) * 8) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+  }
+}
+
 // sum split-K partials into a bf16 matrix (used before the TP all-reduce): y[r][i] = bf16(sum_s p[s][r][i])
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int splits, long long split_stride,
                                        long long ld_partial, bf16* __restrict__ y, int H) {
@@ -195,6 +262,7 @@ struct RopeKvParams {
   const int32_t* tok_pos;                // [T] position within the sequence
   const bf16* cos_tab; const bf16* sin_tab;  // [max_pos][64]
   int nh, nkv;
+  int T, tokens_per_cta;                     // tokens in this launch; consecutive tokens handled by one CTA
 };
 
 __device__ __forceinline__ void load8(const RopeKvParams& p, int t, int col, float (&f)[8]) {
@@ -226,13 +294,15 @@ __global__ void __launch_bounds__(512) rope_kv_kernel(const RopeKvParams p) {
   pdl_launch_dependents();
   pdl_wait();
   _ts.mark();
-  const int t = blockIdx.x;
+  const int rope_items = (p.nh + p.nkv) * 8;   // 8 threads per roped head (each 8 dims of both halves)
+  const int copy_items = p.nkv * 16;           // 16 threads per V head
+  // tokens_per_cta consecutive tokens per CTA (prefill launches: fewer, longer-lived CTAs — the one-token-per-CTA launch
+  // of 32768 CTAs was launch-rate bound at 0.37 of the HBM peak, r01 ncu)
+  for (int t = blockIdx.x * p.tokens_per_cta; t < min(p.T, (int)(blockIdx.x + 1) * p.tokens_per_cta); ++t) {
   const int pos = p.tok_pos[t];
   const int seq = p.tok_seq[t];
   const int page = p.page_table[(long long)seq * p.max_pages + pos / kPageTokens];
   const int slot = pos % kPageTokens;
-  const int rope_items = (p.nh + p.nkv) * 8;   // 8 threads per roped head (each 8 dims of both halves)
-  const int copy_items = p.nkv * 16;           // 16 threads per V head
   for (int it = threadIdx.x; it < rope_items + copy_items; it += blockDim.x) {
     if (it < rope_items) {
       const int head = it >> 3, c = (it & 7) * 8;  // dims [c, c+8) and [c+64, c+72)
@@ -275,6 +345,7 @@ __global__ void __launch_bounds__(512) rope_kv_kernel(const RopeKvParams p) {
       bf16* v = p.vcache + ((long long)page * p.nkv + kvh) * (kPageTokens * kHeadDim) + slot * kHeadDim;
       *reinterpret_cast<uint4*>(v + c) = pack8(f);
     }
+  }
   }
 }
 

@@ -90,13 +90,10 @@ allreduce_norm_kernel(const P2P pp, bf16* __restrict__ x, const bf16* __restrict
     for (int rk = 0; rk < kMaxTp; ++rk) {
       if (rk < pp.tp) {
         const unsigned long long* src = base + (((long long)slot * kMaxTp + rk) * kArRows + r) * (H / 2) + i / 2;
-        uint32_t spins = 0;
+        SpinGuard spins;
         while ((uint32_t)(q[rk][0] >> 32) != epoch || (uint32_t)(q[rk][1] >> 32) != epoch ||
                (uint32_t)(q[rk][2] >> 32) != epoch || (uint32_t)(q[rk][3] >> 32) != epoch) {
-          if (++spins > (1u << 26)) {
-            printf("b200: peer packet timeout (row %d thread %d rank %d epoch %u)\n", r, threadIdx.x, rk, epoch);
-            __trap();
-          }
+          if (spin_give_up(spins, 2)) break;
           ld_ll2(src, q[rk][0], q[rk][1]);
           ld_ll2(src + 2, q[rk][2], q[rk][3]);
         }
@@ -200,13 +197,10 @@ allreduce2_norm_kernel(const P2P pp, bf16* __restrict__ x, const bf16* __restric
     unsigned long long q[4];
     ld_ll2(src, q[0], q[1]);
     ld_ll2(src + 2, q[2], q[3]);
-    uint32_t spins = 0;
+    SpinGuard spins;
     while ((uint32_t)(q[0] >> 32) != epoch || (uint32_t)(q[1] >> 32) != epoch || (uint32_t)(q[2] >> 32) != epoch ||
            (uint32_t)(q[3] >> 32) != epoch) {
-      if (++spins > (1u << 26)) {
-        printf("b200: peer scatter packet timeout (row %d thread %d rank %d epoch %u)\n", r, threadIdx.x, src_rank, epoch);
-        __trap();
-      }
+      if (spin_give_up(spins, 2)) break;
       ld_ll2(src, q[0], q[1]);
       ld_ll2(src + 2, q[2], q[3]);
     }
@@ -242,13 +236,10 @@ allreduce2_norm_kernel(const P2P pp, bf16* __restrict__ x, const bf16* __restric
     unsigned long long q[4];
     ld_ll2(grow + i / 2, q[0], q[1]);
     ld_ll2(grow + i / 2 + 2, q[2], q[3]);
-    uint32_t spins = 0;
+    SpinGuard spins;
     while ((uint32_t)(q[0] >> 32) != epoch || (uint32_t)(q[1] >> 32) != epoch || (uint32_t)(q[2] >> 32) != epoch ||
            (uint32_t)(q[3] >> 32) != epoch) {
-      if (++spins > (1u << 26)) {
-        printf("b200: peer gather packet timeout (row %d thread %d epoch %u)\n", r, threadIdx.x, epoch);
-        __trap();
-      }
+      if (spin_give_up(spins, 2)) break;
       ld_ll2(grow + i / 2, q[0], q[1]);
       ld_ll2(grow + i / 2 + 2, q[2], q[3]);
     }

@@ -72,14 +72,10 @@ __device__ __forceinline__ void st_ll2(void* p, uint32_t d0, uint32_t d1, uint32
 __device__ __forceinline__ void ld_ll2(const void* p, unsigned long long& a, unsigned long long& b) {
   asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
-__device__ __forceinline__ void spin_until(const int* flag, int want) {
-  uint32_t spins = 0;
-  while (ld_sys(flag) != want) {
-    if (++spins > (1u << 28)) {
-      printf("b200: peer flag timeout (block %d thread %d want %d)\n", blockIdx.x, threadIdx.x, want);
-      __trap();
-    }
-  }
+__device__ __forceinline__ void spin_until(const int* flag, int want, int code = 1) {
+  SpinGuard spins;
+  while (ld_sys(flag) != want)
+    if (spin_give_up(spins, code)) return;     // recorded in g_fault_code; the host fails the call
 }
 
 // push this rank's (max, index) candidate of row b to every rank (including itself); called by one thread
@@ -103,7 +99,7 @@ __device__ __forceinline__ void merge_candidates(const P2P& pp, int b, float& be
   tok = 0x7fffffff;
   for (int rk = 0; rk < pp.tp; ++rk) {
     const int off = ((slot * kMaxTp) + rk) * kArRows + b;
-    spin_until(reinterpret_cast<const int*>(pp.peer[pp.rank] + pp.lay.cflag_off) + off, epoch);
+    spin_until(reinterpret_cast<const int*>(pp.peer[pp.rank] + pp.lay.cflag_off) + off, epoch, 3);
     __threadfence_system();
     const float v = ld_sys_f(reinterpret_cast<const float*>(pp.peer[pp.rank] + pp.lay.cval_off) + off);
     const int i = ld_sys(reinterpret_cast<const int*>(pp.peer[pp.rank] + pp.lay.cidx_off) + off);

@@ -279,6 +279,9 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
             try:
                 done(fn(), None)
             except Exception as e:  # delivered to the awaiting coroutine
+                from ._lib import EngineFault
+                if isinstance(e, EngineFault):      # a tensor-parallel peer is gone: stop advertising the model as ready
+                    self.ready = False
                 done(None, e)
 
     async def _submit(self, fn):

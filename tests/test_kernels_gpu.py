@@ -164,7 +164,8 @@ def _rmsnorm_ref(x, w, eps):
     return (w.float() * (xf * torch.rsqrt(var + eps)).to(torch.bfloat16).float())
 
 
-@pytest.mark.parametrize("rows,H", [(1, 512), (33, 1024), (100, 4096)])
+@pytest.mark.parametrize("rows,H", [(1, 512), (33, 1024), (100, 4096),
+                                    (300, 512), (1029, 1024), (4100, 4096), (260, 2048)])   # >= 256 rows: the warp-per-row prefill kernel
 def test_rmsnorm(lib, rows, H):
     x, w = _rand(rows, H, scale=3.0, seed=7), (1 + 0.1 * torch.randn(H)).to(torch.bfloat16).to(DEV)
     xn = torch.empty_like(x)
@@ -286,20 +287,23 @@ def test_attn_decode(lib, nh, nkv, splits):
         _cmp(f"attn_decode b{b} len{l} splits{splits}", out[b:b + 1], ref, 2e-2, 2e-2)
 
 
-def test_rope_kv(lib):
+@pytest.mark.parametrize("T", [70, 4101])      # >= 4096 tokens: four consecutive tokens per CTA
+def test_rope_kv(lib, T):
     from kserve_b200.engine import hf_rope_tables
-    nh, nkv, T = 4, 2, 70
-    cos, sin = hf_rope_tables(500000.0, 128, 256)
+    nh, nkv = 4, 2
+    npages = (T + 3 + 63) // 64 + 1
+    cos, sin = hf_rope_tables(500000.0, 128, npages * 64)
     cosd, sind = cos.to(DEV), sin.to(DEV)
     qkv = _rand(T, (nh + 2 * nkv) * 128, seed=15)
     pos = torch.arange(T, dtype=torch.int32) + 3
     seq = torch.zeros(T, dtype=torch.int32)
-    pt = torch.tensor([[2, 0, 1, 3]], dtype=torch.int32, device=DEV)
-    kc = torch.zeros((4, nkv, 64, 128), dtype=torch.bfloat16, device=DEV)
+    pt = (torch.tensor([[2, 0, 1, 3]], dtype=torch.int32) if T == 70 else
+          torch.randperm(npages, generator=torch.Generator().manual_seed(3)).to(torch.int32)[None]).to(DEV)
+    kc = torch.zeros((npages if T != 70 else 4, nkv, 64, 128), dtype=torch.bfloat16, device=DEV)
     vc = torch.zeros_like(kc)
     qo = torch.zeros((T, nh * 128), dtype=torch.bfloat16, device=DEV)
     seq_d, pos_d = seq.to(DEV), pos.to(DEV)   # keep alive: the kernel reads them after this call returns
-    _check(lib, lib.b200_op_rope_kv(_ptr(qkv), qkv.shape[1], _ptr(qo), nh * 128, _ptr(kc), _ptr(vc), _ptr(pt), 4,
+    _check(lib, lib.b200_op_rope_kv(_ptr(qkv), qkv.shape[1], _ptr(qo), nh * 128, _ptr(kc), _ptr(vc), _ptr(pt), pt.shape[1],
                                     _ptr(seq_d), _ptr(pos_d), _ptr(cosd), _ptr(sind), T, nh, nkv, None), "rope")
     torch.cuda.synchronize()
     # HF apply_rotary_pos_emb in bf16 arithmetic (each op rounds), computed with torch on the same device
@@ -315,11 +319,12 @@ def test_rope_kv(lib):
     q_ref = (qh * c) + (rot(qh) * s)
     k_ref = (kh * c) + (rot(kh) * s)
     assert torch.equal(qo.view(T, nh, 128), q_ref), "rope(q) not bit-identical to the bf16 HF formula"
-    for t in range(T):
+    pt_h = pt.cpu()
+    for t in (range(T) if T == 70 else list(range(0, T, 37)) + [T - 1, T - 2, T - 3]):
         p = int(pos[t])
-        page, slot_ = int(pt[0, p // 64]), p % 64
+        page, slot_ = int(pt_h[0, p // 64]), p % 64
         d = (kc[page, :, slot_].float() - k_ref[t].float()).abs()
-        assert torch.equal(kc[page, :, slot_], k_ref[t]), f"k cache mismatch at token {t}: max diff {float(d.max())} n={int((d>0).sum())} page {page} slot {slot_} got {kc[page, 0, slot_, :4].tolist()} ref {k_ref[t][0, :4].tolist()} nz pages {[int(kc[i].abs().sum()>0) for i in range(4)]}"
+        assert torch.equal(kc[page, :, slot_], k_ref[t]), f"k cache mismatch at token {t}: max diff {float(d.max())} n={int((d>0).sum())} page {page} slot {slot_} got {kc[page, 0, slot_, :4].tolist()} ref {k_ref[t][0, :4].tolist()} "
         assert torch.equal(vc[page, :, slot_], vh[t]), f"v cache mismatch at token {t}"
 
 
