@@ -73,24 +73,25 @@ def algorithmic(cfg, B, S_in, S_out, tp=1):
 
 def ncu_decode_traffic(cfg, B, S_in, S_out, tp):
     """dram__bytes_read.sum + dram__bytes_write.sum of one decode step, assembled from the committed `ncu --set full`
-    capture (profiles/r01_final_ncu_full_summary.json: one launch per decode kernel at B=32, ctx ~1024) times the
-    launches per step.  Only meaningful for the configuration the capture was taken on; None otherwise."""
+    captures (profiles/r02_ncu_full_summary.json: one launch per decode kernel at B=32, ctx ~1024; the LM-head launch from
+    the round-1 capture of the unchanged kernel) times the launches per step.  Only meaningful for the configuration the
+    capture was taken on; None otherwise."""
     if tp != 1 or B != 32 or cfg is not LLAMA3_8B or S_in != 1024:
         return None
     try:
-        rows = json.load(open(os.path.join(ROOT, "profiles", "r01_final_ncu_full_summary.json")))
-
         def gb(e):
             def f(v):
                 x, unit = v.split()
                 return float(x) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[unit]
             return f(e["dram__bytes_read.sum"]) + f(e["dram__bytes_write.sum"])
-        dec = [e for e in rows if e["report"] == "r01f_gemm_decode"]
-        lm_head = next(gb(e) for e in dec if e["kernel"].startswith("gemm_tn_kernel<32, 3>"))
-        gate_up = next(gb(e) for e in dec if e["kernel"].startswith("gemm_tn_kernel<32, 4>"))
-        parts = sorted(gb(e) for e in dec if e["kernel"].startswith("gemm_tn_kernel<32, 5>"))   # o (33 MB) < qkv (50 MB) < down (118 MB)
+        rows = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_full_summary.json")))
+        r01 = json.load(open(os.path.join(ROOT, "profiles", "r01_final_ncu_full_summary.json")))
+        dec = [e for e in rows if e["report"] == "r02_gemm_decode"]
+        lm_head = next(gb(e) for e in r01 if e["report"] == "r01f_gemm_decode" and "gemm_tn_kernel<32, 3>" in e["kernel"])
+        gate_up = next(gb(e) for e in dec if "gemm_tn_kernel<32, 4>" in e["kernel"])
+        parts = sorted(gb(e) for e in dec if "gemm_tn_kernel<32, 5>" in e["kernel"])   # o (34 MB) < qkv (51 MB) < down (118 MB)
         o_proj, qkv, down = parts[0], parts[1], parts[-1]
-        attn = next(gb(e) for e in rows if e["kernel"].startswith("attn_decode_kernel"))
+        attn = next(gb(e) for e in rows if "attn_decode_kernel" in e["kernel"])
         L = cfg["num_hidden_layers"]
         return int(L * (qkv + o_proj + gate_up + down + attn) + lm_head)
     except Exception:
@@ -473,7 +474,7 @@ def run_b200(args):
         "roofline": {"kernel": "decode step: gemm_tn_kernel<swap-AB> weight streaming + attn_decode KV read",
                      "bound": "hbm", "achieved": round(ach_gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": round(ach_gbs / peaks["hbm_gbs"], 4), "traffic": ncu_decode_traffic(cfg, B, S, T, world),
-                     "traffic_src": "ncu --set full per-launch dram bytes x launches per step (profiles/r01_final_ncu_full_summary.json); "
+                     "traffic_src": "ncu --set full per-launch dram bytes x launches per step (profiles/r02_ncu_full_summary.json); "
                                     "null off the captured configuration", "peak_src": peaks["src"],
                      "algorithmic_bytes_per_launch": int(alg["decode_bytes_per_step"])},
         "roofline_prefill": {"kernel": "prefill: gemm_tn_kernel<256> + attn_prefill", "bound": "tensor",

@@ -171,15 +171,20 @@ def test_rmsnorm(lib, rows, H):
     xn = torch.empty_like(x)
     _check(lib, lib.b200_op_rmsnorm(_ptr(x), _ptr(w), _ptr(xn), rows, H, 1e-5, None, 0, None, None), "rmsnorm")
     torch.cuda.synchronize()
-    # same rounding points as LlamaRMSNorm: only the fp32 reduction order differs -> at most 1 bf16 ulp
-    _cmp("rmsnorm", xn, _rmsnorm_ref(x, w, 1e-5), 1e-3, RTOL)
+    # same rounding points as LlamaRMSNorm: only the fp32 reduction order differs.  A last-bit difference of the row scale
+    # flips bf16(x * rs) by one ulp for ~3e-5 of the elements; with the final rounding of the product that is up to 1.5 ulp
+    # on those, so: everything within 2 ulp, and all but 1e-4 of the elements within the 1-ulp bound
+    ref = _rmsnorm_ref(x, w, 1e-5)
+    _cmp("rmsnorm", xn, ref, 1e-3, 2 * RTOL)
+    tight = (xn.float() - ref).abs() <= 1e-3 + RTOL * ref.abs()
+    assert float(tight.float().mean()) >= 0.9999
     y = _rand(rows, H, seed=8)
     x2 = x.clone()
     _check(lib, lib.b200_op_rmsnorm(_ptr(x2), _ptr(w), _ptr(xn), rows, H, 1e-5, None, 0, _ptr(y), None), "rmsnorm")
     torch.cuda.synchronize()
     xr = (x.float() + y.float()).to(torch.bfloat16)
     assert torch.equal(x2, xr)
-    _cmp("rmsnorm(mode2)", xn, _rmsnorm_ref(xr, w, 1e-5), 1e-3, RTOL)
+    _cmp("rmsnorm(mode2)", xn, _rmsnorm_ref(xr, w, 1e-5), 1e-3, 2 * RTOL)
 
 
 def _build_cache(B, lens, nkv, seed):
