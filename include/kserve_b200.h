@@ -223,8 +223,9 @@ int b200_kv_swap_in(b200_engine_t* e, int32_t slot);
  *   b200_cb_poll    per slot: tokens generated so far, finished flag, stop-sequence flag ([max_batch] each)
  *   b200_cb_read    generated tokens [first, first + cap) of a slot (for streaming reads as well as final results)
  *   b200_cb_release free the slot and drop its page references (its row leaves the decode batch at the next step)
- *   b200_cb_stats   out8 = {prompt tokens admitted, of those served from shared pages, prefilled tokens, cache evictions,
- *                   prefill passes, pages an admit could obtain now, cached blocks, prompts still being prefilled}
+ *   b200_cb_stats   out10 = {prompt tokens admitted, of those served from shared pages, prefilled tokens, cache evictions,
+ *                   prefill passes, pages an admit could obtain now, cached blocks, prompts still being prefilled,
+ *                   sequences swapped out to host DRAM, swapped back in}
  *   b200_cb_end     leave the mode
  * Greedy results per sequence are identical to b200_generate on that prompt alone. */
 int b200_cb_begin(b200_engine_t* e, int64_t pad_token_id, const int64_t* eos_token_ids, int32_t num_eos);
@@ -236,8 +237,15 @@ int b200_cb_step(b200_engine_t* e, int32_t n_steps);
 int b200_cb_poll(b200_engine_t* e, int32_t* n_gen, int32_t* finished, int32_t* stop_hit);
 int b200_cb_read(b200_engine_t* e, int32_t slot, int32_t first, int64_t* out, int32_t cap, int32_t* n_out);
 int b200_cb_release(b200_engine_t* e, int32_t slot);
-int b200_cb_stats(b200_engine_t* e, int64_t* out8);
+int b200_cb_stats(b200_engine_t* e, int64_t* out10);
 int b200_cb_end(b200_engine_t* e);
+/* Host-DRAM KV tier (BASELINE.json configs[3]) for the continuous batcher: preempt a RUNNING sequence to pinned host memory
+ * (all of its KV pages, asynchronously on the engine stream; its pages return to the pool, it leaves the decode batch, its
+ * per-sequence state stays on the device) and bring it back later (fresh pages; rc -7 while the pool cannot supply them).
+ * Decoding resumes bit-identically.  The policy is the scheduler's: kserve_b200/continuous.py preempts the most recently
+ * admitted request when an admission finds the pool exhausted and resumes swapped requests before admitting new ones. */
+int b200_cb_swap_out(b200_engine_t* e, int32_t slot);
+int b200_cb_swap_in(b200_engine_t* e, int32_t slot);
 
 /* Debug timeline: capacity > 0 enables per-CTA {t0, t1 (globaltimer ns), kind, block} records (24 bytes each),
  * 0 disables; read drains up to `capacity` records into `out`. */

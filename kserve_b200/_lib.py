@@ -90,6 +90,8 @@ def load() -> C.CDLL:
     lib.b200_cb_admit.argtypes = [vp, i32, C.POINTER(C.POINTER(C.c_int64)), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
                                   C.POINTER(i32), C.POINTER(C.c_int64), C.POINTER(GenParams), C.POINTER(i32)]
     lib.b200_cb_config.argtypes = [vp, i32, i32]
+    lib.b200_cb_swap_out.argtypes = [vp, i32]
+    lib.b200_cb_swap_in.argtypes = [vp, i32]
     lib.b200_cb_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.b200_cb_step.argtypes = [vp, i32]
     lib.b200_cb_poll.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]

@@ -65,16 +65,20 @@ class _Request:
     t_submit: float = field(default_factory=time.perf_counter)
     t_first: float = 0.0
     ttft_recorded: bool = False
+    swapped: bool = False                    # preempted to the host-DRAM KV tier
     cancelled: bool = False                  # set from the event loop when the awaiting task went away (client disconnect)
 
 
 class ContinuousBatcher:
     def __init__(self, engine: B200Engine, pad_token_id: int = 0, eos_token_ids: Sequence[int] = (),
                  steps_per_poll: int = 4, max_prefill_tokens: Optional[int] = None, prefill_chunk_tokens: int = 0,
-                 prefix_cache: bool = False):
+                 prefix_cache: bool = False, kv_offload: bool = True):
         """prefill_chunk_tokens > 0: admitted prompts are prefilled in chunks of that many packed tokens, one chunk pass
         before every decode step, so a long admit never stalls the running sequences (0: whole prompts at admit).
-        prefix_cache: 128-token blocks of earlier prompts stay in the KV pool and are shared by later requests."""
+        prefix_cache: 128-token blocks of earlier prompts stay in the KV pool and are shared by later requests.
+        kv_offload: when an admission finds the KV page pool exhausted, the most recently admitted running request is
+        preempted to pinned host memory (host-DRAM KV tier) instead of making the new request wait; preempted requests
+        are resumed, oldest first, as soon as pages are free again."""
         self.engine = ReplicatedEngine(engine) if getattr(engine, "tp_size", 1) > 1 else engine
         self.prefill_chunk_tokens, self.prefix_cache = int(prefill_chunk_tokens), bool(prefix_cache)
         self.pad = int(pad_token_id or 0)
@@ -83,11 +87,14 @@ class ContinuousBatcher:
         self.max_prefill_tokens = max_prefill_tokens
         self._pending: Deque[_Request] = deque()
         self._running: List[_Request] = []
+        self._swapped: Deque[_Request] = deque()     # preempted to host DRAM, resumed oldest first
+        self.kv_offload = bool(kv_offload)
         self._cv = threading.Condition()
         self._stop = False
         self._thread: Optional[threading.Thread] = None
         self.free_slots = engine.max_batch
         self.ttft_samples: Deque[float] = deque(maxlen=100000)   # submit -> first token, seconds (load tests / metrics)
+        self._pool_blocked_resume = False
         self._pool_blocked = False      # the last admit hit "KV page pool exhausted": retry only after a release
         self.fatal: Optional[BaseException] = None      # set when the scheduler thread died: submit raises it from then on
         self.on_fatal: Optional[Callable[[BaseException], None]] = None   # the model flips `ready` to False here
@@ -198,7 +205,11 @@ class ContinuousBatcher:
                             self._pending.appendleft(r)
                     batch = batch[:1]
                     continue
-                if self._running:            # wait for a release
+                if self._running:
+                    # host-DRAM KV tier: preempt the most recently admitted running request (its KV pages go to pinned
+                    # host memory and back to the pool) and retry; with nothing left to preempt, wait for a release
+                    if self.kv_offload and self._preempt_one():
+                        continue
                     with self._cv:
                         self._pending.appendleft(batch[0])
                     self._pool_blocked = True
@@ -221,6 +232,39 @@ class ContinuousBatcher:
         self.stats["admitted"] += len(batch)
         self.stats["prefill_calls"] += 1
 
+    def _preempt_one(self) -> bool:
+        """swap the youngest fully-prefilled running request out to host DRAM; False when there is none"""
+        n_gen, fin, _ = self.engine.cb_poll()
+        for r in reversed(self._running):
+            if r.swapped or r.cancelled or any(n_gen[s] < 1 or fin[s] for s in r.slots):
+                continue
+            for sl in r.slots:
+                self.engine.cb_swap_out(sl)
+            r.swapped = True
+            self._running.remove(r)
+            self._swapped.append(r)
+            self.stats["preempted"] = self.stats.get("preempted", 0) + 1
+            return True
+        return False
+
+    def _resume_swapped(self) -> None:
+        """bring preempted requests back (oldest first) while the pool has room"""
+        while self._swapped:
+            r = self._swapped[0]
+            done = []
+            try:
+                for sl in r.slots:
+                    self.engine.cb_swap_in(sl)
+                    done.append(sl)
+            except PoolExhausted:
+                for sl in done:                      # multi-row request only partly back: park it again, try later
+                    self.engine.cb_swap_out(sl)
+                return
+            r.swapped = False
+            self._swapped.popleft()
+            self._running.append(r)
+            self.stats["resumed"] = self.stats.get("resumed", 0) + 1
+
     def _finish(self, r: _Request, n_out: int, stop: bool) -> None:
         B, S = r.padded.shape
         out = torch.full((B, S + n_out), r.pad, dtype=torch.int64)
@@ -230,7 +274,7 @@ class ContinuousBatcher:
             out[b, S:S + len(toks)] = torch.tensor(toks, dtype=torch.int64)
             self.engine.cb_release(sl)
         self.free_slots += len(r.slots)
-        self._pool_blocked = False
+        self._pool_blocked = self._pool_blocked_resume = False
         self.stats["finished"] += 1
         res = GenerateResult(output_ids=out, stop_triggered=stop, num_generated=n_out, logits=None,
                              prefill_ms=((r.t_first or time.perf_counter()) - r.t_submit) * 1e3, decode_ms=(time.perf_counter() - (r.t_first or r.t_submit)) * 1e3,
@@ -286,11 +330,15 @@ class ContinuousBatcher:
         try:
             while True:
                 with self._cv:
-                    while not self._stop and not self._pending and not self._running:
+                    while not self._stop and not self._pending and not self._running and not self._swapped:
                         self._cv.wait()
                     if self._stop:
                         break
-                if self._pending and self.free_slots > 0 and not self._pool_blocked:
+                if self._swapped and not self._pool_blocked_resume:
+                    before = len(self._swapped)
+                    self._resume_swapped()
+                    self._pool_blocked_resume = len(self._swapped) == before and bool(self._running)
+                if self._pending and self.free_slots > 0 and not self._pool_blocked and not self._swapped:
                     self._admit()
                 if self._running:
                     rows = sum(len(r.slots) for r in self._running)
@@ -309,9 +357,10 @@ class ContinuousBatcher:
         finally:
             # both exits (stop() and a failure) resolve every request still known to the scheduler
             with self._cv:
-                waiting = list(self._pending) + self._running
+                waiting = list(self._pending) + self._running + list(self._swapped)
                 self._pending.clear()
                 self._running = []
+                self._swapped.clear()
                 err = self.fatal or RuntimeError("continuous batcher stopped")
             for r in waiting:
                 try:

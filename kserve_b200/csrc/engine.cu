@@ -209,6 +209,8 @@ struct b200_engine {
   int cb_chunk_tokens = 0;               // 0: a prompt is prefilled completely inside b200_cb_admit
   bool cb_prefix_on = false;
   long long cb_stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // prompt tokens admitted / served from shared pages / prefilled, evictions, prefill passes
+  std::vector<char> cb_swapped;          // slot's KV pages live in host DRAM (b200_cb_swap_out)
+  std::vector<int> cb_swap_pages;        // number of pages parked per swapped slot
   SampleCfg* d_cb_cfg = nullptr;         // [max_batch] per-slot logits-processor / sampling configuration
   std::vector<char> cb_slot_sampling;    // slot uses the processed-score path
   int cb_sampling_slots = 0;
@@ -1866,6 +1868,8 @@ int b200_cb_begin(b200_engine_t* e, int64_t pad_token_id, const int64_t* eos_tok
   e->cb_pending.clear();
   e->cb_slot_pages.assign(e->cfg.max_batch, {});
   e->cb_slot_sampling.assign(e->cfg.max_batch, 0);
+  e->cb_swapped.assign(e->cfg.max_batch, 0);
+  e->cb_swap_pages.assign(e->cfg.max_batch, 0);
   e->cb_sampling_slots = 0;
   for (auto& v : e->cb_stat) v = 0;
   e->cb_used.assign(e->cfg.max_batch, 0);
@@ -1883,7 +1887,7 @@ int b200_cb_config(b200_engine_t* e, int32_t prefill_chunk_tokens, int32_t prefi
   return 0;
 }
 
-int b200_cb_stats(b200_engine_t* e, int64_t* out8) {
+int b200_cb_stats(b200_engine_t* e, int64_t* out8) {   // (10 entries)
   B200_REQUIRE(e && out8, "null argument");
   int64_t evictable = 0;
   for (auto& kv : e->cb_prefix)
@@ -1892,6 +1896,7 @@ int b200_cb_stats(b200_engine_t* e, int64_t* out8) {
   out8[5] = (int64_t)e->cb_free_pages.size() + evictable;     // pages an admit could obtain right now
   out8[6] = (int64_t)e->cb_prefix.size();
   out8[7] = (int64_t)e->cb_pending.size();
+  out8[8] = e->cb_stat[5]; out8[9] = e->cb_stat[6];      // sequences swapped out to / back in from host DRAM
   return 0;
 }
 
@@ -1961,6 +1966,83 @@ int b200_cb_read(b200_engine_t* e, int32_t slot, int32_t first, int64_t* out, in
   return 0;
 }
 
+// ---- host-DRAM KV tier of the continuous batcher (BASELINE.json configs[3]: "paged-KV with host-DRAM KV-offload tier") ----
+// A running sequence is PREEMPTED to host memory when the page pool cannot serve a new admission: all of its KV pages (every
+// layer, K and V) are copied to a pinned buffer on the engine stream, its pages go back to the pool (shared prefix pages
+// merely lose a reference), and it leaves the decode batch; its per-sequence device state (length, generated tokens, next
+// token, stop sequences) stays where it is.  swap-in takes fresh pages, copies the KV back and the sequence resumes with
+// bit-identical results.  Policy (who, when) lives in the scheduler: kserve_b200/continuous.py preempts the most recently
+// admitted request and resumes swapped requests before admitting new ones.
+static int cb_swap(b200_engine_t* e, int32_t slot, bool out) {
+  B200_REQUIRE(e && e->cb_on, "not in continuous-batching mode");
+  B200_REQUIRE(slot >= 0 && slot < e->cfg.max_batch && e->cb_used[slot], "slot is not in use");
+  B200_CUDA_OK(cudaSetDevice(e->cfg.device));
+  const size_t page_elems = (size_t)e->nkv * kPageTokens * kHeadDim;      // per layer, per K or V
+  const size_t page_bytes = page_elems * sizeof(bf16);
+  cudaStream_t s = e->stream;
+  if (out) {
+    B200_REQUIRE(!e->cb_swapped[slot], "sequence is already swapped out");
+    auto it = std::find(e->cb_active.begin(), e->cb_active.end(), (int)slot);
+    B200_REQUIRE(it != e->cb_active.end(), "only a running sequence (prompt fully prefilled) can be swapped out");
+    std::vector<int>& pages = e->cb_slot_pages[slot];
+    const size_t bytes = pages.size() * page_bytes * 2 * e->L;
+    if (!e->host_kv.count(slot) || e->host_kv_bytes[slot] < bytes) {
+      if (e->host_kv.count(slot)) cudaFreeHost(e->host_kv[slot]);
+      bf16* h = nullptr;
+      B200_CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&h), bytes));
+      e->host_kv[slot] = h; e->host_kv_bytes[slot] = bytes;
+    }
+    unsigned char* h = reinterpret_cast<unsigned char*>(e->host_kv[slot]);
+    for (size_t i = 0; i < pages.size(); ++i) {     // one strided copy per page and cache: [L] rows of page_bytes
+      unsigned char* hk = h + (i * 2) * page_bytes * e->L;
+      B200_CUDA_OK(cudaMemcpy2DAsync(hk, page_bytes, e->kcache + (size_t)pages[i] * page_elems, (size_t)e->layer_stride * sizeof(bf16),
+                                     page_bytes, e->L, cudaMemcpyDeviceToHost, s));
+      B200_CUDA_OK(cudaMemcpy2DAsync(hk + page_bytes * e->L, page_bytes, e->vcache + (size_t)pages[i] * page_elems,
+                                     (size_t)e->layer_stride * sizeof(bf16), page_bytes, e->L, cudaMemcpyDeviceToHost, s));
+    }
+    e->cb_swap_pages[slot] = (int)pages.size();
+    for (int pg : pages) cb_unref_page(e, pg);       // reuse is stream-ordered after the copies above
+    pages.clear();
+    e->cb_active.erase(it);
+    e->cb_rows_dirty = true;
+    e->cb_swapped[slot] = 1;
+    e->cb_stat[5]++;
+    return 0;
+  }
+  B200_REQUIRE(e->cb_swapped[slot], "sequence is not swapped out");
+  const int n = e->cb_swap_pages[slot];
+  std::vector<int> got;
+  for (int i = 0; i < n; ++i) {
+    const int pg = cb_take_page(e);
+    if (pg < 0) {
+      for (int q : got) cb_unref_page(e, q);
+      set_last_error("KV page pool exhausted: cannot swap the sequence back in yet");
+      return -7;
+    }
+    got.push_back(pg);
+  }
+  const unsigned char* h = reinterpret_cast<const unsigned char*>(e->host_kv[slot]);
+  for (int i = 0; i < n; ++i) {
+    const unsigned char* hk = h + ((size_t)i * 2) * page_bytes * e->L;
+    B200_CUDA_OK(cudaMemcpy2DAsync(e->kcache + (size_t)got[i] * page_elems, (size_t)e->layer_stride * sizeof(bf16), hk, page_bytes,
+                                   page_bytes, e->L, cudaMemcpyHostToDevice, s));
+    B200_CUDA_OK(cudaMemcpy2DAsync(e->vcache + (size_t)got[i] * page_elems, (size_t)e->layer_stride * sizeof(bf16), hk + page_bytes * e->L,
+                                   page_bytes, page_bytes, e->L, cudaMemcpyHostToDevice, s));
+  }
+  e->cb_slot_pages[slot] = got;
+  int32_t* row = e->h_page_table.data() + (size_t)slot * e->max_pages;
+  for (int k = 0; k < e->max_pages; ++k) row[k] = k < n ? got[k] : got.back();
+  B200_CUDA_OK(cudaMemcpyAsync(e->d_page_table + (size_t)slot * e->max_pages, row, (size_t)e->max_pages * 4, cudaMemcpyHostToDevice, s));
+  B200_CUDA_OK(cudaStreamSynchronize(s));            // the page-table row is pageable host memory
+  e->cb_swapped[slot] = 0;
+  e->cb_active.push_back(slot);
+  e->cb_rows_dirty = true;
+  e->cb_stat[6]++;
+  return 0;
+}
+int b200_cb_swap_out(b200_engine_t* e, int32_t slot) { return cb_swap(e, slot, true); }
+int b200_cb_swap_in(b200_engine_t* e, int32_t slot) { return cb_swap(e, slot, false); }
+
 int b200_cb_release(b200_engine_t* e, int32_t slot) {
   B200_REQUIRE(e && e->cb_on, "not in continuous-batching mode");
   B200_REQUIRE(slot >= 0 && slot < e->cfg.max_batch && e->cb_used[slot], "slot is not in use");
@@ -1971,6 +2053,7 @@ int b200_cb_release(b200_engine_t* e, int32_t slot) {
     if (pd->slot == slot) { e->cb_pending.erase(pd); break; }      // cancelled before its prompt was in the cache
   for (int pg : e->cb_slot_pages[slot]) cb_unref_page(e, pg);       // shared prefix pages stay alive through the cache's reference
   e->cb_slot_pages[slot].clear();
+  e->cb_swapped[slot] = 0;
   if (e->cb_slot_sampling[slot]) { e->cb_slot_sampling[slot] = 0; e->cb_sampling_slots--; }
   return 0;
 }

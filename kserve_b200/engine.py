@@ -268,10 +268,10 @@ class B200Engine:
         _lib.check(self.lib.b200_cb_config(self.h, int(prefill_chunk_tokens), 1 if prefix_cache else 0), "b200_cb_config")
 
     def cb_stats(self) -> dict:
-        out = (C.c_int64 * 8)()
+        out = (C.c_int64 * 10)()
         _lib.check(self.lib.b200_cb_stats(self.h, out), "b200_cb_stats")
         keys = ("prompt_tokens", "prefix_hit_tokens", "prefilled_tokens", "evictions", "prefill_passes", "available_pages",
-                "cached_blocks", "pending_prompts")
+                "cached_blocks", "pending_prompts", "swap_outs", "swap_ins")
         return dict(zip(keys, [int(v) for v in out]))
 
     def cb_admit(self, prompts: Sequence[Sequence[int]], max_new_tokens: Sequence[int],
@@ -312,6 +312,17 @@ class B200Engine:
             raise PoolExhausted(self.lib.b200_last_error().decode("utf-8", "replace"))
         _lib.check(rc, "b200_cb_admit")
         return list(slots)
+
+    def cb_swap_out(self, slot: int) -> None:
+        """preempt a running sequence: its KV pages go to pinned host memory and back to the pool (host-DRAM KV tier)"""
+        _lib.check(self.lib.b200_cb_swap_out(self.h, int(slot)), "b200_cb_swap_out")
+
+    def cb_swap_in(self, slot: int) -> None:
+        """resume a swapped-out sequence (raises PoolExhausted while the pool cannot supply its pages)"""
+        rc = self.lib.b200_cb_swap_in(self.h, int(slot))
+        if rc == -7:
+            raise PoolExhausted(self.lib.b200_last_error().decode("utf-8", "replace"))
+        _lib.check(rc, "b200_cb_swap_in")
 
     def cb_step(self, n_steps: int = 1) -> None:
         _lib.check(self.lib.b200_cb_step(self.h, n_steps), "b200_cb_step")

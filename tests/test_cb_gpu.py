@@ -321,3 +321,59 @@ def test_per_sequence_logits_processors_in_the_running_batch():
         e.cb_end()
     finally:
         e.close()
+
+
+def test_host_dram_kv_tier_preempt_and_resume_bit_identical(peaked):
+    """BASELINE configs[3] "paged-KV with host-DRAM KV-offload tier" in the continuous batcher: a running sequence is
+    swapped out to pinned host memory (its pages go back to the pool and are overwritten by other sequences), swapped back
+    in on fresh pages, and continues with exactly the ids of an uninterrupted run."""
+    e, c, prompts, ref = peaked
+    rows = [r.tolist() for r in prompts]
+    short = [r.tolist() for r in c["input_ids"]]
+    e.cb_begin(0, [])
+    try:
+        a = e.cb_admit([rows[0]], [12])[0]
+        e.cb_step(3)                                           # 4 tokens generated
+        free0 = e.cb_stats()["available_pages"]
+        e.cb_swap_out(a)
+        st = e.cb_stats()
+        assert st["swap_outs"] == 1 and st["available_pages"] == free0 + 5      # 300 + 12 tokens -> 5 pages back in the pool
+        others = e.cb_admit(short[:3], [16, 16, 16])            # reuse (and overwrite) the freed pages
+        e.cb_step(6)
+        assert e.cb_poll()[0][a] == 4                           # the swapped sequence does not advance
+        e.cb_swap_in(a)
+        assert e.cb_stats()["swap_ins"] == 1
+        _run_until_done(e, [a] + others)
+        assert e.cb_read(a, 0, 12) == ref[0].tolist()
+        for i, s in enumerate(others):
+            assert e.cb_read(s, 0, 16) == c["gen"][i].tolist()
+    finally:
+        e.cb_end()
+
+
+def test_scheduler_preempts_to_host_when_the_pool_is_exhausted():
+    from kserve_b200.continuous import ContinuousBatcher
+    c = load_case("tiny_g2_peaked")
+    m = c["meta"]
+    e = make_engine(m["cfg"], m["seed"], vocab_rows=m["vocab_rows"], max_batch=8, max_seq_len=512, num_kv_pages=10)
+    try:
+        ids = c["input_ids"]
+        prompts = [r.tolist() for r in ids]
+        cb = ContinuousBatcher(e, pad_token_id=0, eos_token_ids=[], steps_per_poll=2, kv_offload=True)
+        cb.start()
+
+        async def main():          # each request needs 4 pages (48 + 200 tokens): the third admission exhausts the 10-page pool
+            t = [asyncio.create_task(cb.submit([prompts[i]], ids[i:i + 1], 200)) for i in range(2)]
+            await asyncio.sleep(0.2)
+            t.append(asyncio.create_task(cb.submit([prompts[2]], ids[2:3], 200)))
+            return await asyncio.gather(*t)
+        try:
+            rs = asyncio.run(main())
+        finally:
+            cb.stop()
+        for i, r in enumerate(rs):
+            assert r.num_generated == 200
+            assert r.output_ids[0, ids.shape[1]:ids.shape[1] + c["T"]].tolist() == c["gen"][i].tolist()
+        assert cb.stats.get("preempted", 0) >= 1 and cb.stats.get("resumed", 0) == cb.stats["preempted"]
+    finally:
+        e.close()

@@ -66,6 +66,8 @@ class ScriptedEngine:
             time.sleep(self.step_delay * n)
         for _ in range(n):
             for st in self.slots.values():
+                if st.get("swapped"):
+                    continue                  # its KV is in host DRAM: not part of the decode batch
                 if st["wait"] > 0:
                     st["wait"] -= 1           # still being prefilled (one chunk per step)
                     if st["wait"] > 0:
@@ -84,6 +86,20 @@ class ScriptedEngine:
 
     def cb_release(self, slot):
         del self.slots[slot]
+
+    def cb_swap_out(self, slot):
+        st = self.slots[slot]
+        assert not st.get("swapped")
+        st["swapped"], st["host_pages"], st["pages"] = True, st["pages"], 0
+        self.calls.append(("swap_out", slot))
+
+    def cb_swap_in(self, slot):
+        from kserve_b200.engine import PoolExhausted
+        st = self.slots[slot]
+        if self.pages is not None and sum(x["pages"] for x in self.slots.values()) + st["host_pages"] > self.pages:
+            raise PoolExhausted("KV page pool exhausted")
+        st["swapped"], st["pages"] = False, st["host_pages"]
+        self.calls.append(("swap_in", slot))
 
 
 def _run(cb, coro):
@@ -242,7 +258,7 @@ def test_pool_exhaustion_defers_admission_until_a_release():
     retries after the next release instead of failing it; a request that can never fit an idle pool is failed."""
     scripts = {(1,) * 6: list(range(10, 20)), (2,) * 6: list(range(20, 30)), (3,) * 50: list(range(30, 40))}
     eng = ScriptedEngine(4, scripts, pages=10)       # two 6-token prompts do not fit together
-    cb = ContinuousBatcher(eng, steps_per_poll=1)
+    cb = ContinuousBatcher(eng, steps_per_poll=1, kv_offload=False)
 
     async def main():
         pad = lambda p: torch.tensor([p])
@@ -292,3 +308,27 @@ def test_replicated_engine_broadcasts_every_scheduler_call(monkeypatch):
     assert names[-1] == "cb_end"
     admit = next(a for m, a, _ in sent if m == "cb_admit")
     assert admit[0] == [[1, 2]] and admit[1] == [3]
+
+
+def test_kv_offload_preempts_the_youngest_and_resumes_it():
+    """host-DRAM KV tier policy: an admission that finds the pool exhausted preempts the most recently admitted running
+    request (swap-out), the new request runs, and the preempted one is swapped back in and finishes with its full output."""
+    scripts = {(1,) * 6: list(range(1000, 1300)), (2,) * 6: list(range(2000, 2300)), (3,) * 6: list(range(70, 100))}
+    eng = ScriptedEngine(4, scripts, pages=12, step_delay=0.002)      # room for two 6-token prompts, not three
+    cb = ContinuousBatcher(eng, steps_per_poll=1, kv_offload=True)
+
+    async def main():
+        pad = lambda p: torch.tensor([p])
+        a = asyncio.create_task(cb.submit([[1] * 6], pad([1] * 6), 150))
+        await asyncio.sleep(0.02)
+        b = asyncio.create_task(cb.submit([[2] * 6], pad([2] * 6), 150))
+        await asyncio.sleep(0.02)
+        c = asyncio.create_task(cb.submit([[3] * 6], pad([3] * 6), 8))          # arrives while both are running
+        return await asyncio.gather(a, b, c)
+    ra, rb, rc = _run(cb, main())
+    assert ra.output_ids[0, 6:].tolist() == list(range(1000, 1150))
+    assert rb.output_ids[0, 6:].tolist() == list(range(2000, 2150))      # preempted in the middle, complete in the end
+    assert rc.output_ids[0, 6:].tolist() == list(range(70, 78))
+    kinds = [c[0] for c in eng.calls]
+    assert "swap_out" in kinds and "swap_in" in kinds and kinds.index("swap_out") < kinds.index("swap_in")
+    assert cb.stats["preempted"] >= 1 and cb.stats["resumed"] == cb.stats["preempted"]
