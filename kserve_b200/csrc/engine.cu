@@ -1871,6 +1871,7 @@ int b200_cb_begin(b200_engine_t* e, int64_t pad_token_id, const int64_t* eos_tok
   e->cb_swapped.assign(e->cfg.max_batch, 0);
   e->cb_swap_pages.assign(e->cfg.max_batch, 0);
   e->cb_sampling_slots = 0;
+  e->cb_chunk_tokens = 0; e->cb_prefix_on = false;     // b200_cb_config applies to one begin .. end span
   for (auto& v : e->cb_stat) v = 0;
   e->cb_used.assign(e->cfg.max_batch, 0);
   e->cb_active.clear();

@@ -355,24 +355,21 @@ def test_scheduler_preempts_to_host_when_the_pool_is_exhausted():
     from kserve_b200.continuous import ContinuousBatcher
     c = load_case("tiny_g2_peaked")
     m = c["meta"]
-    e = make_engine(m["cfg"], m["seed"], vocab_rows=m["vocab_rows"], max_batch=8, max_seq_len=512, num_kv_pages=10)
+    e = make_engine(m["cfg"], m["seed"], vocab_rows=m["vocab_rows"], max_batch=8, max_seq_len=512, num_kv_pages=16)
     try:
         ids = c["input_ids"]
         prompts = [r.tolist() for r in ids]
         cb = ContinuousBatcher(e, pad_token_id=0, eos_token_ids=[], steps_per_poll=2, kv_offload=True)
         cb.start()
 
-        async def main():          # each request needs 4 pages (48 + 200 tokens): the third admission exhausts the 10-page pool
-            t = [asyncio.create_task(cb.submit([prompts[i]], ids[i:i + 1], 200)) for i in range(2)]
-            await asyncio.sleep(0.2)
-            t.append(asyncio.create_task(cb.submit([prompts[2]], ids[2:3], 200)))
-            return await asyncio.gather(*t)
+        async def main():          # each request needs 7 pages (48 + 400 tokens): the third admission exhausts the 16-page pool
+            return await asyncio.gather(*[cb.submit([prompts[i]], ids[i:i + 1], 400) for i in range(3)])
         try:
             rs = asyncio.run(main())
         finally:
             cb.stop()
         for i, r in enumerate(rs):
-            assert r.num_generated == 200
+            assert r.num_generated == 400
             assert r.output_ids[0, ids.shape[1]:ids.shape[1] + c["T"]].tolist() == c["gen"][i].tolist()
         assert cb.stats.get("preempted", 0) >= 1 and cb.stats.get("resumed", 0) == cb.stats["preempted"]
     finally:
