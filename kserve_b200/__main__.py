@@ -23,7 +23,7 @@ def main(argv=None):
     parser.add_argument("--max_batch", type=int, default=32)
     parser.add_argument("--continuous_batching", action="store_true",
                         help="iteration-level batching: requests join / leave the running decode batch between steps")
-    parser.add_argument("--prefill_chunk_tokens", type=int, default=2048,
+    parser.add_argument("--prefill_chunk_tokens", type=int, default=8192,
                         help="with --continuous_batching: prompts are prefilled in chunks of this many tokens between decode steps (0 = whole prompts at admit)")
     parser.add_argument("--enable_prefix_caching", action="store_true",
                         help="with --continuous_batching: share the KV pages of common 128-token prompt prefixes between requests")

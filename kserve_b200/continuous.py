@@ -172,6 +172,14 @@ class ContinuousBatcher:
         batch: List[_Request] = []
         budget = self.max_prefill_tokens
         free = self.free_slots
+        # KV pages the pool can hand out right now: only as many requests as fit are offered to the engine (the head of
+        # the queue always is — the engine may still evict cached blocks, and the scheduler may preempt, for it)
+        pages_left = None
+        if hasattr(self.engine, "cb_stats"):
+            try:
+                pages_left = int(self.engine.cb_stats()["available_pages"])
+            except Exception:
+                pages_left = None
         with self._cv:
             while self._pending:
                 r = self._pending[0]
@@ -183,6 +191,11 @@ class ContinuousBatcher:
                 toks = sum(len(p) for p in r.prompts)
                 if need > free or (budget is not None and batch and toks > budget):
                     break
+                if pages_left is not None:
+                    pg = sum(-(-(len(p) + r.max_new) // 64) for p in r.prompts)
+                    if batch and pg > pages_left:
+                        break
+                    pages_left -= pg
                 self._pending.popleft()
                 batch.append(r)
                 free -= need

@@ -204,10 +204,9 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
                 cap_t, pages = None, self.max_batch * -(-self.max_length // 64)
         except ValueError as e:
             raise OpenAIError(str(e))
-        if self.continuous_batching and pages < self.max_batch * -(-self.max_length // 64):
-            # slots own fixed page ranges in continuous-batching mode: run fewer slots rather than fail at cb_begin
-            self.max_batch = max(1, pages // -(-self.max_length // 64))
-            logger.warning("KV page pool (%d pages) holds %d full-length sequences: max_batch reduced to that", pages, self.max_batch)
+        if getattr(self, "kv_pages_limit", None):       # tests / load experiments: a deliberately small KV page pool
+            pages = min(pages, int(self.kv_pages_limit))
+        # (continuous batching draws pages from the pool per request; an exhausted pool defers or preempts, it never fails load)
         self.max_prefill_tokens = cap_t
         self._engine = B200Engine(cfg, max_batch=self.max_batch, max_seq_len=self.max_length, device=self.device_index,
                                   max_prefill_tokens=cap_t, num_kv_pages=pages,

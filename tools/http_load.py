@@ -33,13 +33,15 @@ def main():
     max_new = int(os.environ.get("MAX_TOKENS", "128"))
     mode = os.environ.get("MODE", "continuous")
     slots = int(os.environ.get("SLOTS", "512" if mode == "continuous" else "64"))
-    chunk = int(os.environ.get("CHUNK", "2048"))
+    chunk = int(os.environ.get("CHUNK", "8192"))
     port = int(os.environ.get("PORT", "18080"))
     cfg = dict(LLAMA3_8B, architectures=["LlamaForCausalLM"], model_type="llama")
     model = B200GenerativeModel("llama", model_config=cfg, state_dict=gpu_weights(LLAMA3_8B, torch.device("cuda")), tokenizer=None,
                                 pad_token_id=cfg["vocab_size"] - 1, max_model_len=1024 + max_new, max_batch=slots,
                                 continuous_batching=(mode == "continuous"))
     model.prefill_chunk_tokens = chunk
+    if os.environ.get("KV_PAGES"):      # over-subscribe the pool: admissions preempt running requests to the host-DRAM KV tier
+        model.kv_pages_limit = int(os.environ["KV_PAGES"])
     model.load()
     server = ModelServer(http_port=port, batcher=(64, 50) if mode == "batcher" else None)
     app = server.create_application([model])
@@ -104,7 +106,7 @@ def main():
         ttft = list(model._cb.ttft_samples)
     q = lambda xs, p: round(sorted(xs)[min(len(xs) - 1, int(p * len(xs)))], 3) if xs else None
     res = dict(config=f"HTTP, mode={mode}, {clients} closed-loop clients, 1 prompt U[512,1024] token ids, "
-                      f"{max_new if mode == 'continuous' else 16} new tokens, slots={slots}" + (f", prefill chunks {chunk}" if mode == "continuous" else ", maxBatchSize 64 / maxLatency 50 ms"),
+                      f"{max_new if mode == 'continuous' else 16} new tokens, slots={slots}" + (f", KV pool limited to {os.environ['KV_PAGES']} pages" if os.environ.get("KV_PAGES") else "") + (f", prefill chunks {chunk}" if mode == "continuous" else ", maxBatchSize 64 / maxLatency 50 ms"),
                seconds=round(elapsed, 2), requests=len(lat), output_tokens_per_s=round(done[0] / elapsed, 1),
                request_latency_s=dict(p50=q(lat, .5), p99=q(lat, .99)), ttft_s=dict(p50=q(ttft, .5), p99=q(ttft, .99)),
                scheduler=dict(model._cb.stats) if model._cb is not None else None,
