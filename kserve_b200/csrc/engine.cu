@@ -230,11 +230,12 @@ namespace b200 {
 constexpr int kMaxRows = 64;   // rows of one decode / LM-head pass (swap-AB GEMM block_n, peer-exchange rows)
 static int pick_block_n(int B) { return B <= 16 ? 16 : (B <= 32 ? 32 : 64); }
 
-// peer-memory all-reduce + residual + RMSNorm of the decode step: one-shot LL below 4 ranks, two-shot (reduce-scatter +
-// all-gather, 4x less NVLink traffic at 8 ranks) from 4 ranks on; B200_AR_TWO_SHOT_MIN_TP moves the switch (A/B runs)
+// peer-memory all-reduce + residual + RMSNorm of the decode step: one-shot LL up to 4 ranks, two-shot (reduce-scatter +
+// all-gather, 4x less NVLink traffic) at 8 ranks.  Measured r02: TP = 8 decode 2.64 -> 2.20 ms/step with two-shot; at TP = 4
+// two-shot is slower (2.57 vs 2.46 ms/step: one more NVLink hop for only 2x less traffic).  B200_AR_TWO_SHOT_MIN_TP moves the switch.
 typedef void (*ArKernel)(const P2P, bf16*, const bf16*, bf16*, float, const float*, int, long long, long long, const bf16*, int, int);
 static ArKernel ar_kernel(const b200_engine* e) {
-  static const int min_tp = getenv("B200_AR_TWO_SHOT_MIN_TP") ? atoi(getenv("B200_AR_TWO_SHOT_MIN_TP")) : 4;
+  static const int min_tp = getenv("B200_AR_TWO_SHOT_MIN_TP") ? atoi(getenv("B200_AR_TWO_SHOT_MIN_TP")) : 8;
   return (e->cfg.tp_size >= min_tp && (e->H / e->cfg.tp_size) % 8 == 0) ? allreduce2_norm_kernel : allreduce_norm_kernel;
 }
 
