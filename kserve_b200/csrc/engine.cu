@@ -342,6 +342,7 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
     bf16* vc = e->vcache + (long long)l * e->layer_stride;
     // ---- QKV projection
     RopeKvParams rp{};
+    bool fused_rope = false;
     rp.ld = e->qkv_cols;
     if (decode) {
       // uniform split-K with fp32 partials: the consumer kernel (attention prologue / rmsnorm) reduces them in
@@ -356,17 +357,24 @@ static int forward_layers(b200_engine* e, int T_all, int B_all, int max_len, boo
       rp.q_out = e->qdec; rp.ldq = e->nh * kHeadDim;
       rp.tok_seq = e->d_seq_slot; rp.tok_pos = e->d_dec_pos;
     } else {
-      GemmArgs a{e->xn + r0 * H, e->cap_T - (int)r0, w.wqkv, e->qkv_cols, T, e->qkv_cols, H, EPI_STORE, 256, 1,
-                 e->qkv + r0 * e->qkv_cols, nullptr, e->qkv_cols, 0, 0, false};
-      if ((rc = launch_gemm(e, a, gsms, s))) return rc;
       rp.qkv = e->qkv + r0 * e->qkv_cols;
       rp.q_out = e->qkv + r0 * e->qkv_cols; rp.ldq = e->qkv_cols;  // in place
       rp.tok_seq = e->d_tok_seq + r0; rp.tok_pos = e->d_tok_pos + r0;
+      rp.kcache = kc; rp.vcache = vc; rp.page_table = e->d_page_table; rp.max_pages = e->max_pages;
+      rp.cos_tab = e->cos_tab; rp.sin_tab = e->sin_tab; rp.nh = e->nh; rp.nkv = e->nkv;
+      // RoPE + KV append in the QKV GEMM's epilogue (the separate rope_kv_kernel pass re-read and re-wrote 750 MB per layer
+      // at 0.37 of the HBM peak); B200_NO_ROPE_FUSION=1 / B200_NO_2CTA=1 restore the two-kernel path
+      static const bool rope_fused = getenv("B200_NO_ROPE_FUSION") == nullptr && getenv("B200_NO_2CTA") == nullptr;
+      fused_rope = rope_fused;
+      GemmArgs a{e->xn + r0 * H, e->cap_T - (int)r0, w.wqkv, e->qkv_cols, T, e->qkv_cols, H, fused_rope ? EPI_ROPE_KV : EPI_STORE, 256, 1,
+                 e->qkv + r0 * e->qkv_cols, nullptr, e->qkv_cols, 0, 0, false};
+      a.rope = &rp;
+      if ((rc = launch_gemm(e, a, gsms, s))) return rc;
     }
     rp.kcache = kc; rp.vcache = vc; rp.page_table = e->d_page_table; rp.max_pages = e->max_pages;
     rp.cos_tab = e->cos_tab; rp.sin_tab = e->sin_tab; rp.nh = e->nh; rp.nkv = e->nkv;
     e->launches++;
-    if (!decode) {   // decode: RoPE + KV append are fused into attn_decode_kernel
+    if (!decode && !fused_rope) {   // decode: RoPE + KV append are fused into attn_decode_kernel
       rp.T = T; rp.tokens_per_cta = 1;   // (4 tokens per CTA measured SLOWER: 446 vs 312 us per launch, r02 ncu)
       B200_CUDA_OK(launch_k(rope_kv_kernel, dim3((T + rp.tokens_per_cta - 1) / rp.tokens_per_cta), dim3(512), 0, s, rp));
       e->launches++;

@@ -202,6 +202,79 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * k2BlockN;
       constexpr int CH = 32;
+      if constexpr (EPI == EPI_ROPE_KV) {
+        // the tile's 256 columns are two whole heads; this thread owns token row m
+        const bool row_ok = m < M_rt;
+        int pos = 0;
+        long long page_row = 0;     // (page * nkv) * 64 + slot: row of kv head 0 of this token inside the [.. ][64][128] cache
+        if (row_ok) {
+          pos = p.rope_tok_pos[m + roff];
+          const int page = p.rope_page_table[(long long)p.rope_tok_seq[m + roff] * p.rope_max_pages + (pos >> 6)];
+          page_row = (long long)page * p.rope_nkv * 64 + (pos & 63);
+        }
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int col0 = n0 + hh * 128;
+          if (col0 >= p.N) break;
+          const int head = col0 >> 7;
+          if (head >= p.rope_nh + p.rope_nkv) {           // ---- V head: copy to the cache
+            const int kvh = head - p.rope_nh - p.rope_nkv;
+            bf16* vrow = p.rope_vcache + (page_row + (long long)kvh * 64) * 128;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += CH) {
+              uint32_t r[CH];
+              tmem_ld_32x32(taddr + hh * 128 + c0, r);
+              tmem_ld_wait();
+              if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < CH; j += 8) {
+                  uint4 o;
+                  o.x = pack_bf16x2(__uint_as_float(r[j + 0]), __uint_as_float(r[j + 1]));
+                  o.y = pack_bf16x2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                  o.z = pack_bf16x2(__uint_as_float(r[j + 4]), __uint_as_float(r[j + 5]));
+                  o.w = pack_bf16x2(__uint_as_float(r[j + 6]), __uint_as_float(r[j + 7]));
+                  *reinterpret_cast<uint4*>(vrow + c0 + j) = o;
+                }
+              }
+            }
+            continue;
+          }
+          // ---- q or k head: rotate-half RoPE on the pairs (d, d + 64)
+          bf16* dst = head < p.rope_nh ? reinterpret_cast<bf16*>(p.out) + (long long)(m + roff) * p.ldo + col0
+                                       : p.rope_kcache + (page_row + (long long)(head - p.rope_nh) * 64) * 128;
+#pragma unroll 1
+          for (int c = 0; c < 64; c += CH) {
+            uint32_t r1[CH], r2[CH];
+            tmem_ld_32x32(taddr + hh * 128 + c, r1);
+            tmem_ld_32x32(taddr + hh * 128 + 64 + c, r2);
+            tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < CH; j += 8) {
+                const uint4 cu = *reinterpret_cast<const uint4*>(p.rope_cos + (long long)pos * 64 + c + j);
+                const uint4 su = *reinterpret_cast<const uint4*>(p.rope_sin + (long long)pos * 64 + c + j);
+                const uint32_t cw[4] = {cu.x, cu.y, cu.z, cu.w}, sw[4] = {su.x, su.y, su.z, su.w};
+                float o1[8], o2[8];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 cs = unpack_bf16x2(cw[t]), sn = unpack_bf16x2(sw[t]);
+                  const float a0 = bf16_round(__uint_as_float(r1[j + 2 * t])), a1 = bf16_round(__uint_as_float(r1[j + 2 * t + 1]));
+                  const float b0 = bf16_round(__uint_as_float(r2[j + 2 * t])), b1 = bf16_round(__uint_as_float(r2[j + 2 * t + 1]));
+                  o1[2 * t] = bf16_round(a0 * cs.x) + bf16_round(-b0 * sn.x);
+                  o1[2 * t + 1] = bf16_round(a1 * cs.y) + bf16_round(-b1 * sn.y);
+                  o2[2 * t] = bf16_round(b0 * cs.x) + bf16_round(a0 * sn.x);
+                  o2[2 * t + 1] = bf16_round(b1 * cs.y) + bf16_round(a1 * sn.y);
+                }
+                uint4 w1, w2;
+                w1.x = pack_bf16x2(o1[0], o1[1]); w1.y = pack_bf16x2(o1[2], o1[3]); w1.z = pack_bf16x2(o1[4], o1[5]); w1.w = pack_bf16x2(o1[6], o1[7]);
+                w2.x = pack_bf16x2(o2[0], o2[1]); w2.y = pack_bf16x2(o2[2], o2[3]); w2.z = pack_bf16x2(o2[4], o2[5]); w2.w = pack_bf16x2(o2[6], o2[7]);
+                *reinterpret_cast<uint4*>(dst + c + j) = w1;
+                *reinterpret_cast<uint4*>(dst + 64 + c + j) = w2;
+              }
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < k2BlockN; c0 += CH) {
         if (n0 + c0 >= p.N) break;
@@ -266,6 +339,7 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
       }
+      }   // EPI != EPI_ROPE_KV
       tcgen05_fence_before();
       mbar_arrive_leader(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -22,6 +22,8 @@ enum GemmEpi : int {
   EPI_T_STORE = 3,    // out[n][m] = bf16(acc)                                    (swap-AB)
   EPI_T_SWIGLU = 4,   // A rows interleaved {16 gate,16 up}: out[n][m/2] = ...    (swap-AB)
   EPI_T_PARTIAL = 5,  // ws[split][n][m] = acc (fp32)                             (swap-AB split-K)
+  EPI_ROPE_KV = 6,    // prefill QKV projection (2-CTA kernel only): columns are [q heads | k heads | v heads] x 128;
+                      // q <- RoPE(q) in place in `out`, RoPE(k) and v go straight to the paged KV cache
 };
 
 struct GemmParams {
@@ -55,6 +57,12 @@ struct GemmParams {
   // empty groups are skipped: their weights are never streamed) and whose outputs start at out + g * group_out_stride
   int group_m_tiles;
   long long group_out_stride;
+  // EPI_ROPE_KV: one output row = one prompt token (HF bf16 rounding points of apply_rotary_pos_emb; bit-identical to rope_kv_kernel)
+  const int32_t* rope_tok_seq; const int32_t* rope_tok_pos;   // [M] page-table row / position of each token
+  const int32_t* rope_page_table; int rope_max_pages;
+  bf16* rope_kcache; bf16* rope_vcache;                      // this layer's [page][kv_head][64][128]
+  const bf16* rope_cos; const bf16* rope_sin;                // [max_pos][64]
+  int rope_nh, rope_nkv;
   int group_pairs;         // 2-CTA prefill kernel: m-pairs per raster group (0 = default 8)
   int stream_out;          // 2-CTA prefill kernel: cache-streaming output stores
   int sched;

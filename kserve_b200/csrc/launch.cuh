@@ -168,6 +168,7 @@ struct GemmArgs {
   int groups = 0;                   // > 0: grouped swap-AB problem (see GemmParams::group_m_tiles); A rows = groups * M,
   long long group_out_stride = 0;   // n_rt / row_off are arrays of `groups` entries
   PfCtx* pf = nullptr;              // weight-stream prefetcher context of the step being enqueued (decode only)
+  const RopeKvParams* rope = nullptr;   // EPI_ROPE_KV: where RoPE(k) / v go and the tables (q is rotated in place in `out`)
 };
 
 // GEMMs whose weight operand depends on nothing the step computes (decode swap-AB, no device-side extents)
@@ -240,7 +241,20 @@ inline int launch_gemm(TmapCache& cache, const GemmArgs& a, int num_sms, cudaStr
     a.pf->count++;
   }
   B200_REQUIRE(p.splits == 1 || a.epi == EPI_T_PARTIAL, "split-K only with the fp32 partial epilogue");
+  p.rope_tok_seq = nullptr; p.rope_tok_pos = nullptr; p.rope_page_table = nullptr; p.rope_max_pages = 0;
+  p.rope_kcache = nullptr; p.rope_vcache = nullptr; p.rope_cos = nullptr; p.rope_sin = nullptr; p.rope_nh = 0; p.rope_nkv = 0;
   const bool use_2cta = getenv("B200_NO_2CTA") == nullptr;
+  if (a.epi == EPI_ROPE_KV) {
+    B200_REQUIRE(use_2cta && a.block_n == 256 && a.rope && a.N == (a.rope->nh + 2 * a.rope->nkv) * kHeadDim,
+                 "EPI_ROPE_KV is the 2-CTA prefill QKV projection");
+    p.rope_tok_seq = a.rope->tok_seq; p.rope_tok_pos = a.rope->tok_pos; p.rope_page_table = a.rope->page_table;
+    p.rope_max_pages = a.rope->max_pages; p.rope_kcache = a.rope->kcache; p.rope_vcache = a.rope->vcache;
+    p.rope_cos = a.rope->cos_tab; p.rope_sin = a.rope->sin_tab; p.rope_nh = a.rope->nh; p.rope_nkv = a.rope->nkv;
+    const CUtensorMap* tb2;
+    int rc2 = cache.get(a.B, a.b_rows, a.K, 128, &tb2);
+    if (rc2) return rc2;
+    return launch_gemm_2cta_inst<EPI_ROPE_KV>(ta, tb2, p, num_sms, s);
+  }
   if (use_2cta && a.block_n == 256 && a.epi <= EPI_SWIGLU) {
     const CUtensorMap* tb2;
     int rc2 = cache.get(a.B, a.b_rows, a.K, 128, &tb2);   // each CTA of the pair stages half of the 256 weight rows
