@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libkserve_b200.so")
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(HERE, "lib", "libkserve_b200.so")   # (override: A/B of two builds on one box)
 
 
 class ModelConfig(C.Structure):
