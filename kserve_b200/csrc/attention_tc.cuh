@@ -193,18 +193,19 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       mbar_wait(&s_full[buf], (j >> 1) & 1);
       tcgen05_fence_after();
       const bool diag = (j >= ntiles - 2);
-      // one TMEM pass: the 64 scores of this row stay in registers
+      // one TMEM pass: the 64 raw scores of this row stay in registers; the softmax scale is folded into the exponent
+      // (max on the raw scores — the scale is positive — then p = exp2(fma(s, scale, -m)): one FFMA per element)
       float sv[64];
       {
         uint32_t sr[32];
         tmem_ld_32x32(tmem_s + lane_base + buf * 64, sr);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(sr[i]) * p.scale_log2;
+        for (int i = 0; i < 32; ++i) sv[i] = __uint_as_float(sr[i]);
         tmem_ld_32x32(tmem_s + lane_base + buf * 64 + 32, sr);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sv[32 + i] = __uint_as_float(sr[i]) * p.scale_log2;
+        for (int i = 0; i < 32; ++i) sv[32 + i] = __uint_as_float(sr[i]);
       }
       tcgen05_fence_before();
       mbar_arrive(&s_empty[buf]);      // S[buf] is in registers: the next QK^T may overwrite it
@@ -219,7 +220,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 #pragma unroll
         for (int i = 0; i < 64; ++i) mx = fmaxf(mx, sv[i]);
       }
-      const float m_new = fmaxf(m_ref, mx);      // finite from tile 0 on: key 0 is visible to every row
+      const float m_new = fmaxf(m_ref, mx * p.scale_log2);      // finite from tile 0 on: key 0 is visible to every row
       // lazy rescale: keep the reference max unless it would let exp2 grow past 2^8
       const bool grow = (m_ref == -INFINITY) || (m_new > m_ref + 8.0f);
       const float corr = grow ? ((m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new)) : 1.0f;
@@ -248,7 +249,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         float pv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          pv[i] = exp2f(sv[8 * g8 + i] - m_ref);
+          pv[i] = exp2f(fmaf(sv[8 * g8 + i], p.scale_log2, -m_ref));
           l_run += pv[i];
         }
         uint4 o;
