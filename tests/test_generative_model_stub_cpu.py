@@ -287,3 +287,21 @@ def test_logit_bias_reproduces_the_reference_error(served):
     r = client.post("/openai/v1/completions", json={"model": "stub", "prompt": "abc", "max_tokens": 3, "logit_bias": {}})
     assert r.status_code == 500 and "`sequence_bias` has to be a non-empty dictionary" in r.text
     assert len(m._engine.calls) == n0          # nothing reached the engine, as nothing is generated in the reference
+
+
+def test_predict_rejects_bad_user_parameters_with_400(served):
+    """user errors of the V1 / V2 predict legs are 400s, not 500s from inside the engine."""
+    client, m, tok = served
+    r = client.post("/v1/models/stub:predict", json={"instances": [[5, 6, 7]], "parameters": {"max_tokens": 0}})
+    assert r.status_code == 400 and "max_tokens" in r.text
+    r = client.post("/v1/models/stub:predict", json={"instances": [[5, 6, 7]], "parameters": {"max_tokens": "many"}})
+    assert r.status_code == 400
+    r = client.post("/v1/models/stub:predict", json={"instances": [[5] * 10], "parameters": {"max_tokens": 510}})
+    assert r.status_code == 400 and "maximum context length" in r.text
+    ids = {"name": "input_ids", "shape": [2, 3], "datatype": "INT64", "data": [1, 2, 3, 4, 5, 6]}
+    bad_mask = {"name": "attention_mask", "shape": [2, 2], "datatype": "INT64", "data": [1, 1, 1, 1]}
+    r = client.post("/v2/models/stub/infer", json={"inputs": [ids, bad_mask]})
+    assert r.status_code == 400 and "attention_mask shape" in r.text
+    holes = {"name": "attention_mask", "shape": [2, 3], "datatype": "INT64", "data": [1, 0, 1, 0, 1, 1]}
+    r = client.post("/v2/models/stub/infer", json={"inputs": [ids, holes]})
+    assert r.status_code == 400 and "left padding" in r.text
