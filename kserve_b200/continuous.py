@@ -33,7 +33,8 @@ class ReplicatedEngine:
     follower ranks (tp.leader_call -> tp.follower_loop), which execute it on their engine in the same order.  All
     host-side decisions of the engine (slots, pages, prefix hits, chunk boundaries) are deterministic, so the ranks stay
     in lockstep and their poll / read results are identical."""
-    _REPLICATED = ("cb_begin", "cb_config", "cb_admit", "cb_step", "cb_poll", "cb_read", "cb_release", "cb_end")
+    _REPLICATED = ("cb_begin", "cb_config", "cb_admit", "cb_step", "cb_poll", "cb_read", "cb_release", "cb_swap_out", "cb_swap_in",
+                   "cb_end")
 
     def __init__(self, engine: B200Engine):
         self._e = engine

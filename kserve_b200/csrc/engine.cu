@@ -1224,7 +1224,7 @@ static int copy_cols(bf16* dst, const bf16* src, long long rows, long long src_c
 extern "C" {
 
 const char* b200_last_error(void) { return g_last_error.c_str(); }
-const char* b200_version(void) { return "kserve_b200 0.1 (sm_100a)"; }
+const char* b200_version(void) { return "kserve_b200 0.2 (sm_100a)"; }
 
 int b200_nccl_unique_id(void* out128) {
   Nccl& n = Nccl::get();
