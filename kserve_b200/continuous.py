@@ -261,6 +261,15 @@ class ContinuousBatcher:
             return True
         return False
 
+    def _drop_cancelled_swapped(self) -> None:
+        """a client that went away while its request was parked in the host tier: free the slots, never swap it back in"""
+        for r in [r for r in self._swapped if r.cancelled]:
+            self._swapped.remove(r)
+            for sl in r.slots:
+                self.engine.cb_release(sl)
+            self.free_slots += len(r.slots)
+            self.stats["cancelled"] += 1
+
     def _resume_swapped(self) -> None:
         """bring preempted requests back (oldest first) while the pool has room"""
         while self._swapped:
@@ -348,6 +357,8 @@ class ContinuousBatcher:
                         self._cv.wait()
                     if self._stop:
                         break
+                if self._swapped:
+                    self._drop_cancelled_swapped()
                 if self._swapped and not self._pool_blocked_resume:
                     before = len(self._swapped)
                     self._resume_swapped()

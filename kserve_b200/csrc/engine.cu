@@ -1078,6 +1078,7 @@ static int cb_admit(b200_engine* e, int n, const int64_t* const* rows, const int
     if (!e->cb_used[sl]) slots.push_back(sl);
   // ---- pages: plan every prompt first; on exhaustion everything taken so far is handed back
   std::vector<b200_engine::CbPending> plans(n);
+  long long stat_prompt = 0, stat_hit = 0;      // counted only when the whole admit goes through
   auto rollback = [&](int upto) {
     for (int i = 0; i < upto; ++i) {
       for (int pg : e->cb_slot_pages[slots[i]]) cb_unref_page(e, pg);
@@ -1128,7 +1129,7 @@ static int cb_admit(b200_engine* e, int n, const int64_t* const* rows, const int
       }
       pages.push_back(pg);
     }
-    e->cb_stat[0] += lens[i]; e->cb_stat[1] += pd.done;
+    stat_prompt += lens[i]; stat_hit += pd.done;
   }
   for (int i = 0; i < n; ++i) {
     const std::vector<int>& pages = e->cb_slot_pages[slots[i]];
@@ -1192,6 +1193,7 @@ static int cb_admit(b200_engine* e, int n, const int64_t* const* rows, const int
     B200_CUDA_OK(cudaMemset(e->d_seen, 0, (size_t)e->cfg.max_batch * e->seen_words * 4));
   }
   B200_CUDA_OK(cudaStreamSynchronize(s));   // h_cb / sc are reused
+  e->cb_stat[0] += stat_prompt; e->cb_stat[1] += stat_hit;
   for (int i = 0; i < n; ++i) {
     e->cb_used[slots[i]] = 1;
     slots_out[i] = slots[i];
@@ -1899,16 +1901,16 @@ int b200_cb_config(b200_engine_t* e, int32_t prefill_chunk_tokens, int32_t prefi
   return 0;
 }
 
-int b200_cb_stats(b200_engine_t* e, int64_t* out8) {   // (10 entries)
-  B200_REQUIRE(e && out8, "null argument");
+int b200_cb_stats(b200_engine_t* e, int64_t* out10) {
+  B200_REQUIRE(e && out10, "null argument");
   int64_t evictable = 0;
   for (auto& kv : e->cb_prefix)
     if (e->cb_page_ref[kv.second.p0] == 1 && e->cb_page_ref[kv.second.p1] == 1) evictable += 2;
-  out8[0] = e->cb_stat[0]; out8[1] = e->cb_stat[1]; out8[2] = e->cb_stat[2]; out8[3] = e->cb_stat[3]; out8[4] = e->cb_stat[4];
-  out8[5] = (int64_t)e->cb_free_pages.size() + evictable;     // pages an admit could obtain right now
-  out8[6] = (int64_t)e->cb_prefix.size();
-  out8[7] = (int64_t)e->cb_pending.size();
-  out8[8] = e->cb_stat[5]; out8[9] = e->cb_stat[6];      // sequences swapped out to / back in from host DRAM
+  out10[0] = e->cb_stat[0]; out10[1] = e->cb_stat[1]; out10[2] = e->cb_stat[2]; out10[3] = e->cb_stat[3]; out10[4] = e->cb_stat[4];
+  out10[5] = (int64_t)e->cb_free_pages.size() + evictable;     // pages an admit could obtain right now
+  out10[6] = (int64_t)e->cb_prefix.size();
+  out10[7] = (int64_t)e->cb_pending.size();
+  out10[8] = e->cb_stat[5]; out10[9] = e->cb_stat[6];      // sequences swapped out to / back in from host DRAM
   return 0;
 }
 

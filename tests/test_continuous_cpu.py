@@ -332,3 +332,36 @@ def test_kv_offload_preempts_the_youngest_and_resumes_it():
     kinds = [c[0] for c in eng.calls]
     assert "swap_out" in kinds and "swap_in" in kinds and kinds.index("swap_out") < kinds.index("swap_in")
     assert cb.stats["preempted"] >= 1 and cb.stats["resumed"] == cb.stats["preempted"]
+
+
+def test_request_cancelled_while_swapped_out_is_released_not_resumed():
+    """a client that disconnects while its request is parked in the host-DRAM tier frees its slot at the next scheduler
+    pass; the request is never swapped back in"""
+    scripts = {(1,) * 6: list(range(1000, 1400)), (2,) * 6: list(range(2000, 2400)), (3,) * 6: list(range(3000, 3400))}
+    eng = ScriptedEngine(4, scripts, pages=12, step_delay=0.002)
+    cb = ContinuousBatcher(eng, steps_per_poll=1, kv_offload=True)
+
+    async def main():
+        pad = lambda p: torch.tensor([p])
+        a = asyncio.create_task(cb.submit([[1] * 6], pad([1] * 6), 120))
+        await asyncio.sleep(0.02)
+        b = asyncio.create_task(cb.submit([[2] * 6], pad([2] * 6), 300))
+        await asyncio.sleep(0.02)
+        c = asyncio.create_task(cb.submit([[3] * 6], pad([3] * 6), 120))      # preempts b (the youngest running request)
+        for _ in range(200):
+            await asyncio.sleep(0.005)
+            if any(k[0] == "swap_out" for k in eng.calls):
+                break
+        b.cancel()
+        ra, rc = await asyncio.gather(a, c)
+        try:
+            await b
+        except asyncio.CancelledError:
+            pass
+        return ra, rc
+    ra, rc = _run(cb, main())
+    assert ra.output_ids[0, 6:].tolist() == list(range(1000, 1120))
+    assert rc.output_ids[0, 6:].tolist() == list(range(3000, 3120))
+    kinds = [c[0] for c in eng.calls]
+    assert "swap_out" in kinds and "swap_in" not in kinds
+    assert cb.stats["cancelled"] == 1 and cb.free_slots == 4 and not eng.slots

@@ -153,3 +153,56 @@ def test_follower_replays_leader_calls_and_survives_request_errors():
     mp.spawn(_cmd_worker, args=(2, 29612, ret), nprocs=2, join=True)
     assert ret["calls"] == [("generate", [[1, 2, 3]], 4), ("generate", [[9, 9]], 2)]
     assert ret["rc"] == 0 and ret["stopped"] is True
+
+
+def _cb_worker(rank, world, port, ret):
+    """rank 0 runs the continuous-batching scheduler over a ReplicatedEngine, rank 1 replays its cb_* calls"""
+    import asyncio
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kserve_b200.continuous import ContinuousBatcher, ReplicatedEngine
+    from kserve_b200.tp import follower_loop, leader_call
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_continuous_cpu import ScriptedEngine
+    scripts = {(1, 2): [5, 6, 7, 8], (3,): [9, 2, 4], (4, 4, 4): [11, 12]}
+    eng = ScriptedEngine(2, scripts, eos=(2,))
+    eng.tp_size = world
+    if rank == 0:
+        cb = ContinuousBatcher(eng, pad_token_id=0, eos_token_ids=(2,), steps_per_poll=1, prefill_chunk_tokens=128, prefix_cache=True)
+        assert isinstance(cb.engine, ReplicatedEngine)
+
+        async def main():
+            t = lambda p: torch.tensor([p])
+            return await asyncio.gather(cb.submit([[1, 2]], t([1, 2]), 4), cb.submit([[3]], t([3]), 3),
+                                        cb.submit([[4, 4, 4]], t([4, 4, 4]), 2))       # three requests over two slots
+        cb.start()
+        try:
+            res = asyncio.run(main())
+        finally:
+            cb.stop()
+        leader_call("stop", (), {})
+        ret["leader_out"] = [r.output_ids.tolist() for r in res]
+        ret["leader_calls"] = [c for c in eng.calls if c[0] in ("admit", "step", "swap_out", "swap_in")]
+        ret["leader_cfg"] = eng.configured
+    else:
+        m = _FakeModel()
+        m._engine = eng
+        ret["rc"] = follower_loop(m)
+        ret["follower_calls"] = [c for c in eng.calls if c[0] in ("admit", "step", "swap_out", "swap_in")]
+        ret["follower_cfg"] = eng.configured
+        ret["follower_slots_left"] = len(eng.slots)
+    dist.destroy_process_group()
+
+
+def test_continuous_batcher_calls_are_replicated_to_the_follower_rank():
+    """tensor parallel + continuous batching: every engine call the rank-0 scheduler makes (config, admits, steps, polls,
+    reads, releases) reaches the follower in the same order, so both ranks hold the same slots / pages at every step"""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cb_worker, args=(2, 29613, ret), nprocs=2, join=True)
+    assert ret["leader_out"] == [[[1, 2, 5, 6, 7, 8]], [[3, 9, 2]], [[4, 4, 4, 11, 12]]]
+    assert ret["rc"] == 0
+    assert ret["leader_cfg"] == ret["follower_cfg"] == (128, True)
+    assert ret["leader_calls"] == ret["follower_calls"] and any(c[0] == "admit" for c in ret["follower_calls"])
+    assert ret["follower_slots_left"] == 0          # every release was replayed too
