@@ -235,6 +235,12 @@ def main():
     gen_case("tiny_kv8_peaked", "tiny_kv8_peaked", 5, ids_prompt(4, 70, 4000, 4321), 16, pad_token_id=4098)
     # (j) rope_scaling "llama3" (Llama-3.1 checkpoints), prompt longer than original_max_position_embeddings
     gen_case("tiny_g2_rope3", "tiny_g2_rope3", 0, ids_prompt(2, 300, 1000, 55), 8, pad_token_id=1030)
+    # (k) boundary lengths: rows of 1 / 63 / 64 / 65 / 127 / 128 prompt tokens (one KV page = 64 tokens, one attention query
+    # tile = 128), left padded with the pad id, decoded until prompt + generated = 192 = exactly three full pages — the
+    # GPU test runs it on an engine whose max_seq_len is that 192 (the "maximum size" case)
+    rows = ids_prompt(6, 128, 2048, 4242)
+    rows = [[0] * (128 - n) + r[128 - n:] for r, n in zip(rows, (1, 63, 64, 65, 127, 128))]
+    gen_case("tiny_g4_peaked_edges", "tiny_g4_peaked", 1, rows, 64, pad_token_id=0)
     if args.big:
         gen_case("llama3_8b_2l_ids", "llama3_8b_2l", 0, ids_prompt(2, 96, 128000, 1234), 8,
                  pad_token_id=128255, full_logits=False)

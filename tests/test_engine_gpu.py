@@ -100,10 +100,7 @@ def test_free_running_ids(engines, name):
     assert torch.equal(r.output_ids, r2.output_ids)
 
 
-@pytest.mark.parametrize("name", PEAKED)
-def test_peaked_logits_greedy_ids_exact(engines, name):
-    c = load_case(name)
-    eng = engines(c)
+def _check_peaked(eng, c, name):
     pad = c["meta"]["pad_token_id"]
     r = eng.generate(c["input_ids"], c["mask"], max_new_tokens=c["T"], pad_token_id=pad, forced_tokens=c["gen"], want_logits=True)
     got = r.logits.float().permute(1, 0, 2)
@@ -125,6 +122,28 @@ def test_peaked_logits_greedy_ids_exact(engines, name):
         for b in range(exact.shape[0]):
             upto = int(first_soft[b]) if not bool(decisive[b].all()) else exact.shape[1]
             assert bool(exact[b, :upto].all())
+
+
+@pytest.mark.parametrize("name", PEAKED)
+def test_peaked_logits_greedy_ids_exact(engines, name):
+    c = load_case(name)
+    _check_peaked(engines(c), c, name)
+
+
+def test_boundary_lengths_on_an_engine_sized_exactly_for_them():
+    """rows of 1 / 63 / 64 / 65 / 127 / 128 prompt tokens (KV page = 64 tokens, attention query tile = 128), left padded,
+    decoded until prompt + generated = 192 tokens = three full pages, on an engine whose max_seq_len IS 192 and whose
+    max_batch is the batch: every page and tile boundary and the maximum size in one oracle fixture"""
+    c = load_case("tiny_g4_peaked_edges")
+    m = c["meta"]
+    assert c["S"] + c["T"] == 192 and c["mask"].sum(1).tolist() == [1, 63, 64, 65, 127, 128]
+    eng = make_engine(m["cfg"], m["seed"], vocab_rows=m["vocab_rows"], max_batch=c["input_ids"].shape[0], max_seq_len=c["S"] + c["T"])
+    try:
+        _check_peaked(eng, c, "tiny_g4_peaked_edges")
+        with pytest.raises(Exception):      # one token more than the engine was sized for is refused, not truncated
+            eng.generate(c["input_ids"], c["mask"], max_new_tokens=c["T"] + 1, pad_token_id=m["pad_token_id"])
+    finally:
+        eng.close()
 
 
 HEADLINE = ["llama3_8b_2l_b4", "llama3_8b_2l_peaked_b4", "llama3_8b_2l_peaked_ragged"]

@@ -15,7 +15,7 @@ from oracle import weights as W
 from oracle.hf_oracle import OracleGenerativeModel, build_llama
 
 
-@pytest.mark.parametrize("name", ["tiny_g2_ids", "tiny_g2_stop", "tiny_g2_padinfer"])
+@pytest.mark.parametrize("name", ["tiny_g2_ids", "tiny_g2_stop", "tiny_g2_padinfer", "tiny_g4_peaked_edges"])
 def test_oracle_reproduces_fixture(name):
     c = load_case(name)
     m = c["meta"]
