@@ -194,6 +194,12 @@ class B200GenerativeModel(OpenAIChatAdapterModel, Model):
         if gpath and os.path.exists(gpath):
             with open(gpath) as f:
                 self.generation_defaults = {**json.load(f), **self.generation_defaults}
+        ck_dtype = cfg.get("torch_dtype") or cfg.get("dtype")
+        if ck_dtype not in (None, "bfloat16"):
+            # the reference's `--dtype auto` would compute in the checkpoint's type (__main__.py:249-259); this runtime's
+            # only arithmetic type is bfloat16 (fp32 accumulation), so other checkpoints are converted at load
+            logger.warning("checkpoint dtype %s: weights are converted to bfloat16, the only compute type of the B200 runtime",
+                           ck_dtype)
         eos = cfg.get("eos_token_id")
         self.eos_token_ids = [] if eos is None else ([int(e) for e in eos] if isinstance(eos, list) else [int(eos)])
         try:
