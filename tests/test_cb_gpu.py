@@ -374,3 +374,35 @@ def test_scheduler_preempts_to_host_when_the_pool_is_exhausted():
         assert cb.stats.get("preempted", 0) >= 1 and cb.stats.get("resumed", 0) == cb.stats["preempted"]
     finally:
         e.close()
+
+
+def test_boundary_lengths_through_the_continuous_batcher_match_the_oracle():
+    """the boundary-length oracle fixture (rows of 1 / 63 / 64 / 65 / 127 / 128 prompt tokens, 64 generated each) through
+    b200_cb_*: two rows start, four join the running batch, prompts go through 128-token chunks with the prefix cache on,
+    the KV pool holds exactly the 15 pages these six sequences need and max_seq_len is the longest row's 192 tokens.
+    Every step of the fixture is decisive, so each sequence's ids must equal the oracle's token for token."""
+    c = load_case("tiny_g4_peaked_edges")
+    m = c["meta"]
+    T, B = c["T"], c["input_ids"].shape[0]
+    rows = [c["input_ids"][b][c["mask"][b].bool()].tolist() for b in range(B)]
+    assert [len(r) for r in rows] == [1, 63, 64, 65, 127, 128] and T == 64
+    pages = sum(-(-(len(r) + T) // 64) for r in rows)
+    assert pages == 15
+    e = make_engine(m["cfg"], m["seed"], vocab_rows=m["vocab_rows"], max_batch=B, max_seq_len=192, num_kv_pages=pages)
+    try:
+        e.cb_begin(m["pad_token_id"], [])
+        e.cb_config(128, True)
+        slots = e.cb_admit(rows[:2], [T, T])
+        e.cb_step(5)
+        slots += e.cb_admit(rows[2:], [T] * 4)                # join a running batch; the pool is now fully committed
+        assert e.cb_stats()["available_pages"] == 0
+        n_gen, fin, stop = _run_until_done(e, slots)
+        for b, s in enumerate(slots):
+            assert n_gen[s] == T and not stop[s]
+            assert e.cb_read(s, 0, T) == c["gen"][b].tolist(), f"row {b} ({len(rows[b])} prompt tokens)"
+        for s in slots:
+            e.cb_release(s)
+        assert e.cb_stats()["available_pages"] == pages      # nothing leaked (the cached 128-token block is evictable)
+    finally:
+        e.cb_end()
+        e.close()
